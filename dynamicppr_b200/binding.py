@@ -1,0 +1,255 @@
+"""ctypes binding of include/dppr.h (one-to-one; no logic lives here)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+OPTIMIZED, FAST_FRONTIER, EAGER, VANILLA = 0, 1, 2, 3
+ENGINE_PERSISTENT, ENGINE_STEPWISE = 0, 1
+
+# every symbol include/dppr.h declares (tests/test_abi.py checks the library exports all of them)
+ABI_SYMBOLS = [
+    "dppr_version", "dppr_last_error", "dppr_create", "dppr_destroy", "dppr_init_window",
+    "dppr_init_window_pairs", "dppr_solve_initial", "dppr_apply_batch", "dppr_apply_batch_pairs",
+    "dppr_apply_batch_device_pairs", "dppr_refresh", "dppr_slide", "dppr_slide_pairs",
+    "dppr_slide_device_pairs", "dppr_sync", "dppr_get_batch_stats", "dppr_batches_done",
+    "dppr_get_estimates", "dppr_get_residuals", "dppr_copy_estimates_device", "dppr_export_window_csr",
+    "dppr_window_csr_entries", "dppr_set_state", "dppr_repair_only", "dppr_test_sort_pairs",
+    "dppr_test_exclusive_scan",
+]
+
+
+class DpprError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"dppr error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("vertex_count", C.c_int32), ("directed", C.c_int32), ("window_edges", C.c_int64),
+        ("max_batch_edges", C.c_int64), ("alpha", C.c_double), ("epsilon", C.c_double),
+        ("variant", C.c_int32), ("device", C.c_int32), ("n_sources", C.c_int32),
+        ("sources", C.POINTER(C.c_int32)), ("engine_mode", C.c_int32), ("record_timing", C.c_int32),
+        ("pool_factor", C.c_double), ("frontier_capacity", C.c_int64), ("hub_degree", C.c_int32),
+        ("reserved0", C.c_int32),
+    ]
+
+
+class BatchStats(C.Structure):
+    _fields_ = [
+        ("batch_index", C.c_int64), ("edges", C.c_int64), ("batch_entries", C.c_int64),
+        ("touched_vertices", C.c_int64), ("iterations", C.c_int64), ("frontier_pops", C.c_int64),
+        ("traversed_edges", C.c_int64), ("hub_pops", C.c_int64), ("relocations", C.c_int64),
+        ("pool_used", C.c_int64), ("ms_upload", C.c_float), ("ms_window", C.c_float),
+        ("ms_repair", C.c_float), ("ms_push", C.c_float), ("error_flags", C.c_int32), ("reserved0", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved0"}
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "lib", "libdppr.so")
+
+
+def load_library():
+    """Load libdppr.so.  Raises loudly if it is missing: there is no fallback implementation."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: build the CUDA library first (`make lib` or `python -c 'import "
+            "__graft_entry__ as g; g.build()'`).  dynamicppr_b200 has no CPU fallback.")
+    L = C.CDLL(path)
+    i32p, f64p, vp = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_void_p
+    L.dppr_version.restype = C.c_int
+    L.dppr_last_error.argtypes = [vp]; L.dppr_last_error.restype = C.c_char_p
+    L.dppr_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.dppr_destroy.argtypes = [vp]; L.dppr_destroy.restype = None
+    L.dppr_init_window.argtypes = [vp, i32p, i32p, C.c_int64]
+    L.dppr_init_window_pairs.argtypes = [vp, i32p, C.c_int64]
+    L.dppr_solve_initial.argtypes = [vp]
+    for name in ("dppr_apply_batch", "dppr_slide"):
+        getattr(L, name).argtypes = [vp, i32p, i32p, C.c_int64]
+    for name in ("dppr_apply_batch_pairs", "dppr_slide_pairs"):
+        getattr(L, name).argtypes = [vp, i32p, C.c_int64]
+    for name in ("dppr_apply_batch_device_pairs", "dppr_slide_device_pairs"):
+        getattr(L, name).argtypes = [vp, vp, C.c_int64]
+    L.dppr_refresh.argtypes = [vp]
+    L.dppr_sync.argtypes = [vp]
+    L.dppr_get_batch_stats.argtypes = [vp, C.c_int64, C.POINTER(BatchStats)]
+    L.dppr_batches_done.argtypes = [vp]; L.dppr_batches_done.restype = C.c_int64
+    L.dppr_get_estimates.argtypes = [vp, C.c_int32, f64p]
+    L.dppr_get_residuals.argtypes = [vp, C.c_int32, f64p]
+    L.dppr_copy_estimates_device.argtypes = [vp, C.c_int32, vp]
+    L.dppr_export_window_csr.argtypes = [vp, i32p, i32p, i32p]
+    L.dppr_window_csr_entries.argtypes = [vp]; L.dppr_window_csr_entries.restype = C.c_int64
+    L.dppr_set_state.argtypes = [vp, C.c_int32, f64p, f64p]
+    L.dppr_repair_only.argtypes = [vp]
+    L.dppr_test_sort_pairs.argtypes = [C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int64, C.c_int32]
+    L.dppr_test_exclusive_scan.argtypes = [C.c_int32, C.POINTER(C.c_uint32), C.c_int64, C.POINTER(C.c_uint64)]
+    _LIB = L
+    return L
+
+
+def _i32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class DynamicPPR:
+    """One engine = one GPU.  Mirrors the C ABI call for call."""
+
+    def __init__(self, vertex_count, directed, window_edges, max_batch_edges, sources, epsilon=1e-9, variant=0,
+                 device=0, engine_mode=ENGINE_PERSISTENT, record_timing=True, alpha=0.15, pool_factor=0.0,
+                 frontier_capacity=0, hub_degree=0):
+        self.L = load_library()
+        self.V = int(vertex_count)
+        self._sources = np.ascontiguousarray(np.atleast_1d(sources), dtype=np.int32)
+        cfg = Config(vertex_count=self.V, directed=int(bool(directed)), window_edges=int(window_edges),
+                     max_batch_edges=int(max_batch_edges), alpha=alpha, epsilon=epsilon, variant=int(variant),
+                     device=int(device), n_sources=len(self._sources), sources=_i32(self._sources),
+                     engine_mode=int(engine_mode), record_timing=int(bool(record_timing)), pool_factor=pool_factor,
+                     frontier_capacity=int(frontier_capacity), hub_degree=int(hub_degree), reserved0=0)
+        self.h = C.c_void_p()
+        rc = self.L.dppr_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            msg = self.L.dppr_last_error(None).decode()
+            self.h = None
+            raise DpprError(rc, msg)
+        self.n_sources = len(self._sources)
+
+    # -- plumbing --------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise DpprError(rc, self.L.dppr_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dppr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @staticmethod
+    def _pairs(edges):
+        e = np.ascontiguousarray(edges, dtype=np.int32)
+        assert e.ndim == 2 and e.shape[1] == 2
+        return e
+
+    # -- the C ABI ---------------------------------------------------------------------------------
+    def init_window_pairs(self, edges):
+        e = self._pairs(edges)
+        self._check(self.L.dppr_init_window_pairs(self.h, _i32(e), len(e)))
+
+    def init_window(self, edge1, edge2):
+        a = np.ascontiguousarray(edge1, np.int32); b = np.ascontiguousarray(edge2, np.int32)
+        self._check(self.L.dppr_init_window(self.h, _i32(a), _i32(b), len(a)))
+
+    def solve_initial(self):
+        self._check(self.L.dppr_solve_initial(self.h))
+
+    def apply_batch_pairs(self, edges):
+        e = self._pairs(edges)
+        self._check(self.L.dppr_apply_batch_pairs(self.h, _i32(e), len(e)))
+
+    def apply_batch(self, edge1, edge2):
+        a = np.ascontiguousarray(edge1, np.int32); b = np.ascontiguousarray(edge2, np.int32)
+        self._check(self.L.dppr_apply_batch(self.h, _i32(a), _i32(b), len(a)))
+
+    def refresh(self):
+        self._check(self.L.dppr_refresh(self.h))
+
+    def repair_only(self):
+        self._check(self.L.dppr_repair_only(self.h))
+
+    def slide_pairs(self, edges):
+        e = self._pairs(edges)
+        self._check(self.L.dppr_slide_pairs(self.h, _i32(e), len(e)))
+
+    def slide(self, edge1, edge2):
+        a = np.ascontiguousarray(edge1, np.int32); b = np.ascontiguousarray(edge2, np.int32)
+        self._check(self.L.dppr_slide(self.h, _i32(a), _i32(b), len(a)))
+
+    def slide_device_pairs(self, device_ptr, B):
+        self._check(self.L.dppr_slide_device_pairs(self.h, C.c_void_p(int(device_ptr)), int(B)))
+
+    def apply_batch_device_pairs(self, device_ptr, B):
+        self._check(self.L.dppr_apply_batch_device_pairs(self.h, C.c_void_p(int(device_ptr)), int(B)))
+
+    def sync(self):
+        self._check(self.L.dppr_sync(self.h))
+
+    def stats(self, batch_index=-1) -> BatchStats:
+        s = BatchStats()
+        self._check(self.L.dppr_get_batch_stats(self.h, batch_index, C.byref(s)))
+        return s
+
+    def batches_done(self):
+        return int(self.L.dppr_batches_done(self.h))
+
+    def estimates(self, source_index=0):
+        out = np.empty(self.V, np.float64)
+        self._check(self.L.dppr_get_estimates(self.h, source_index, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def residuals(self, source_index=0):
+        out = np.empty(self.V, np.float64)
+        self._check(self.L.dppr_get_residuals(self.h, source_index, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def copy_estimates_device(self, source_index, device_ptr):
+        self._check(self.L.dppr_copy_estimates_device(self.h, source_index, C.c_void_p(int(device_ptr))))
+
+    def window_csr_entries(self):
+        return int(self.L.dppr_window_csr_entries(self.h))
+
+    def export_window_csr(self):
+        E = self.window_csr_entries()
+        rp = np.empty(self.V + 1, np.int32); ci = np.empty(max(E, 1), np.int32); od = np.empty(self.V, np.int32)
+        self._check(self.L.dppr_export_window_csr(self.h, _i32(rp), _i32(ci), _i32(od)))
+        return rp, ci[:E], od
+
+    def set_state(self, source_index, p=None, r=None):
+        f64p = C.POINTER(C.c_double)
+        pp = np.ascontiguousarray(p, np.float64) if p is not None else None
+        rr = np.ascontiguousarray(r, np.float64) if r is not None else None
+        self._check(self.L.dppr_set_state(self.h, source_index,
+                                          pp.ctypes.data_as(f64p) if pp is not None else None,
+                                          rr.ctypes.data_as(f64p) if rr is not None else None))
+
+
+def test_sort_pairs(keys, vals, key_bits, device=0):
+    L = load_library()
+    k = np.ascontiguousarray(keys, np.uint32).copy(); v = np.ascontiguousarray(vals, np.uint32).copy()
+    rc = L.dppr_test_sort_pairs(device, k.ctypes.data_as(C.POINTER(C.c_uint32)), v.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                len(k), key_bits)
+    if rc != 0:
+        raise DpprError(rc, L.dppr_last_error(None).decode())
+    return k, v
+
+
+def test_exclusive_scan(data, device=0):
+    L = load_library()
+    d = np.ascontiguousarray(data, np.uint32).copy()
+    tot = C.c_uint64()
+    rc = L.dppr_test_exclusive_scan(device, d.ctypes.data_as(C.POINTER(C.c_uint32)), len(d), C.byref(tot))
+    if rc != 0:
+        raise DpprError(rc, L.dppr_last_error(None).decode())
+    return d, int(tot.value)

@@ -1,0 +1,559 @@
+// engine.cu -- see engine.cuh.  Reference call stack being replaced: SURVEY.md 3.1 / 3.2.
+#include "engine.cuh"
+#include <algorithm>
+#include <cstddef>
+#include <cstdlib>
+#include <cstring>
+
+namespace dppr {
+
+namespace {
+
+__global__ void gather_record(BatchRecord *rec, const PushCtrl *ctrl, const uint32_t *counters,
+                              const unsigned long long *pool_top) {
+    rec->ctrl = *ctrl;
+    rec->nseg_in = counters[0];
+    rec->nseg_out = counters[1];
+    rec->njobs = counters[2];
+    rec->pad = 0;
+    rec->pool_top = *pool_top;
+}
+
+__global__ void fold_window_errors(PushCtrl *ctrl, int *win_err) {
+    if (*win_err) atomicOr(&ctrl->errflags, *win_err);
+}
+
+int env_int(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+template <int VAR>
+void *persistent_kernel() { return (void *)push_persistent<VAR>; }
+
+}  // namespace
+
+int Engine::grid_for(int64_t n) const {
+    int64_t g = (n + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sm_count_ * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
+    if (cfg.vertex_count <= 0) throw InvalidArgument("vertex_count must be positive");
+    if (cfg.window_edges <= 0) throw InvalidArgument("window_edges must be positive");
+    if (cfg.max_batch_edges < 0 || cfg.max_batch_edges > cfg.window_edges)
+        throw InvalidArgument("max_batch_edges must be in [0, window_edges]");
+    if (cfg.variant < DPPR_OPTIMIZED || cfg.variant > DPPR_VANILLA)
+        throw InvalidArgument("variant must be 0..3 (Meta.h:11-17)");
+    if (cfg.n_sources < 1 || cfg.sources == nullptr) throw InvalidArgument("at least one source vertex is required");
+    if (cfg.engine_mode != DPPR_ENGINE_PERSISTENT && cfg.engine_mode != DPPR_ENGINE_STEPWISE)
+        throw InvalidArgument("engine_mode must be DPPR_ENGINE_PERSISTENT or DPPR_ENGINE_STEPWISE");
+    if (cfg_.alpha <= 0.0) cfg_.alpha = 0.15;
+    if (cfg_.alpha >= 1.0) throw InvalidArgument("alpha must be in (0, 1)");
+    if (cfg_.epsilon <= 0.0) cfg_.epsilon = 1e-9;
+    if (cfg_.pool_factor <= 0.0) cfg_.pool_factor = 8.0;
+    if (cfg_.hub_degree <= 0) cfg_.hub_degree = 4096;
+    V_ = cfg.vertex_count;
+    D_ = cfg.directed ? 1 : 2;
+    W_ = cfg.window_edges;
+    Ew_ = W_ * D_;
+    Bmax_ = cfg.max_batch_edges;
+    Nb_ = std::max<int64_t>(2 * D_ * Bmax_, 1);
+    S_ = cfg.n_sources;
+    Vp_ = ((int64_t)V_ + 31) / 32 * 32;
+    sources_.assign(cfg.sources, cfg.sources + S_);
+    cfg_.sources = sources_.data();
+    for (int32_t s : sources_)
+        if (s < 0 || s >= V_) throw InvalidArgument("source vertex id out of range");
+    if ((uint64_t)V_ >= (1ull << 31)) throw InvalidArgument("vertex ids must fit in 31 bits");
+    if (Ew_ >= (int64_t)0xffffffffll) throw InvalidArgument("window too large for 32-bit CSR offsets");
+    key_bits_ = bits_for((uint64_t)(V_ - 1));
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw CudaFailure(std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (cfg.device < 0 || cfg.device >= ndev) throw InvalidArgument("device ordinal out of range");
+    dev_ = cfg.device;
+    DPPR_CUDA(cudaSetDevice(dev_));
+    cudaDeviceProp prop;
+    DPPR_CUDA(cudaGetDeviceProperties(&prop, dev_));
+    sm_count_ = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) throw CudaFailure("device does not support cooperative launch");
+    DPPR_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+
+    // cooperative grid per variant: every CTA must be co-resident for the software grid barrier
+    void *kern[4] = {persistent_kernel<0>(), persistent_kernel<1>(), persistent_kernel<2>(), persistent_kernel<3>()};
+    const int want_per_sm = env_int("DPPR_CTAS_PER_SM", 4);
+    for (int v = 0; v < 4; ++v) {
+        int per_sm = 0;
+        DPPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern[v], kThreads, 0));
+        if (per_sm < 1) throw CudaFailure("push kernel does not fit on an SM");
+        coop_grid_[v] = std::min(per_sm, std::max(want_per_sm, 1)) * sm_count_;
+    }
+
+    // window
+    log_.alloc((size_t)W_);
+    vmeta_.alloc((size_t)V_);
+    outdeg_.alloc((size_t)V_);
+    double pc = cfg_.pool_factor * (double)Ew_ + 4096.0;
+    if (pc > 4294967295.0) pc = 4294967295.0;
+    pool_cap_ = (unsigned long long)pc;
+    pool_.alloc((size_t)pool_cap_);
+    pool_top_.alloc(1);
+    // batch scratch
+    arriving_.alloc((size_t)std::max<int64_t>(Bmax_, 1));
+    for (int i = 0; i < 2; ++i) {
+        akey_[i].alloc((size_t)Nb_);
+        aval_[i].alloc((size_t)Nb_);
+        if (D_ == 1) {
+            bkey_[i].alloc((size_t)Nb_);
+            bval_[i].alloc((size_t)Nb_);
+        }
+    }
+    sort_scratch_.alloc(sort_scratch_elems(Nb_) + scan_scratch_elems(Nb_));
+    flags_.alloc((size_t)Nb_);
+    segA_vertex_.alloc((size_t)Nb_); segA_start_.alloc((size_t)Nb_ + 1); segA_first_.alloc((size_t)Nb_); segA_of_.alloc((size_t)Nb_);
+    counters_.alloc(4);
+    segA_ = Segments{segA_vertex_.ptr, segA_start_.ptr, segA_first_.ptr, segA_of_.ptr, counters_.ptr + 0};
+    if (D_ == 1) {
+        segB_vertex_.alloc((size_t)Nb_); segB_start_.alloc((size_t)Nb_ + 1); segB_first_.alloc((size_t)Nb_); segB_of_.alloc((size_t)Nb_);
+        segB_ = Segments{segB_vertex_.ptr, segB_start_.ptr, segB_first_.ptr, segB_of_.ptr, counters_.ptr + 1};
+    } else {
+        segB_ = segA_;
+    }
+    ins_pos_.alloc((size_t)Nb_);
+    jobs_.alloc((size_t)Nb_);
+    seg_d0_.alloc((size_t)Nb_);
+    delta_.alloc((size_t)Nb_ * S_);
+    DPPR_CUDA(cudaMemsetAsync(delta_.ptr, 0, delta_.bytes(), st_));
+    DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, counters_.bytes(), st_));
+    // state
+    p_.alloc((size_t)Vp_ * S_);
+    r_.alloc((size_t)Vp_ * S_);
+    if (cfg_.variant >= DPPR_EAGER) status_.alloc((size_t)Vp_ * S_);
+    src_.alloc((size_t)S_);
+    DPPR_CUDA(cudaMemcpyAsync(src_.ptr, sources_.data(), sizeof(int32_t) * S_, cudaMemcpyHostToDevice, st_));
+    // push queues: a frontier holds each (source, vertex) at most once
+    int64_t qc = cfg_.frontier_capacity > 0 ? cfg_.frontier_capacity : std::min<int64_t>((int64_t)V_ * S_, (int64_t)1 << 29);
+    qc = std::max<int64_t>(qc, 1024);
+    if (qc > 0xfffffff0ll) qc = 0xfffffff0ll;
+    qcap_ = (uint32_t)qc;
+    hcap_ = (uint32_t)std::min<int64_t>(qc, std::max<int64_t>(1024, (Ew_ / cfg_.hub_degree + 1) * S_));
+    for (int i = 0; i < 2; ++i) {
+        q_[i].alloc(qcap_);
+        if (cfg_.variant != DPPR_OPTIMIZED) qr_[i].alloc(qcap_);
+        hub_[i].alloc(hcap_);
+    }
+    ctrl_.alloc(1);
+    DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, sizeof(PushCtrl), st_));
+    dev_record_.alloc(1);
+    for (int i = 0; i < kStageSlots; ++i) {
+        hstage_[i].alloc((size_t)std::max<int64_t>(Bmax_, 1));
+        DPPR_CUDA(cudaEventCreateWithFlags(&hstage_free_[i], cudaEventDisableTiming));
+    }
+    DPPR_CUDA(cudaStreamSynchronize(st_));
+}
+
+Engine::~Engine() {
+    cudaSetDevice(dev_);
+    if (st_) cudaStreamSynchronize(st_);
+    for (auto &m : meta_)
+        for (auto &ev : m.ev)
+            if (ev) cudaEventDestroy(ev);
+    for (auto &ev : hstage_free_)
+        if (ev) cudaEventDestroy(ev);
+    if (st_) cudaStreamDestroy(st_);
+}
+
+void Engine::record(int which) {
+    if (!cfg_.record_timing) return;
+    BatchMeta &m = cur();
+    if (!m.ev[which]) DPPR_CUDA(cudaEventCreate(&m.ev[which]));
+    DPPR_CUDA(cudaEventRecord(m.ev[which], st_));
+}
+
+BatchRecord *Engine::record_slot(size_t k) {
+    while (records_.size() * kRecordsPerChunk <= k) {
+        records_.emplace_back(new PinnedBuf<BatchRecord>());
+        records_.back()->alloc(kRecordsPerChunk);
+        std::memset(records_.back()->ptr, 0, sizeof(BatchRecord) * kRecordsPerChunk);
+    }
+    return records_[k / kRecordsPerChunk]->ptr + (k % kRecordsPerChunk);
+}
+
+void Engine::finish_record() {
+    fold_window_errors<<<1, 1, 0, st_>>>(ctrl_.ptr, (int *)(counters_.ptr + 3));
+    gather_record<<<1, 1, 0, st_>>>(dev_record_.ptr, ctrl_.ptr, counters_.ptr, pool_top_.ptr);
+    DPPR_CUDA(cudaGetLastError());
+    DPPR_CUDA(cudaMemcpyAsync(record_slot(meta_.size() - 1), dev_record_.ptr, sizeof(BatchRecord),
+                              cudaMemcpyDeviceToHost, st_));
+}
+
+// ---------------------------------------------------------------------------------------------
+// initial window
+// ---------------------------------------------------------------------------------------------
+int2 *Engine::stage_pairs(const int32_t *pairs, const int32_t *e1, const int32_t *e2, int64_t n) {
+    const int slot = hstage_next_;
+    hstage_next_ = (hstage_next_ + 1) % kStageSlots;
+    DPPR_CUDA(cudaEventSynchronize(hstage_free_[slot]));  // the H2D copy that last used this slot is done
+    int2 *h = hstage_[slot].ptr;
+    if (pairs) {
+        std::memcpy(h, pairs, sizeof(int2) * (size_t)n);
+    } else {  // EdgeBatch is SoA (EdgeBatch.h:24-26)
+        for (int64_t i = 0; i < n; ++i) h[i] = make_int2(e1[i], e2[i]);
+    }
+    DPPR_CUDA(cudaMemcpyAsync(arriving_.ptr, h, sizeof(int2) * (size_t)n, cudaMemcpyHostToDevice, st_));
+    DPPR_CUDA(cudaEventRecord(hstage_free_[slot], st_));
+    return arriving_.ptr;
+}
+
+void Engine::init_window_soa(const int32_t *e1, const int32_t *e2, int64_t n) {
+    if (!e1 || !e2) throw InvalidArgument("null edge arrays");
+    if (n != W_) throw InvalidArgument("init_window needs exactly window_edges edges (InitWindowStream asserts the same)");
+    std::vector<int32_t> pairs((size_t)n * 2);
+    for (int64_t i = 0; i < n; ++i) {
+        pairs[2 * i] = e1[i];
+        pairs[2 * i + 1] = e2[i];
+    }
+    init_window_pairs(pairs.data(), n);
+}
+
+void Engine::init_window_pairs(const int32_t *pairs, int64_t n) {
+    if (!pairs) throw InvalidArgument("null edge array");
+    if (n != W_) throw InvalidArgument("init_window needs exactly window_edges edges (InitWindowStream asserts the same)");
+    DPPR_CUDA(cudaSetDevice(dev_));
+    DPPR_CUDA(cudaMemcpyAsync(log_.ptr, pairs, sizeof(int2) * (size_t)W_, cudaMemcpyHostToDevice, st_));
+    log_start_ = 0;
+
+    DevBuf<uint32_t> key[2], val[2], indeg, caps, rowptr, capbase, scratch, total;
+    for (int i = 0; i < 2; ++i) {
+        key[i].alloc((size_t)Ew_);
+        val[i].alloc((size_t)Ew_);
+    }
+    indeg.alloc((size_t)V_); caps.alloc((size_t)V_); rowptr.alloc((size_t)V_); capbase.alloc((size_t)V_);
+    scratch.alloc(std::max(sort_scratch_elems(Ew_), scan_scratch_elems(V_)));
+    total.alloc(1);
+    DPPR_CUDA(cudaMemsetAsync(indeg.ptr, 0, indeg.bytes(), st_));
+    DPPR_CUDA(cudaMemsetAsync(outdeg_.ptr, 0, outdeg_.bytes(), st_));
+    DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, counters_.bytes(), st_));
+    int *werr = (int *)(counters_.ptr + 3);
+
+    win_init_entries<<<grid_for(W_), kThreads, 0, st_>>>(log_.ptr, W_, D_ == 1, V_, key[0].ptr, val[0].ptr, indeg.ptr,
+                                                        outdeg_.ptr, werr);
+    win_init_caps<<<grid_for(V_), kThreads, 0, st_>>>(indeg.ptr, caps.ptr, V_);
+    exclusive_scan<uint32_t>(indeg.ptr, rowptr.ptr, V_, scratch.ptr, nullptr, st_);
+    exclusive_scan<uint32_t>(caps.ptr, capbase.ptr, V_, scratch.ptr, total.ptr, st_);
+    const int res = sort_pairs(key[0].ptr, val[0].ptr, key[1].ptr, val[1].ptr, Ew_, key_bits_, scratch.ptr, st_);
+    win_init_fill<<<grid_for(Ew_), kThreads, 0, st_>>>(key[res].ptr, val[res].ptr, Ew_, rowptr.ptr, capbase.ptr, pool_.ptr);
+    win_init_meta<<<grid_for(V_), kThreads, 0, st_>>>(indeg.ptr, caps.ptr, capbase.ptr, vmeta_.ptr, V_);
+    DPPR_CUDA(cudaGetLastError());
+    uint32_t htotal = 0;
+    int herr = 0;
+    DPPR_CUDA(cudaMemcpyAsync(&htotal, total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
+    DPPR_CUDA(cudaMemcpyAsync(&herr, werr, sizeof(int), cudaMemcpyDeviceToHost, st_));
+    DPPR_CUDA(cudaStreamSynchronize(st_));
+    if (herr & kErrBadId) throw InvalidArgument("edge endpoint outside [0, vertex_count) (GraphVec.h:55-56 asserts the same)");
+    if ((unsigned long long)htotal > pool_cap_) throw CapacityError("adjacency pool too small for the initial window; raise pool_factor");
+    const unsigned long long top = htotal;
+    DPPR_CUDA(cudaMemcpyAsync(pool_top_.ptr, &top, sizeof(top), cudaMemcpyHostToDevice, st_));
+    DPPR_CUDA(cudaStreamSynchronize(st_));
+    window_ready_ = true;
+    solved_ = false;
+    batch_pending_ = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// push launch
+// ---------------------------------------------------------------------------------------------
+void Engine::launch_push(bool init_mode) {
+    DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, kCtrlZeroBytes, st_));
+    PushArgs a{};
+    a.vmeta = vmeta_.ptr; a.pool = pool_.ptr; a.outdeg = outdeg_.ptr;
+    a.p = p_.ptr; a.r = r_.ptr; a.status = status_.ptr;
+    a.Vp = Vp_; a.S = S_; a.src = src_.ptr;
+    for (int i = 0; i < 2; ++i) { a.q[i] = q_[i].ptr; a.qr[i] = qr_[i].ptr; a.hub[i] = hub_[i].ptr; }
+    a.qcap = qcap_; a.hcap = hcap_;
+    a.cand = segB_.vertex; a.ncand = segB_.count;
+    a.ctrl = ctrl_.ptr;
+    a.eps = cfg_.epsilon; a.alpha = cfg_.alpha;
+    a.hub_degree = cfg_.hub_degree;
+    a.init_mode = init_mode ? 1 : 0;
+    a.max_iters = env_int("DPPR_MAX_ITERS", 400000);
+    if (cfg_.engine_mode == DPPR_ENGINE_STEPWISE) {
+        launch_push_stepwise(a);
+        return;
+    }
+    void *params[] = {(void *)&a};
+    void *kern = nullptr;
+    switch (cfg_.variant) {
+        case 0: kern = persistent_kernel<0>(); break;
+        case 1: kern = persistent_kernel<1>(); break;
+        case 2: kern = persistent_kernel<2>(); break;
+        default: kern = persistent_kernel<3>(); break;
+    }
+    DPPR_CUDA(cudaLaunchCooperativeKernel(kern, dim3(coop_grid_[cfg_.variant]), dim3(kThreads), params, 0, st_));
+}
+
+// Debug / profiling mode with the reference's structure: one launch per sub-pass and a blocking
+// read of the frontier counters per iteration (gpu/PPRRevPushGPU.cuh:106-108).
+void Engine::launch_push_stepwise(PushArgs &a) {
+    const int grid = coop_grid_[cfg_.variant];
+    const int var = cfg_.variant;
+    uint32_t it = 0;
+    PushCtrl h{};
+    const int nphases = a.init_mode ? 1 : 2;
+    for (int phase = 0; phase < nphases; ++phase) {
+        push_step_seed<<<grid, kThreads, 0, st_>>>(a, it, phase);
+        while (true) {
+            DPPR_CUDA(cudaMemcpyAsync(&h, ctrl_.ptr, sizeof(PushCtrl), cudaMemcpyDeviceToHost, st_));
+            DPPR_CUDA(cudaStreamSynchronize(st_));
+            if (h.cnt[it % 3] == 0 && h.hcnt[(it + 2) % 3] == 0) break;
+            if ((int)it >= a.max_iters) throw CapacityError("push did not converge within DPPR_MAX_ITERS iterations");
+            const int level = step_level_ + (int)it + 1;
+            switch (var) {
+                case 0: push_step_expand<0><<<grid, kThreads, 0, st_>>>(a, it, phase, level); break;
+                case 1:
+                    push_step_pre<1><<<grid, kThreads, 0, st_>>>(a, it, level);
+                    push_step_expand<1><<<grid, kThreads, 0, st_>>>(a, it, phase, level);
+                    break;
+                case 2:
+                    push_step_pre<2><<<grid, kThreads, 0, st_>>>(a, it, level);
+                    push_step_expand<2><<<grid, kThreads, 0, st_>>>(a, it, phase, level);
+                    push_step_post<<<grid, kThreads, 0, st_>>>(a, it, phase);
+                    break;
+                default:
+                    push_step_pre<3><<<grid, kThreads, 0, st_>>>(a, it, level);
+                    push_step_expand<3><<<grid, kThreads, 0, st_>>>(a, it, phase, level);
+                    break;
+            }
+            DPPR_CUDA(cudaGetLastError());
+            ++it;
+        }
+    }
+    step_level_ += (int)it + 2;
+}
+
+void Engine::solve_initial() {
+    if (!window_ready_) throw StateError("dppr_solve_initial before dppr_init_window");
+    DPPR_CUDA(cudaSetDevice(dev_));
+    for (auto &m : meta_)
+        for (auto &ev : m.ev)
+            if (ev) cudaEventDestroy(ev);
+    meta_.clear();
+    meta_.emplace_back();
+    record(0);
+    state_init<<<grid_for(Vp_ * S_), kThreads, 0, st_>>>(p_.ptr, r_.ptr, status_.ptr, Vp_, S_, src_.ptr);
+    DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, sizeof(PushCtrl), st_));
+    DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, counters_.bytes(), st_));
+    step_level_ = 0;
+    record(3);
+    launch_push(true);
+    record(4);
+    finish_record();
+    DPPR_CUDA(cudaGetLastError());
+    solved_ = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one batch: window update
+// ---------------------------------------------------------------------------------------------
+void Engine::apply_batch_host_pairs(const int32_t *pairs, int64_t B) {
+    if (!pairs && B > 0) throw InvalidArgument("null edge array");
+    if (B <= 0 || B > Bmax_) throw InvalidArgument("batch size must be in [1, max_batch_edges]");
+    if (!solved_) throw StateError("dppr_apply_batch before dppr_solve_initial");
+    if (batch_pending_) throw StateError("dppr_apply_batch twice without dppr_refresh");
+    DPPR_CUDA(cudaSetDevice(dev_));
+    meta_.emplace_back();
+    record(0);
+    int2 *d = stage_pairs(pairs, nullptr, nullptr, B);
+    cur().has_upload = true;
+    record(1);
+    apply_batch_common(d, B);
+}
+
+void Engine::apply_batch_host_soa(const int32_t *e1, const int32_t *e2, int64_t B) {
+    if ((!e1 || !e2) && B > 0) throw InvalidArgument("null edge arrays");
+    if (B <= 0 || B > Bmax_) throw InvalidArgument("batch size must be in [1, max_batch_edges]");
+    if (!solved_) throw StateError("dppr_apply_batch before dppr_solve_initial");
+    if (batch_pending_) throw StateError("dppr_apply_batch twice without dppr_refresh");
+    DPPR_CUDA(cudaSetDevice(dev_));
+    meta_.emplace_back();
+    record(0);
+    int2 *d = stage_pairs(nullptr, e1, e2, B);
+    cur().has_upload = true;
+    record(1);
+    apply_batch_common(d, B);
+}
+
+void Engine::apply_batch_device_pairs(const int32_t *dpairs, int64_t B) {
+    if (!dpairs && B > 0) throw InvalidArgument("null device edge array");
+    if (B <= 0 || B > Bmax_) throw InvalidArgument("batch size must be in [1, max_batch_edges]");
+    if (!solved_) throw StateError("dppr_apply_batch before dppr_solve_initial");
+    if (batch_pending_) throw StateError("dppr_apply_batch twice without dppr_refresh");
+    DPPR_CUDA(cudaSetDevice(dev_));
+    meta_.emplace_back();
+    record(0);
+    record(1);
+    apply_batch_common((const int2 *)dpairs, B);
+}
+
+void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
+    BatchMeta &m = cur();
+    const int64_t nA = 2 * D_ * B;  // entries in a group (directed: 2B per group, undirected: 4B in the one group)
+    m.edges = B;
+    m.entries = nA;
+    m.has_window = true;
+    int *werr = (int *)(counters_.ptr + 3);
+    DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, sizeof(uint32_t) * 3, st_));
+    win_batch_entries<<<grid_for(B), kThreads, 0, st_>>>(log_.ptr, W_, log_start_, arriving, B, D_ == 1, V_,
+                                                        akey_[0].ptr, aval_[0].ptr, bkey_[0].ptr, bval_[0].ptr, werr);
+    log_start_ = (log_start_ + B) % W_;
+    uint32_t *scan_scratch = sort_scratch_.ptr + sort_scratch_elems(Nb_);
+
+    // group A: keyed by destination -> in-lists
+    int res = sort_pairs(akey_[0].ptr, aval_[0].ptr, akey_[1].ptr, aval_[1].ptr, nA, key_bits_, sort_scratch_.ptr, st_);
+    sa_key_ = akey_[res].ptr; sa_val_ = aval_[res].ptr;
+    rle_heads<<<grid_for(nA), kThreads, 0, st_>>>(sa_key_, nA, flags_.ptr);
+    exclusive_scan<uint32_t>(flags_.ptr, segA_.segof, nA, scan_scratch, nullptr, st_);
+    rle_fill<<<grid_for(nA), kThreads, 0, st_>>>(sa_key_, sa_val_, nA, segA_);
+    WindowView wv{V_, vmeta_.ptr, pool_.ptr, outdeg_.ptr, pool_top_.ptr, pool_cap_, werr};
+    win_plan<<<grid_for(nA), kThreads, 0, st_>>>(segA_, wv, ins_pos_.ptr, jobs_.ptr, counters_.ptr + 2);
+    win_relocate<<<std::min(grid_for(nA), 4 * sm_count_), kThreads, 0, st_>>>(jobs_.ptr, counters_.ptr + 2, pool_.ptr);
+    win_insert<<<grid_for(nA), kThreads, 0, st_>>>(sa_key_, sa_val_, nA, segA_, ins_pos_.ptr, wv);
+
+    // group B: keyed by source -> out-degrees + residual repair (undirected: same runs as group A)
+    if (D_ == 1) {
+        res = sort_pairs(bkey_[0].ptr, bval_[0].ptr, bkey_[1].ptr, bval_[1].ptr, nA, key_bits_, sort_scratch_.ptr, st_);
+        sb_key_ = bkey_[res].ptr; sb_val_ = bval_[res].ptr;
+        rle_heads<<<grid_for(nA), kThreads, 0, st_>>>(sb_key_, nA, flags_.ptr);
+        exclusive_scan<uint32_t>(flags_.ptr, segB_.segof, nA, scan_scratch, nullptr, st_);
+        rle_fill<<<grid_for(nA), kThreads, 0, st_>>>(sb_key_, sb_val_, nA, segB_);
+    } else {
+        sb_key_ = sa_key_; sb_val_ = sa_val_;
+    }
+    win_out_degrees<<<grid_for(nA), kThreads, 0, st_>>>(segB_, outdeg_.ptr, seg_d0_.ptr);
+    DPPR_CUDA(cudaGetLastError());
+    record(2);
+    batch_pending_ = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one batch: residual repair + both push phases (the reference's timed region)
+// ---------------------------------------------------------------------------------------------
+void Engine::refresh(bool repair_only) {
+    if (!batch_pending_) throw StateError("dppr_refresh without a preceding dppr_apply_batch");
+    DPPR_CUDA(cudaSetDevice(dev_));
+    const int64_t n = cur().entries;
+    dim3 g((unsigned)std::min(grid_for(n), 8 * sm_count_), (unsigned)S_);
+    repair_accumulate<<<g, kThreads, 0, st_>>>(sb_val_, n, segB_.segof, p_.ptr, Vp_, delta_.ptr, Nb_);
+    repair_finalize<<<grid_for(n * S_), kThreads, 0, st_>>>(segB_, seg_d0_.ptr, src_.ptr, S_, p_.ptr, r_.ptr, Vp_,
+                                                          delta_.ptr, Nb_, cfg_.alpha);
+    DPPR_CUDA(cudaGetLastError());
+    record(3);
+    if (!repair_only) launch_push(false);
+    else DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, kCtrlZeroBytes, st_));
+    record(4);
+    finish_record();
+    batch_pending_ = false;
+}
+
+void Engine::sync() {
+    DPPR_CUDA(cudaSetDevice(dev_));
+    DPPR_CUDA(cudaStreamSynchronize(st_));
+}
+
+void Engine::get_stats(int64_t batch_index, dppr_batch_stats *out) {
+    if (!out) throw InvalidArgument("null stats pointer");
+    if (meta_.empty()) throw StateError("no batch has been processed yet");
+    if (batch_index < 0) batch_index = (int64_t)meta_.size() - 1;
+    if (batch_index >= (int64_t)meta_.size()) throw InvalidArgument("batch index out of range");
+    if (batch_index == (int64_t)meta_.size() - 1 && batch_pending_) throw StateError("batch applied but not refreshed yet");
+    sync();
+    const BatchMeta &m = meta_[(size_t)batch_index];
+    const BatchRecord *rec = record_slot((size_t)batch_index);
+    std::memset(out, 0, sizeof(*out));
+    out->batch_index = batch_index;
+    out->edges = m.edges;
+    out->batch_entries = m.entries;  // N_b = 2*D*B
+    out->touched_vertices = (D_ == 1) ? rec->nseg_out : rec->nseg_in;
+    out->iterations = (int64_t)rec->ctrl.iters;
+    out->frontier_pops = (int64_t)rec->ctrl.pops;
+    out->traversed_edges = (int64_t)rec->ctrl.edges;
+    out->hub_pops = (int64_t)rec->ctrl.hubs;
+    out->relocations = rec->njobs;
+    out->pool_used = (int64_t)rec->pool_top;
+    out->error_flags = rec->ctrl.errflags;
+    auto ms = [&](int a, int b) -> float {
+        if (!cfg_.record_timing || !m.ev[a] || !m.ev[b]) return 0.f;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, m.ev[a], m.ev[b]) != cudaSuccess) return 0.f;
+        return t;
+    };
+    out->ms_upload = m.has_upload ? ms(0, 1) : 0.f;
+    out->ms_window = m.has_window ? ms(1, 2) : 0.f;
+    out->ms_repair = m.has_window ? ms(2, 3) : 0.f;
+    out->ms_push = ms(3, 4);
+}
+
+void Engine::get_vector(int which, int32_t s, double *out) {
+    if (!out) throw InvalidArgument("null output pointer");
+    if (s < 0 || s >= S_) throw InvalidArgument("source index out of range");
+    if (!solved_) throw StateError("no estimates before dppr_solve_initial");
+    sync();
+    const double *src = (which == 0 ? p_.ptr : r_.ptr) + (size_t)s * Vp_;
+    DPPR_CUDA(cudaMemcpy(out, src, sizeof(double) * (size_t)V_, cudaMemcpyDeviceToHost));
+}
+
+void Engine::copy_estimates_device(int32_t s, void *dptr) {
+    if (!dptr) throw InvalidArgument("null device pointer");
+    if (s < 0 || s >= S_) throw InvalidArgument("source index out of range");
+    DPPR_CUDA(cudaSetDevice(dev_));
+    DPPR_CUDA(cudaMemcpyAsync(dptr, p_.ptr + (size_t)s * Vp_, sizeof(double) * (size_t)V_, cudaMemcpyDeviceToDevice, st_));
+    DPPR_CUDA(cudaStreamSynchronize(st_));
+}
+
+void Engine::set_state(int32_t s, const double *p, const double *r) {
+    if (s < 0 || s >= S_) throw InvalidArgument("source index out of range");
+    sync();
+    if (p) DPPR_CUDA(cudaMemcpy(p_.ptr + (size_t)s * Vp_, p, sizeof(double) * (size_t)V_, cudaMemcpyHostToDevice));
+    if (r) DPPR_CUDA(cudaMemcpy(r_.ptr + (size_t)s * Vp_, r, sizeof(double) * (size_t)V_, cudaMemcpyHostToDevice));
+    solved_ = true;
+    if (meta_.empty()) meta_.emplace_back();
+}
+
+// canonical CSR: rows ascending, duplicates kept.  Device sort, test/validation path.
+void Engine::export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_deg) {
+    if (!window_ready_) throw StateError("dppr_export_window_csr before dppr_init_window");
+    sync();
+    DevBuf<uint32_t> len, rowptr, key[2], val[2], scratch, total;
+    len.alloc((size_t)V_); rowptr.alloc((size_t)V_ + 1);
+    for (int i = 0; i < 2; ++i) { key[i].alloc((size_t)Ew_); val[i].alloc((size_t)Ew_); }
+    scratch.alloc(std::max(sort_scratch_elems(Ew_), scan_scratch_elems(V_)));
+    total.alloc(1);
+    win_export_len<<<grid_for(V_), kThreads, 0, st_>>>(vmeta_.ptr, len.ptr, V_);
+    exclusive_scan<uint32_t>(len.ptr, rowptr.ptr, V_, scratch.ptr, total.ptr, st_);
+    DPPR_CUDA(cudaMemcpyAsync(rowptr.ptr + V_, total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st_));
+    uint32_t htotal = 0;
+    DPPR_CUDA(cudaMemcpyAsync(&htotal, total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
+    DPPR_CUDA(cudaStreamSynchronize(st_));
+    if ((int64_t)htotal != Ew_)
+        throw StateError("window graph holds " + std::to_string(htotal) + " entries, expected " + std::to_string(Ew_));
+    win_export_entries<<<grid_for((int64_t)V_ * 32), kThreads, 0, st_>>>(vmeta_.ptr, pool_.ptr, rowptr.ptr, key[0].ptr,
+                                                                      val[0].ptr, V_);
+    // sort by (dst, src): LSD over the pair = stable sort by src, then stable sort by dst
+    int res = sort_pairs(val[0].ptr, key[0].ptr, val[1].ptr, key[1].ptr, Ew_, key_bits_, scratch.ptr, st_);
+    uint32_t *k0 = key[res].ptr, *v0 = val[res].ptr, *k1 = key[1 - res].ptr, *v1 = val[1 - res].ptr;
+    res = sort_pairs(k0, v0, k1, v1, Ew_, key_bits_, scratch.ptr, st_);
+    const uint32_t *cols = res ? v1 : v0;
+    DPPR_CUDA(cudaGetLastError());
+    DPPR_CUDA(cudaStreamSynchronize(st_));
+    if (in_row_ptr) DPPR_CUDA(cudaMemcpy(in_row_ptr, rowptr.ptr, sizeof(int32_t) * ((size_t)V_ + 1), cudaMemcpyDeviceToHost));
+    if (in_col_ind && Ew_ > 0) DPPR_CUDA(cudaMemcpy(in_col_ind, cols, sizeof(int32_t) * (size_t)Ew_, cudaMemcpyDeviceToHost));
+    if (out_deg) DPPR_CUDA(cudaMemcpy(out_deg, outdeg_.ptr, sizeof(int32_t) * (size_t)V_, cudaMemcpyDeviceToHost));
+}
+
+}  // namespace dppr

@@ -1,0 +1,483 @@
+// push.cuh -- the reverse-push loop (north-star subsystem 3).
+//
+// Replaces InspectPureRev / InspectExtra (gpu/Inspect.cuh), UpdateFrontierStatus
+// (gpu/PPRCommon.cuh:24-34), the four Expand*Rev kernels and RepairFrontierRev (gpu/ExpandRev.cuh)
+// and the host while(1) around them (gpu/PPRRevPushGPU.cuh:97-131, PPRRevPushGPUVariants.cuh),
+// which costs a blocking 4-byte D2H + a memset + 2-3 launches per push iteration.
+//
+// Structure here:
+//   * The whole refresh (seed phase 0, iterate to exhaustion, seed phase 1, iterate) is ONE
+//     persistent cooperative launch; iterations are separated by a software grid barrier, frontier
+//     counters live on the device (three rotating slots so that a slot is only cleared one full
+//     iteration after its last reader).  A stepwise mode drives the same device functions with one
+//     launch per sub-pass, for debugging and per-iteration profiling.
+//   * Seeds come from the repaired vertices only -- the reference GPU path scans all V
+//     residuals twice per batch (gpu/Inspect.cuh:9-48).
+//   * Frontier items are (source, vertex) pairs, so S sources share one launch, one queue and one
+//     window graph.
+//   * Neighbour expansion is edge-balanced: a CTA prefix-sums the in-degrees of a tile of frontier
+//     items in shared memory and its threads walk the concatenated edge range, finding the owner by
+//     binary search, so a thread's work does not depend on its vertex's degree (the reference's
+//     CTA / warp / scan three-tier scheme, gpu/ExpandRev.cuh:48-179).  Vertices with in-degree >=
+//     hub_degree are moved to a hub list and expanded by the whole grid in the next iteration.
+//   * The next frontier is compacted with warp ballot + popc into a shared-memory staging buffer and
+//     flushed with one global atomicAdd per CTA per tile (reference: a cub::BlockScan and a global
+//     atomic per 256-edge step).
+//   * Residual scatter uses the native FP64 atomicAdd returning the old value (the reference emulates
+//     it with a CAS loop, gpu/GPUUtil.cuh:21-30): every variant needs `old` for its enqueue rule.
+//
+// Variants (-o), semantics of SURVEY A.5:
+//   0 OPTIMIZED      eager + fast frontier.  ru is claimed with one atomicExch(r[u], 0) at pop time, so
+//                    adds that reach u later in the same iteration are kept and u re-enters the next
+//                    frontier exactly when they carry it across the threshold -- the same set the
+//                    reference obtains by reading r[u] live, subtracting ru afterwards and re-checking
+//                    (RepairFrontierRev, gpu/ExpandRev.cuh:709-743), without the second pass.
+//   1 FAST_FRONTIER  snapshot pass (InspectExtra: ft_r=r, p+=a r, r=0), barrier, push; threshold-crossing dedupe.
+//   2 EAGER          stamp status[u]=level, barrier, live read + push with atomicExch(status) dedupe,
+//                    barrier, repair pass r[u]-=ru with re-enqueue.
+//   3 VANILLA        snapshot pass, barrier, push with atomicExch(status) dedupe.
+#pragma once
+#include "common.cuh"
+#include "window.cuh"
+
+namespace dppr {
+
+constexpr int kStage = 1024;            // staged next-frontier items per CTA
+constexpr int kHubChunk = 4 * kThreads; // edges of a hub one CTA takes at a time
+
+// device-resident control block.  [0, kCtrlZeroBytes) is cleared before every refresh.
+struct PushCtrl {
+    unsigned int cnt[3];    // frontier sizes, slot it % 3 is consumed in iteration `it`
+    unsigned int hcnt[3];   // hub list sizes, slot it % 3 is produced in iteration `it`
+    unsigned int bar;       // grid barrier arrivals (monotone within a launch)
+    unsigned int pad0;
+    unsigned long long iters, pops, edges, hubs;
+    // ---- persistent across launches ----
+    int errflags;
+    int level;              // last status stamp handed out (variants 2, 3)
+};
+constexpr size_t kCtrlZeroBytes = offsetof(PushCtrl, errflags);
+
+struct HubItem {            // 16 bytes
+    unsigned long long item;
+    double ru;
+};
+
+struct PushArgs {
+    const uint4 *vmeta;
+    const int32_t *pool;
+    const int32_t *outdeg;
+    double *p;
+    double *r;
+    int32_t *status;
+    int64_t Vp;
+    int32_t S;
+    const int32_t *src;
+    unsigned long long *q[2];
+    double *qr[2];
+    uint32_t qcap;
+    HubItem *hub[2];
+    uint32_t hcap;
+    const uint32_t *cand;        // seed candidates: distinct repaired vertices
+    const uint32_t *ncand;       // device scalar
+    PushCtrl *ctrl;
+    double eps, alpha;
+    int32_t hub_degree;
+    int32_t init_mode;           // 1: seed = the sources themselves, phase 0 only (initial solve)
+    int32_t max_iters;
+};
+
+struct PushSmem {
+    unsigned long long stage[kStage];
+    double t_ru[kThreads];
+    unsigned long long t_sb[kThreads];
+    uint32_t t_off[kThreads];
+    uint32_t t_base[kThreads];
+    uint32_t t_head[kThreads];
+    uint32_t t_mask[kThreads];
+    uint32_t t_s[kThreads];
+    uint32_t scan[kWarps + 1];
+    unsigned int stage_cnt;
+    unsigned int gbase;
+    int abort_flag;
+};
+
+__device__ __forceinline__ bool legal_push(double x, int phase, double eps) {  // gpu/PPRCommon.cuh:6-11
+    return phase == 0 ? (x > eps) : (x < -eps);
+}
+
+// ---- next-frontier staging ------------------------------------------------------------------
+// must be called by all 32 lanes of a warp together
+__device__ __forceinline__ void stage_push(bool want, unsigned long long item, PushSmem &sm,
+                                           unsigned long long *qout, unsigned int *cnt_out, uint32_t qcap,
+                                           PushCtrl *ctrl) {
+    const unsigned m = __ballot_sync(kFull, want);
+    if (m == 0) return;
+    const int n = __popc(m);
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(&sm.stage_cnt, (unsigned)n);
+    base = __shfl_sync(kFull, base, leader);
+    // stage_cnt only ever grows between flushes (so reserved positions below kStage have exactly one
+    // writer and no holes); positions at or beyond kStage spill straight to the global queue
+    const unsigned pos = base + __popc(m & lanemask_lt());
+    const bool spill = want && pos >= (unsigned)kStage;
+    if (want && !spill) sm.stage[pos] = item;
+    if (base + n > (unsigned)kStage) {  // warp-uniform
+        const unsigned m2 = __ballot_sync(kFull, spill);
+        const int leader2 = __ffs(m2) - 1;
+        unsigned g = 0;
+        if ((int)lane_id() == leader2) g = atomicAdd(cnt_out, (unsigned)__popc(m2));
+        g = __shfl_sync(kFull, g, leader2);
+        if (spill) {
+            const unsigned gp = g + __popc(m2 & lanemask_lt());
+            if (gp < qcap) __stcg(&qout[gp], item);
+            else atomicOr(&ctrl->errflags, kErrQueue);
+        }
+    }
+}
+
+// CTA-wide; leaves stage empty.  Contains barriers: call from uniform control flow.
+__device__ __forceinline__ void stage_flush(PushSmem &sm, unsigned long long *qout, unsigned int *cnt_out,
+                                            uint32_t qcap, PushCtrl *ctrl) {
+    __syncthreads();
+    const unsigned n = sm.stage_cnt < (unsigned)kStage ? sm.stage_cnt : (unsigned)kStage;  // the rest spilled
+    if (n) {
+        if (threadIdx.x == 0) sm.gbase = atomicAdd(cnt_out, n);
+        __syncthreads();
+        const unsigned g = sm.gbase;
+        for (unsigned i = threadIdx.x; i < n; i += kThreads) {
+            if (g + i < qcap) __stcg(&qout[g + i], sm.stage[i]);
+            else atomicOr(&ctrl->errflags, kErrQueue);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) sm.stage_cnt = 0;
+    }
+    __syncthreads();
+}
+
+// ---- one traversed in-edge --------------------------------------------------------------------
+template <int VAR>
+__device__ __forceinline__ bool push_edge(const PushArgs &a, uint32_t nbr, double ru_scaled, unsigned long long sb,
+                                          int phase, int level) {
+    const int32_t dv = __ldg(&a.outdeg[nbr]);
+    const double add = ru_scaled / (double)(dv + 1);  // (1-alpha)*ru/(outdeg(v)+1), gpu/ExpandRev.cuh:71-72
+    const unsigned long long ridx = sb + nbr;
+    const double old = atomicAdd(&a.r[ridx], add);
+    const double cur = old + add;
+    if (VAR == 0 || VAR == 1) {  // threshold crossing, gpu/ExpandRev.cuh:75
+        return !legal_push(old, phase, a.eps) && legal_push(cur, phase, a.eps);
+    } else {                     // status stamp, gpu/ExpandRev.cuh:254-257
+        if (!legal_push(cur, phase, a.eps)) return false;
+        return atomicExch(&a.status[ridx], level) < level;
+    }
+}
+
+// ---- seeds --------------------------------------------------------------------------------------
+__device__ void seed_pass(const PushArgs &a, PushSmem &sm, int phase, unsigned long long *qout,
+                          unsigned int *cnt_out) {
+    const uint32_t ncand = a.init_mode ? 1u : __ldcg(a.ncand);
+    const unsigned long long total = (unsigned long long)ncand * (unsigned)a.S;
+    const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
+    const unsigned long long rounds = (total + stride - 1) / stride;
+    for (unsigned long long rd = 0; rd < rounds; ++rd) {
+        const unsigned long long j = rd * stride + (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
+        bool want = false;
+        unsigned long long item = 0;
+        if (j < total) {
+            const uint32_t s = (uint32_t)(j / ncand);
+            const uint32_t c = (uint32_t)(j - (unsigned long long)s * ncand);
+            const uint32_t u = a.init_mode ? (uint32_t)a.src[s] : a.cand[c];
+            const double x = __ldcg(&a.r[(unsigned long long)s * a.Vp + u]);
+            want = legal_push(x, phase, a.eps);
+            item = ((unsigned long long)s << 32) | u;
+        }
+        stage_push(want, item, sm, qout, cnt_out, a.qcap, a.ctrl);
+        if ((rd & 3) == 3) stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
+    }
+    stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
+}
+
+// ---- pre pass: variants 1,3 snapshot + zero (gpu/Inspect.cuh:52-65); variant 2 status stamp ------
+template <int VAR>
+__device__ void pre_pass(const PushArgs &a, const unsigned long long *qin, double *qr, uint32_t n, int level) {
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const unsigned long long item = __ldcg(&qin[i]);
+        const unsigned long long idx = (item >> 32) * a.Vp + (uint32_t)item;
+        if (VAR == 1 || VAR == 3) {
+            const double x = __ldcg(&a.r[idx]);
+            __stcg(&qr[i], x);
+            __stcg(&a.p[idx], __ldcg(&a.p[idx]) + a.alpha * x);
+            __stcg(&a.r[idx], 0.0);
+        } else if (VAR == 2) {
+            __stcg(&a.status[idx], level);
+        }
+    }
+}
+
+// ---- post pass (variant 2): r[u] -= ru, still legal -> next frontier (gpu/ExpandRev.cuh:709-743) ---
+__device__ void post_pass(const PushArgs &a, PushSmem &sm, const unsigned long long *qin, const double *qr, uint32_t n,
+                          unsigned long long *qout, unsigned int *cnt_out, int phase) {
+    const uint32_t stride = gridDim.x * kThreads;
+    const uint32_t rounds = (n + stride - 1) / stride;
+    for (uint32_t rd = 0; rd < rounds; ++rd) {
+        const uint32_t i = rd * stride + blockIdx.x * kThreads + threadIdx.x;
+        bool want = false;
+        unsigned long long item = 0;
+        if (i < n) {
+            item = __ldcg(&qin[i]);
+            const unsigned long long idx = (item >> 32) * a.Vp + (uint32_t)item;
+            const double ru = __ldcg(&qr[i]);
+            const double old = atomicAdd(&a.r[idx], -ru);
+            want = legal_push(old - ru, phase, a.eps);
+        }
+        stage_push(want, item, sm, qout, cnt_out, a.qcap, a.ctrl);
+        if ((rd & 3) == 3) stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
+    }
+    stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
+}
+
+// ---- hubs popped in the previous iteration: every CTA takes chunks of every hub ---------------------
+template <int VAR>
+__device__ void expand_hubs(const PushArgs &a, PushSmem &sm, const HubItem *hin, uint32_t nh, unsigned long long *qout,
+                            unsigned int *cnt_out, int phase, int level, unsigned long long &edges_acc) {
+    for (uint32_t h = 0; h < nh; ++h) {
+        const unsigned long long item = __ldcg(&hin[h].item);
+        const double ru_scaled = (1.0 - a.alpha) * __ldcg(&hin[h].ru);
+        const uint32_t s = (uint32_t)(item >> 32), v = (uint32_t)item;
+        const unsigned long long sb = (unsigned long long)s * a.Vp;
+        const uint4 m = __ldg(&a.vmeta[v]);
+        const uint32_t deg = m.z, mask = m.w - 1u;
+        for (uint32_t c0 = blockIdx.x * kHubChunk; c0 < deg; c0 += gridDim.x * kHubChunk) {
+#pragma unroll
+            for (int k = 0; k < kHubChunk / kThreads; ++k) {
+                const uint32_t e = c0 + k * kThreads + threadIdx.x;
+                bool want = false;
+                uint32_t nbr = 0;
+                if (e < deg) {
+                    nbr = (uint32_t)__ldg(&a.pool[m.x + ((m.y + e) & mask)]);
+                    want = push_edge<VAR>(a, nbr, ru_scaled, sb, phase, level);
+                }
+                stage_push(want, ((unsigned long long)s << 32) | nbr, sm, qout, cnt_out, a.qcap, a.ctrl);
+            }
+            if (threadIdx.x == 0) edges_acc += min(deg - c0, (uint32_t)kHubChunk);
+            stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
+        }
+    }
+}
+
+// ---- frontier tiles: pop, edge-balanced expansion -----------------------------------------------------
+template <int VAR>
+__device__ void expand_tiles(const PushArgs &a, PushSmem &sm, const unsigned long long *qin, double *qr, uint32_t n,
+                             unsigned long long *qout, unsigned int *cnt_out, HubItem *hout, unsigned int *hcnt_out,
+                             int phase, int level, unsigned long long &edges_acc) {
+    if (n == 0) return;
+    // spread small frontiers over the grid: fewer items per tile, more CTAs with atomics in flight
+    uint32_t tile_items = (n + gridDim.x - 1) / gridDim.x;
+    tile_items = tile_items < 8u ? 8u : (tile_items > (uint32_t)kThreads ? (uint32_t)kThreads : tile_items);
+    const uint32_t ntiles = (n + tile_items - 1) / tile_items;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t i = tile * tile_items + threadIdx.x;
+        uint32_t deg = 0;
+        if (threadIdx.x < tile_items && i < n) {
+            const unsigned long long item = __ldcg(&qin[i]);
+            const uint32_t s = (uint32_t)(item >> 32), v = (uint32_t)item;
+            const unsigned long long sb = (unsigned long long)s * a.Vp;
+            const unsigned long long idx = sb + v;
+            const uint4 m = __ldg(&a.vmeta[v]);
+            double ru;
+            if (VAR == 0) {
+                ru = __longlong_as_double((long long)atomicExch((unsigned long long *)&a.r[idx], 0ull));
+                __stcg(&a.p[idx], __ldcg(&a.p[idx]) + a.alpha * ru);
+            } else if (VAR == 2) {
+                ru = __ldcg(&a.r[idx]);            // live read, kept until the post pass subtracts it
+                __stcg(&qr[i], ru);
+                __stcg(&a.p[idx], __ldcg(&a.p[idx]) + a.alpha * ru);
+            } else {
+                ru = __ldcg(&qr[i]);               // taken by the snapshot pass
+            }
+            deg = m.z;
+            if (deg >= (uint32_t)a.hub_degree) {
+                const unsigned hp = atomicAdd(hcnt_out, 1u);
+                if (hp < a.hcap) {
+                    __stcg(&hout[hp].item, item);
+                    __stcg(&hout[hp].ru, ru);
+                } else {
+                    atomicOr(&a.ctrl->errflags, kErrHubQ);
+                }
+                deg = 0;
+            }
+            sm.t_ru[threadIdx.x] = (1.0 - a.alpha) * ru;
+            sm.t_sb[threadIdx.x] = sb;
+            sm.t_base[threadIdx.x] = m.x;
+            sm.t_head[threadIdx.x] = m.y;
+            sm.t_mask[threadIdx.x] = m.w - 1u;
+            sm.t_s[threadIdx.x] = s;
+        }
+        uint32_t total;
+        const uint32_t off = block_exclusive_sum<uint32_t>(deg, sm.scan, total);
+        sm.t_off[threadIdx.x] = off;
+        __syncthreads();
+        for (uint32_t e0 = 0; e0 < total; e0 += kThreads) {
+            const uint32_t e = e0 + threadIdx.x;
+            bool want = false;
+            unsigned long long item_out = 0;
+            if (e < total) {
+                // owner = last j with t_off[j] <= e   (zero-degree items share an offset with their successor)
+                uint32_t lo = 0, hi = tile_items;
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (sm.t_off[mid] <= e) lo = mid; else hi = mid;
+                }
+                const uint32_t k = e - sm.t_off[lo];
+                const uint32_t nbr = (uint32_t)__ldg(&a.pool[sm.t_base[lo] + ((sm.t_head[lo] + k) & sm.t_mask[lo])]);
+                want = push_edge<VAR>(a, nbr, sm.t_ru[lo], sm.t_sb[lo], phase, level);
+                item_out = ((unsigned long long)sm.t_s[lo] << 32) | nbr;
+            }
+            stage_push(want, item_out, sm, qout, cnt_out, a.qcap, a.ctrl);
+        }
+        if (threadIdx.x == 0) edges_acc += total;
+        stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
+    }
+}
+
+// ---- software grid barrier (all CTAs co-resident: cooperative launch) --------------------------------
+__device__ __forceinline__ bool grid_barrier(PushCtrl *c, unsigned &gen, PushSmem &sm) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++gen;
+        const unsigned target = gen * gridDim.x;
+        __threadfence();
+        atomicAdd(&c->bar, 1u);
+        const long long t0 = clock64();
+        bool ok = true;
+        while (*(volatile unsigned *)&c->bar < target) {
+            if (clock64() - t0 > 8000000000ll) {  // ~4 s: a CTA is missing, give up loudly instead of hanging
+                atomicOr(&c->errflags, kErrWatchdog);
+                ok = false;
+                break;
+            }
+        }
+        __threadfence();
+        sm.abort_flag = ok ? 0 : 1;
+    }
+    __syncthreads();
+    return sm.abort_flag == 0;
+}
+
+// ---- the persistent kernel ----------------------------------------------------------------------------
+template <int VAR>
+__global__ void __launch_bounds__(kThreads) push_persistent(const PushArgs a) {
+    __shared__ PushSmem sm;
+    PushCtrl *c = a.ctrl;
+    if (threadIdx.x == 0) { sm.stage_cnt = 0; sm.abort_flag = 0; }
+    __syncthreads();
+    unsigned gen = 0;
+    unsigned long long edges_acc = 0, pops_acc = 0, hubs_acc = 0;
+    const int level0 = __ldcg(&c->level);
+    uint32_t it = 0;
+    const int nphases = a.init_mode ? 1 : 2;
+    bool alive = true;
+    for (int phase = 0; phase < nphases && alive; ++phase) {
+        seed_pass(a, sm, phase, a.q[it & 1], &c->cnt[it % 3]);
+        if (!(alive = grid_barrier(c, gen, sm))) break;
+        while (true) {
+            const uint32_t n = __ldcg(&c->cnt[it % 3]);
+            const uint32_t nh = __ldcg(&c->hcnt[(it + 2) % 3]);
+            if (n == 0 && nh == 0) break;
+            if ((int)it >= a.max_iters) {
+                if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&c->errflags, kErrWatchdog);
+                alive = false;
+                break;
+            }
+            if (blockIdx.x == 0 && threadIdx.x == 0) {  // slots nobody reads or writes during this iteration
+                c->cnt[(it + 2) % 3] = 0;
+                c->hcnt[(it + 1) % 3] = 0;
+                pops_acc += n;
+                hubs_acc += nh;
+            }
+            const int level = level0 + (int)it + 1;
+            const unsigned long long *qin = a.q[it & 1];
+            unsigned long long *qout = a.q[(it + 1) & 1];
+            if (VAR != 0) {
+                pre_pass<VAR>(a, qin, a.qr[it & 1], n, level);
+                if (!(alive = grid_barrier(c, gen, sm))) break;
+            }
+            expand_hubs<VAR>(a, sm, a.hub[(it + 1) & 1], nh, qout, &c->cnt[(it + 1) % 3], phase, level, edges_acc);
+            expand_tiles<VAR>(a, sm, qin, a.qr[it & 1], n, qout, &c->cnt[(it + 1) % 3], a.hub[it & 1],
+                              &c->hcnt[it % 3], phase, level, edges_acc);
+            if (VAR == 2) {
+                if (!(alive = grid_barrier(c, gen, sm))) break;
+                post_pass(a, sm, qin, a.qr[it & 1], n, qout, &c->cnt[(it + 1) % 3], phase);
+            }
+            if (!(alive = grid_barrier(c, gen, sm))) break;
+            ++it;
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (edges_acc) atomicAdd(&c->edges, edges_acc);
+        if (blockIdx.x == 0) {
+            c->iters = it;
+            c->pops = pops_acc;
+            c->hubs = hubs_acc;
+            c->level = level0 + (int)it + 2;
+        }
+    }
+}
+
+// ---- stepwise mode: the same device functions, one launch per sub-pass ----------------------------------
+__global__ void __launch_bounds__(kThreads) push_step_seed(const PushArgs a, uint32_t it, int phase) {
+    __shared__ PushSmem sm;
+    if (threadIdx.x == 0) { sm.stage_cnt = 0; sm.abort_flag = 0; }
+    __syncthreads();
+    seed_pass(a, sm, phase, a.q[it & 1], &a.ctrl->cnt[it % 3]);
+}
+
+template <int VAR>
+__global__ void __launch_bounds__(kThreads) push_step_pre(const PushArgs a, uint32_t it, int level) {
+    pre_pass<VAR>(a, a.q[it & 1], a.qr[it & 1], a.ctrl->cnt[it % 3], level);
+}
+
+template <int VAR>
+__global__ void __launch_bounds__(kThreads) push_step_expand(const PushArgs a, uint32_t it, int phase, int level) {
+    __shared__ PushSmem sm;
+    if (threadIdx.x == 0) { sm.stage_cnt = 0; sm.abort_flag = 0; }
+    __syncthreads();
+    PushCtrl *c = a.ctrl;
+    const uint32_t n = c->cnt[it % 3], nh = c->hcnt[(it + 2) % 3];
+    unsigned long long edges_acc = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        c->cnt[(it + 2) % 3] = 0;
+        c->hcnt[(it + 1) % 3] = 0;
+        c->pops += n;
+        c->hubs += nh;
+        c->iters += 1;
+    }
+    expand_hubs<VAR>(a, sm, a.hub[(it + 1) & 1], nh, a.q[(it + 1) & 1], &c->cnt[(it + 1) % 3], phase, level, edges_acc);
+    expand_tiles<VAR>(a, sm, a.q[it & 1], a.qr[it & 1], n, a.q[(it + 1) & 1], &c->cnt[(it + 1) % 3], a.hub[it & 1],
+                      &c->hcnt[it % 3], phase, level, edges_acc);
+    if (threadIdx.x == 0 && edges_acc) atomicAdd(&c->edges, edges_acc);
+}
+
+__global__ void __launch_bounds__(kThreads) push_step_post(const PushArgs a, uint32_t it, int phase) {
+    __shared__ PushSmem sm;
+    if (threadIdx.x == 0) { sm.stage_cnt = 0; sm.abort_flag = 0; }
+    __syncthreads();
+    post_pass(a, sm, a.q[it & 1], a.qr[it & 1], a.ctrl->cnt[it % 3], a.q[(it + 1) & 1], &a.ctrl->cnt[(it + 1) % 3], phase);
+}
+
+// ---- state initialisation (gpu/PPRCommon.cuh:13-22) ------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    state_init(double *__restrict__ p, double *__restrict__ r, int32_t *__restrict__ status, int64_t Vp, int S,
+               const int32_t *__restrict__ src) {
+    const int64_t total = Vp * S;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        const int s = (int)(i / Vp);
+        const int64_t v = i - (int64_t)s * Vp;
+        p[i] = 0.0;
+        r[i] = (v == src[s]) ? 1.0 : 0.0;
+        if (status) status[i] = -1;
+    }
+}
+
+}  // namespace dppr

@@ -1,0 +1,297 @@
+// window.cuh -- device-resident sliding-window graph (north-star subsystem 1).
+//
+// Replaces gpu/SlidingGraphBuilder.cuh, which after EVERY batch shifts the whole arrival-order
+// edge list and rebuilds the in-CSR by a comparator sort of all E_w window edges
+// (:163-181, :203-221) and recounts every out-degree (:193-201).  Here the update is O(batch):
+//
+//   * `log`   : the W window edges in arrival order, kept as a RING (no shifting).  The B edges
+//               that expire are exactly the B ring slots the arriving edges overwrite.
+//   * in-adjacency: one FIFO ring per vertex inside a pooled slot array.  A window slides in
+//               stream order, so per vertex the expiring in-edges are always the oldest ones:
+//               expire = advance `head`, insert = append at `head+len`.  VMeta{base,head,len,cap}
+//               is one 16-byte load per frontier pop; cap is a power of two (ring index = mask).
+//               A ring that fills up moves to a fresh, larger slot range (amortised doubling).
+//   * out-degree: plain int32 per vertex (the reference only ever uses row_ptr differences,
+//               gpu/ExpandRev.cuh:71, gpu/StreamUpdate.cuh:13).
+//
+// Determinism: the batch's directed entries are radix-sorted by vertex (stable => stream order
+// within a vertex), run-length encoded, and every per-vertex quantity is then written by exactly
+// one thread.  No order-dependent atomic touches the graph, which is what makes the exported
+// canonical CSR bit-exact with the reference's (gpu/PPRRevPushGPU.cuh:45-90).
+#pragma once
+#include "common.cuh"
+
+namespace dppr {
+
+enum : int {
+    kErrPool = 1, kErrQueue = 2, kErrHubQ = 4, kErrWatchdog = 8, kErrUnderflow = 16, kErrBadId = 32
+};
+
+struct VMeta {            // layout-compatible with uint4
+    uint32_t base, head, len, cap;
+};
+
+struct RelocJob {
+    uint32_t old_base, old_head, old_cap, len, new_base, pad;
+};
+
+struct WindowView {
+    int32_t V;
+    uint4 *vmeta;
+    int32_t *pool;
+    int32_t *outdeg;
+    unsigned long long *pool_top;
+    unsigned long long pool_cap;
+    int *errflags;
+};
+
+__host__ __device__ __forceinline__ uint32_t next_pow2_u32(uint32_t x) {
+    if (x <= 1) return 1;
+    --x;
+    x |= x >> 1; x |= x >> 2; x |= x >> 4; x |= x >> 8; x |= x >> 16;
+    return x + 1;
+}
+// capacity policy: 12.5% headroom, at least 4 slots, power of two
+__host__ __device__ __forceinline__ uint32_t ring_capacity_for(uint32_t need) {
+    uint32_t c = next_pow2_u32(need + (need >> 3));
+    return c < 4u ? 4u : c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// initial window: entries (dst, src) in stream order + degree histograms
+// (replaces InitWindowStream + BuildInGraph, gpu/SlidingGraphBuilder.cuh:182-192,145-160)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    win_init_entries(const int2 *__restrict__ log, int64_t W, int directed, int32_t V, uint32_t *__restrict__ key,
+                     uint32_t *__restrict__ val, uint32_t *__restrict__ indeg, int32_t *__restrict__ outdeg,
+                     int *errflags) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < W; i += (int64_t)gridDim.x * kThreads) {
+        int2 e = log[i];
+        if ((uint32_t)e.x >= (uint32_t)V || (uint32_t)e.y >= (uint32_t)V) {
+            atomicOr(errflags, kErrBadId);
+            e.x = 0; e.y = 0;
+        }
+        if (directed) {
+            key[i] = (uint32_t)e.y; val[i] = (uint32_t)e.x;
+            atomicAdd(&indeg[e.y], 1u);
+            atomicAdd(&outdeg[e.x], 1);
+        } else {  // mirrored at load (SlidingGraphVec.h:84-90); same interleaving as the host push_back order
+            key[2 * i] = (uint32_t)e.y; val[2 * i] = (uint32_t)e.x;
+            key[2 * i + 1] = (uint32_t)e.x; val[2 * i + 1] = (uint32_t)e.y;
+            atomicAdd(&indeg[e.y], 1u); atomicAdd(&indeg[e.x], 1u);
+            atomicAdd(&outdeg[e.x], 1); atomicAdd(&outdeg[e.y], 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    win_init_caps(const uint32_t *__restrict__ indeg, uint32_t *__restrict__ caps, int32_t V) {
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < V; v += (int64_t)gridDim.x * kThreads)
+        caps[v] = indeg[v] ? ring_capacity_for(indeg[v]) : 0u;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    win_init_meta(const uint32_t *__restrict__ indeg, const uint32_t *__restrict__ caps,
+                  const uint32_t *__restrict__ capbase, uint4 *__restrict__ vmeta, int32_t V) {
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < V; v += (int64_t)gridDim.x * kThreads)
+        vmeta[v] = make_uint4(capbase[v], 0u, indeg[v], caps[v]);
+}
+
+// sorted (dst, src) entries -> ring slots; rank within the row = i - rowptr[dst]
+__global__ void __launch_bounds__(kThreads)
+    win_init_fill(const uint32_t *__restrict__ key, const uint32_t *__restrict__ val, int64_t n,
+                  const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ capbase, int32_t *__restrict__ pool) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        const uint32_t d = key[i];
+        pool[capbase[d] + ((uint32_t)i - rowptr[d])] = (int32_t)val[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per batch: expiring + arriving edges -> directed entries (vertex key, (other << 1) | is_insert)
+// Entry order = reference EdgeBatch order (deletes then inserts, SlidingGraphVec.h:238-262) with
+// the two orientations of an undirected edge interleaved in stream order.
+//   directed  : group A keyed by dst (in-lists), group B keyed by src (out-degree + residual repair)
+//   undirected: the entry set is symmetric, one group keyed by u serves both roles
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    win_batch_entries(int2 *__restrict__ log, int64_t W, int64_t log_start, const int2 *__restrict__ arriving, int64_t B,
+                      int directed, int32_t V, uint32_t *__restrict__ akey, uint32_t *__restrict__ aval,
+                      uint32_t *__restrict__ bkey, uint32_t *__restrict__ bval, int *errflags) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < B; i += (int64_t)gridDim.x * kThreads) {
+        int64_t slot = log_start + i;
+        if (slot >= W) slot -= W;
+        const int2 old = log[slot];
+        int2 nw = arriving[i];
+        if ((uint32_t)nw.x >= (uint32_t)V || (uint32_t)nw.y >= (uint32_t)V) {
+            atomicOr(errflags, kErrBadId);
+            nw.x = 0; nw.y = 0;
+        }
+        log[slot] = nw;
+        if (directed) {
+            akey[i] = (uint32_t)old.y;     aval[i] = ((uint32_t)old.x << 1);
+            akey[B + i] = (uint32_t)nw.y;  aval[B + i] = ((uint32_t)nw.x << 1) | 1u;
+            bkey[i] = (uint32_t)old.x;     bval[i] = ((uint32_t)old.y << 1);
+            bkey[B + i] = (uint32_t)nw.x;  bval[B + i] = ((uint32_t)nw.y << 1) | 1u;
+        } else {
+            akey[2 * i] = (uint32_t)old.y;              aval[2 * i] = ((uint32_t)old.x << 1);
+            akey[2 * i + 1] = (uint32_t)old.x;          aval[2 * i + 1] = ((uint32_t)old.y << 1);
+            akey[2 * B + 2 * i] = (uint32_t)nw.y;       aval[2 * B + 2 * i] = ((uint32_t)nw.x << 1) | 1u;
+            akey[2 * B + 2 * i + 1] = (uint32_t)nw.x;   aval[2 * B + 2 * i + 1] = ((uint32_t)nw.y << 1) | 1u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// run-length encoding of the sorted entries.  Within a vertex's run the stable sort leaves all
+// deletes before all inserts, so a run is described by (start, first_insert, end).
+// ---------------------------------------------------------------------------------------------
+struct Segments {
+    uint32_t *vertex;      // [cap]   run -> vertex id
+    uint32_t *start;       // [cap+1] run -> first entry
+    uint32_t *first_ins;   // [cap]   run -> first insert entry (== end if none)
+    uint32_t *segof;       // [cap]   entry -> run
+    uint32_t *count;       // device scalar: number of runs
+};
+
+__global__ void __launch_bounds__(kThreads)
+    rle_heads(const uint32_t *__restrict__ key, int64_t n, uint32_t *__restrict__ flag) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+        flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
+}
+
+// `scanned` holds the exclusive scan of the head flags on entry and the run index on exit.
+__global__ void __launch_bounds__(kThreads)
+    rle_fill(const uint32_t *__restrict__ key, const uint32_t *__restrict__ val, int64_t n, Segments sg) {
+    uint32_t *scanned = sg.segof;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        const uint32_t k = key[i];
+        const bool head = (i == 0) || (key[i - 1] != k);
+        const bool last = (i == n - 1) || (key[i + 1] != k);
+        const uint32_t s = scanned[i] + (head ? 1u : 0u) - 1u;
+        const bool ins = val[i] & 1u;
+        if (head) {
+            sg.vertex[s] = k;
+            sg.start[s] = (uint32_t)i;
+        }
+        if (ins && (head || !(val[i - 1] & 1u))) sg.first_ins[s] = (uint32_t)i;
+        if (last && !ins) sg.first_ins[s] = (uint32_t)i + 1u;
+        if (i == n - 1) {
+            sg.start[s + 1] = (uint32_t)n;
+            *sg.count = s + 1u;
+        }
+        scanned[i] = s;  // each thread rewrites only its own slot, after reading it
+    }
+}
+
+// one thread per touched vertex: expire (advance head), reserve room for the inserts, grow the ring
+__global__ void __launch_bounds__(kThreads)
+    win_plan(Segments sg, WindowView w, uint32_t *__restrict__ ins_pos, RelocJob *__restrict__ jobs, uint32_t *njobs) {
+    const uint32_t nseg = *sg.count;
+    for (uint32_t s = blockIdx.x * kThreads + threadIdx.x; s < nseg; s += gridDim.x * kThreads) {
+        const uint32_t v = sg.vertex[s];
+        const uint32_t st = sg.start[s], fi = sg.first_ins[s], en = sg.start[s + 1];
+        uint32_t ndel = fi - st;
+        const uint32_t nins = en - fi;
+        uint4 q = w.vmeta[v];
+        VMeta m{q.x, q.y, q.z, q.w};
+        if (ndel > m.len) {  // the caller slid edges the window never held
+            atomicOr(w.errflags, kErrUnderflow);
+            ndel = m.len;
+        }
+        if (ndel) {
+            m.head = (m.head + ndel) & (m.cap - 1u);
+            m.len -= ndel;
+        }
+        uint32_t pos = m.len;
+        if (nins) {
+            const uint32_t need = m.len + nins;
+            if (need > m.cap) {
+                const uint32_t ncap = ring_capacity_for(need);
+                const unsigned long long nb = atomicAdd(w.pool_top, (unsigned long long)ncap);
+                if (nb + ncap > w.pool_cap) {
+                    atomicOr(w.errflags, kErrPool);
+                    pos = 0xffffffffu;  // inserts of this run are dropped; engine is flagged unhealthy
+                } else {
+                    if (m.len) {
+                        const uint32_t j = atomicAdd(njobs, 1u);
+                        jobs[j] = RelocJob{m.base, m.head, m.cap, m.len, (uint32_t)nb, 0u};
+                    }
+                    m.base = (uint32_t)nb;
+                    m.head = 0u;
+                    m.cap = ncap;
+                }
+            }
+            if (pos != 0xffffffffu) m.len += nins;
+        }
+        ins_pos[s] = pos;
+        w.vmeta[v] = make_uint4(m.base, m.head, m.len, m.cap);
+    }
+}
+
+// one CTA per relocated ring (grid-stride over jobs)
+__global__ void __launch_bounds__(kThreads)
+    win_relocate(const RelocJob *__restrict__ jobs, const uint32_t *__restrict__ njobs, int32_t *__restrict__ pool) {
+    const uint32_t n = *njobs;
+    for (uint32_t j = blockIdx.x; j < n; j += gridDim.x) {
+        const RelocJob jb = jobs[j];
+        for (uint32_t k = threadIdx.x; k < jb.len; k += kThreads)
+            pool[jb.new_base + k] = pool[jb.old_base + ((jb.old_head + k) & (jb.old_cap - 1u))];
+    }
+}
+
+// one thread per entry: inserts take slot head + (len before inserts) + rank within the run
+__global__ void __launch_bounds__(kThreads)
+    win_insert(const uint32_t *__restrict__ key, const uint32_t *__restrict__ val, int64_t n, Segments sg,
+               const uint32_t *__restrict__ ins_pos, WindowView w) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        const uint32_t x = val[i];
+        if (!(x & 1u)) continue;
+        const uint32_t s = sg.segof[i];
+        const uint32_t pos = ins_pos[s];
+        if (pos == 0xffffffffu) continue;
+        const uint4 m = w.vmeta[key[i]];
+        const uint32_t rank = (uint32_t)i - sg.first_ins[s];
+        w.pool[m.x + ((m.y + pos + rank) & (m.w - 1u))] = (int32_t)(x >> 1);
+    }
+}
+
+// out-degree side (group keyed by src): remember the pre-batch degree for the repair, store the new one
+__global__ void __launch_bounds__(kThreads)
+    win_out_degrees(Segments sg, int32_t *__restrict__ outdeg, int32_t *__restrict__ seg_d0) {
+    const uint32_t nseg = *sg.count;
+    for (uint32_t s = blockIdx.x * kThreads + threadIdx.x; s < nseg; s += gridDim.x * kThreads) {
+        const uint32_t u = sg.vertex[s];
+        const uint32_t st = sg.start[s], fi = sg.first_ins[s], en = sg.start[s + 1];
+        const int32_t d0 = outdeg[u];
+        seg_d0[s] = d0;
+        outdeg[u] = d0 + (int32_t)(en - fi) - (int32_t)(fi - st);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// export (test / validation path): ring contents -> (dst, src) entries
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    win_export_len(const uint4 *__restrict__ vmeta, uint32_t *__restrict__ len, int32_t V) {
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < V; v += (int64_t)gridDim.x * kThreads)
+        len[v] = vmeta[v].z;
+}
+
+// one warp per vertex
+__global__ void __launch_bounds__(kThreads)
+    win_export_entries(const uint4 *__restrict__ vmeta, const int32_t *__restrict__ pool,
+                       const uint32_t *__restrict__ rowptr, uint32_t *__restrict__ key, uint32_t *__restrict__ val,
+                       int32_t V) {
+    const int64_t warps = (int64_t)gridDim.x * kWarps;
+    for (int64_t v = (int64_t)blockIdx.x * kWarps + warp_id(); v < V; v += warps) {
+        const uint4 m = vmeta[v];
+        const uint32_t o = rowptr[v];
+        for (uint32_t k = lane_id(); k < m.z; k += 32) {
+            key[o + k] = (uint32_t)v;
+            val[o + k] = (uint32_t)pool[m.x + ((m.y + k) & (m.w - 1u))];
+        }
+    }
+}
+
+}  // namespace dppr

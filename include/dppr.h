@@ -1,0 +1,172 @@
+/* dppr.h -- C ABI of the B200-native streaming reverse-push PPR engine.
+ *
+ * This is the drop-in boundary for the hot path of guowentian/dynamicppr.
+ * The reference has no FFI layer; what `gpu/PPRGPUMain.cu` calls is a C++ class surface
+ * (PPRGPU / PPRRevPushGPU{,FF,Eager,Vanilla}, SlidingGraphBuilder, DeviceMemory).  Every entry
+ * point below names the reference interface it replaces (file:line relative to the reference
+ * root).  Plain C types only: pointers, sizes, an opaque handle.  No exceptions, no exit() and
+ * no torch types cross this boundary; every function returns 0 on success or a DPPR_E_* code,
+ * with text available from dppr_last_error().
+ *
+ * Ownership: the engine owns every device allocation (reference: DeviceMemory owns all arrays,
+ * gpu/DeviceMemory.cuh:9-135).  Host pointers passed in are borrowed for the duration of the
+ * call only (they are staged into pinned memory before the call returns).
+ * Threading: one handle = one GPU = one CUDA stream; a handle is not thread-safe; distinct
+ * handles may be driven from distinct host threads or processes (one process per GPU is how
+ * bench.py shards sources).
+ * Asynchrony: dppr_slide*, dppr_apply_batch* and dppr_refresh only enqueue work; call
+ * dppr_sync() (or any dppr_get_* / dppr_export_* call, which synchronise) before reading
+ * results on the host.
+ */
+#ifndef DPPR_H
+#define DPPR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPPR_VERSION 100
+
+enum {
+    DPPR_OK = 0,
+    DPPR_E_INVALID = 1,   /* bad argument / configuration (reference: ArgumentsChecker, Arguments.h:42-64) */
+    DPPR_E_CUDA = 2,      /* CUDA runtime failure (reference: CUDA_ERROR prints + exit(-1), gpu/GPUUtil.cuh:7-19) */
+    DPPR_E_STATE = 3,     /* call out of order (e.g. slide before init_window) */
+    DPPR_E_CAPACITY = 4,  /* adjacency pool / frontier queue exhausted -- enlarge via dppr_config */
+    DPPR_E_NODEVICE = 5   /* no usable CUDA device: there is NO CPU fallback */
+};
+
+/* the four push variants of the reference CLI flag -o (Meta.h:11-17) */
+enum { DPPR_OPTIMIZED = 0, DPPR_FAST_FRONTIER = 1, DPPR_EAGER = 2, DPPR_VANILLA = 3 };
+
+/* how the push loop is driven */
+enum {
+    DPPR_ENGINE_PERSISTENT = 0, /* one cooperative kernel per refresh, device-side loop + grid barrier */
+    DPPR_ENGINE_STEPWISE = 1    /* one launch per push iteration, host reads the frontier count
+                                   (the reference's structure, gpu/PPRRevPushGPU.cuh:97-131) */
+};
+
+typedef struct dppr_engine dppr_engine;
+
+typedef struct dppr_config {
+    int32_t vertex_count;       /* V: first int32 of the .bin file (SlidingGraphVec.h:42) */
+    int32_t directed;           /* -i: 1 directed, 0 undirected (edges mirrored on device) */
+    int64_t window_edges;       /* W: stream edges in the window (SlidingGraphVec.h:48) */
+    int64_t max_batch_edges;    /* largest B that will be passed to dppr_slide / dppr_apply_batch */
+    double alpha;               /* teleport probability; the reference fixes 0.15 (Meta.h:31). <=0 -> 0.15 */
+    double epsilon;             /* -e: residual tolerance (Arguments.h:83). <=0 -> 1e-9 */
+    int32_t variant;            /* -o: DPPR_OPTIMIZED .. DPPR_VANILLA */
+    int32_t device;             /* CUDA device ordinal */
+    int32_t n_sources;          /* >=1; one (p, r) pair per source, all sharing the window graph */
+    const int32_t *sources;     /* n_sources vertex ids (-s; the reference runs one per process) */
+    int32_t engine_mode;        /* DPPR_ENGINE_* */
+    int32_t record_timing;      /* 1: bracket every batch phase with CUDA events (see dppr_batch_stats) */
+    double pool_factor;         /* adjacency pool slots per window CSR entry; <=0 -> default (8.0) */
+    int64_t frontier_capacity;  /* (source, vertex) items per frontier queue; <=0 -> default */
+    int32_t hub_degree;         /* in-degree at/above which a vertex is expanded grid-wide; <=0 -> 4096 */
+    int32_t reserved0;
+} dppr_config;
+
+typedef struct dppr_batch_stats {
+    int64_t batch_index;        /* 0 = initial solve, k = k-th slide */
+    int64_t edges;              /* B stream edges slid in this batch */
+    int64_t batch_entries;      /* N_b = 2*D*B directed insert/delete entries */
+    int64_t touched_vertices;   /* distinct u whose residual was repaired (seed candidates) */
+    int64_t iterations;         /* push iterations, both phases */
+    int64_t frontier_pops;      /* F: (source, vertex) pops */
+    int64_t traversed_edges;    /* T: in-edges traversed = FP64 atomics issued */
+    int64_t hub_pops;           /* pops expanded grid-wide */
+    int64_t relocations;        /* adjacency rings moved to a larger slot range in this batch */
+    int64_t pool_used;          /* adjacency pool high-water mark (slots) */
+    float ms_upload;            /* H2D of the batch (0 for device-resident input) */
+    float ms_window;            /* device window update (sort + expire + insert) */
+    float ms_repair;            /* residual repair   } reference "ppr_time" = ms_repair + ms_push */
+    float ms_push;              /* both push phases  } (gpu/PPRGPU.cuh:128-163)                    */
+    int32_t error_flags;        /* device-side DPPR_DEVERR_* bits, 0 when healthy */
+    int32_t reserved0;
+} dppr_batch_stats;
+
+enum {
+    DPPR_DEVERR_POOL = 1,       /* adjacency pool exhausted */
+    DPPR_DEVERR_QUEUE = 2,      /* frontier queue overflow */
+    DPPR_DEVERR_HUBQ = 4,       /* hub list overflow */
+    DPPR_DEVERR_WATCHDOG = 8,   /* grid barrier / iteration watchdog fired */
+    DPPR_DEVERR_UNDERFLOW = 16  /* expiry of an edge the window does not hold (caller broke FIFO order) */
+};
+
+int dppr_version(void);
+/* text of the last failure on this handle (or of the last failed dppr_create when e == NULL) */
+const char *dppr_last_error(const dppr_engine *e);
+
+/* Replaces: new PPRRevPushGPU*(graph) -- PPRGPU::PPRGPU (gpu/PPRGPU.cuh:23-34), DeviceMemory
+ * allocation (gpu/DeviceMemory.cuh:52-74), new SlidingGraphBuilder (gpu/SlidingGraphBuilder.cuh:64-76)
+ * and the variant choice of gpu/PPRGPUMain.cu:24-27. */
+int dppr_create(const dppr_config *cfg, dppr_engine **out);
+void dppr_destroy(dppr_engine *e);
+
+/* Replaces: SlidingGraphBuilder::InitWindowStream (gpu/SlidingGraphBuilder.cuh:182-192) +
+ * DeviceMemory::CudaMemcpyGraph/CudaMemcpyRowPtr (gpu/DeviceMemory.cuh:76-108): loads the first W
+ * stream edges and builds the device-resident window graph.  SoA form mirrors EdgeBatch
+ * (EdgeBatch.h:6-30); the pairs form takes the .bin payload as it lies in the file. */
+int dppr_init_window(dppr_engine *e, const int32_t *edge1, const int32_t *edge2, int64_t n);
+int dppr_init_window_pairs(dppr_engine *e, const int32_t *pairs, int64_t n);
+
+/* Replaces: Init<<<>>> + ExecuteMainLoop(0) of PPRGPU::DynamicExecute (gpu/PPRGPU.cuh:84-89):
+ * r[s]=1, p=0, push phase 0 to exhaustion on the initial window, for every source. */
+int dppr_solve_initial(dppr_engine *e);
+
+/* Replaces: GPUEdgeBatch::CudaMemcpy (gpu/GPUEdgeBatch.cuh:20-26) + GPUBuildSlidingGraph ->
+ * SlidingGraphBuilder::IncBuildInGraph (gpu/PPRRevPushGPU.cuh:38-44, gpu/SlidingGraphBuilder.cuh:117-133).
+ * Takes only the B ARRIVING edges (the reference's `new_stream`, SlidingGraphVec.h:226-236); the B
+ * expiring edges are read from the device's own arrival-order ring.  O(B) work, no re-sort of the window. */
+int dppr_apply_batch(dppr_engine *e, const int32_t *new_edge1, const int32_t *new_edge2, int64_t B);
+int dppr_apply_batch_pairs(dppr_engine *e, const int32_t *pairs, int64_t B);
+/* same, input already resident in device memory (B x int32 pairs) */
+int dppr_apply_batch_device_pairs(dppr_engine *e, const int32_t *device_pairs, int64_t B);
+
+/* Replaces: IncrementalBatchUpdate + ExecuteMainLoop(0) + ExecuteMainLoop(1), the region the reference
+ * times as ppr_time (gpu/PPRGPU.cuh:128-163; kernels gpu/StreamUpdate.cuh, Inspect.cuh, ExpandRev.cuh). */
+int dppr_refresh(dppr_engine *e);
+
+/* apply_batch + refresh: one streaming step (body of SlidingWindowExecuteMainLoop, gpu/PPRGPU.cuh:109-169) */
+int dppr_slide(dppr_engine *e, const int32_t *new_edge1, const int32_t *new_edge2, int64_t B);
+int dppr_slide_pairs(dppr_engine *e, const int32_t *pairs, int64_t B);
+int dppr_slide_device_pairs(dppr_engine *e, const int32_t *device_pairs, int64_t B);
+
+int dppr_sync(dppr_engine *e);
+
+/* stats of batch `batch_index` (0 = initial solve); -1 = most recent.  Synchronises. */
+int dppr_get_batch_stats(dppr_engine *e, int64_t batch_index, dppr_batch_stats *out);
+int64_t dppr_batches_done(const dppr_engine *e);
+
+/* Replaces: the cudaMemcpy D2H of pagerank / residual in ValidateResult (gpu/PPRRevPushGPU.cuh:134-139).
+ * out has V doubles.  Synchronises. */
+int dppr_get_estimates(dppr_engine *e, int32_t source_index, double *out);
+int dppr_get_residuals(dppr_engine *e, int32_t source_index, double *out);
+/* device-to-device copy of one estimate vector into caller-owned device memory (for the final
+ * NCCL gather done by the caller; there is no collective on the hot path). */
+int dppr_copy_estimates_device(dppr_engine *e, int32_t source_index, void *device_out);
+
+/* Canonical window graph, the object the reference validator compares
+ * (gpu/PPRRevPushGPU.cuh:45-90): in_row_ptr[V+1], in_col_ind[E_w] with rows ascending and duplicates
+ * kept, out_deg[V] (reference row_ptr differences).  Any pointer may be NULL.  Test/export path:
+ * sorts on the device; not part of the hot path. */
+int dppr_export_window_csr(dppr_engine *e, int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_deg);
+int64_t dppr_window_csr_entries(const dppr_engine *e); /* E_w = D*W */
+
+/* ---- test hooks (used by tests/ only) ---------------------------------------------------- */
+/* overwrite (p, r) of one source (V doubles each; either may be NULL) */
+int dppr_set_state(dppr_engine *e, int32_t source_index, const double *p, const double *r);
+/* residual repair only (no push): the closed form checked against the sequential oracle */
+int dppr_repair_only(dppr_engine *e);
+/* stable LSD radix sort of (key, value) pairs on the device, host in / host out */
+int dppr_test_sort_pairs(int32_t device, uint32_t *keys, uint32_t *vals, int64_t n, int32_t key_bits);
+/* exclusive prefix sum on the device, host in / host out; returns the total in *total */
+int dppr_test_exclusive_scan(int32_t device, uint32_t *data, int64_t n, uint64_t *total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPPR_H */
