@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "dppr_slide_device_pairs", "dppr_sync", "dppr_get_batch_stats", "dppr_batches_done",
     "dppr_get_estimates", "dppr_get_residuals", "dppr_copy_estimates_device", "dppr_export_window_csr",
     "dppr_window_csr_entries", "dppr_set_state", "dppr_repair_only", "dppr_test_sort_pairs",
-    "dppr_test_exclusive_scan",
+    "dppr_test_exclusive_scan", "dppr_debug_iterlog", "dppr_debug_ctalog",
 ]
 
 
@@ -93,6 +93,8 @@ def load_library():
     L.dppr_window_csr_entries.argtypes = [vp]; L.dppr_window_csr_entries.restype = C.c_int64
     L.dppr_set_state.argtypes = [vp, C.c_int32, f64p, f64p]
     L.dppr_repair_only.argtypes = [vp]
+    L.dppr_debug_ctalog.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_int32)]
+    L.dppr_debug_iterlog.argtypes = [vp, C.POINTER(C.c_uint32), C.c_int32, C.POINTER(C.c_int32)]
     L.dppr_test_sort_pairs.argtypes = [C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int64, C.c_int32]
     L.dppr_test_exclusive_scan.argtypes = [C.c_int32, C.POINTER(C.c_uint32), C.c_int64, C.POINTER(C.c_uint64)]
     _LIB = L
@@ -225,6 +227,20 @@ class DynamicPPR:
         rp = np.empty(self.V + 1, np.int32); ci = np.empty(max(E, 1), np.int32); od = np.empty(self.V, np.int32)
         self._check(self.L.dppr_export_window_csr(self.h, _i32(rp), _i32(ci), _i32(od)))
         return rp, ci[:E], od
+
+    def iterlog(self, cap=4096):
+        """debug (needs DPPR_ITERLOG=1 at construction): rows (frontier, hub_chunks, t_ns) per push iteration"""
+        buf = np.zeros((cap, 4), np.uint32)
+        n = C.c_int32(0)
+        self._check(self.L.dppr_debug_iterlog(self.h, buf.ctypes.data_as(C.POINTER(C.c_uint32)), cap, C.byref(n)))
+        b = buf[: n.value].astype(np.uint64)
+        return np.stack([b[:, 0], b[:, 1], b[:, 2] | (b[:, 3] << np.uint64(32))], axis=1)
+
+    def ctalog(self, cap=148 * 16):
+        buf = np.zeros((cap, 8), np.uint64)
+        n = C.c_int32(0)
+        self._check(self.L.dppr_debug_ctalog(self.h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(n)))
+        return buf[: n.value]
 
     def set_state(self, source_index, p=None, r=None):
         f64p = C.POINTER(C.c_double)

@@ -141,6 +141,14 @@ int dppr_repair_only(dppr_engine *e) {
     return guarded(e, [&](dppr::Engine &g) { g.refresh(true); });
 }
 
+int dppr_debug_iterlog(dppr_engine *e, uint32_t *out, int32_t cap, int32_t *n_out) {
+    return guarded(e, [&](dppr::Engine &g) { *n_out = g.get_iterlog(out, cap); });
+}
+
+int dppr_debug_ctalog(dppr_engine *e, unsigned long long *out, int32_t cap_rows, int32_t *n_out) {
+    return guarded(e, [&](dppr::Engine &g) { *n_out = g.get_ctalog(out, cap_rows); });
+}
+
 // ---- primitive test hooks ------------------------------------------------------------------------
 int dppr_test_sort_pairs(int32_t device, uint32_t *keys, uint32_t *vals, int64_t n, int32_t key_bits) {
     using namespace dppr;

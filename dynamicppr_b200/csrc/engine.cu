@@ -55,7 +55,7 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     if (cfg_.alpha >= 1.0) throw InvalidArgument("alpha must be in (0, 1)");
     if (cfg_.epsilon <= 0.0) cfg_.epsilon = 1e-9;
     if (cfg_.pool_factor <= 0.0) cfg_.pool_factor = 8.0;
-    if (cfg_.hub_degree <= 0) cfg_.hub_degree = 4096;
+    if (cfg_.hub_degree <= 0) cfg_.hub_degree = kHubChunk;
     V_ = cfg.vertex_count;
     D_ = cfg.directed ? 1 : 2;
     W_ = cfg.window_edges;
@@ -151,6 +151,11 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     ctrl_.alloc(1);
     DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, sizeof(PushCtrl), st_));
     dev_record_.alloc(1);
+    if (env_int("DPPR_ITERLOG", 0)) {
+        iterlog_.alloc(kIterLogCap);
+        ctalog_.alloc((size_t)8 * 148 * 16);
+        DPPR_CUDA(cudaMemsetAsync(ctalog_.ptr, 0, ctalog_.bytes(), st_));
+    }
     for (int i = 0; i < kStageSlots; ++i) {
         hstage_[i].alloc((size_t)std::max<int64_t>(Bmax_, 1));
         DPPR_CUDA(cudaEventCreateWithFlags(&hstage_free_[i], cudaEventDisableTiming));
@@ -283,6 +288,10 @@ void Engine::launch_push(bool init_mode) {
     a.hub_degree = cfg_.hub_degree;
     a.init_mode = init_mode ? 1 : 0;
     a.max_iters = env_int("DPPR_MAX_ITERS", 400000);
+    a.iterlog = iterlog_.ptr;
+    a.iterlog_cap = iterlog_.ptr ? kIterLogCap : 0;
+    a.ctalog = ctalog_.ptr;
+    a.probe_iter = env_int("DPPR_PROBE_ITER", 10);
     if (cfg_.engine_mode == DPPR_ENGINE_STEPWISE) {
         launch_push_stepwise(a);
         return;
@@ -307,11 +316,16 @@ void Engine::launch_push_stepwise(PushArgs &a) {
     PushCtrl h{};
     const int nphases = a.init_mode ? 1 : 2;
     for (int phase = 0; phase < nphases; ++phase) {
+        if (phase > 0) {  // same slot hygiene as push_persistent at a phase change
+            DPPR_CUDA(cudaMemsetAsync(&ctrl_.ptr->cnt[(it + 2) % 3], 0, sizeof(unsigned), st_));
+            DPPR_CUDA(cudaMemsetAsync(&ctrl_.ptr->hpk[(it + 1) % 3], 0, sizeof(unsigned long long), st_));
+            ++it;
+        }
         push_step_seed<<<grid, kThreads, 0, st_>>>(a, it, phase);
         while (true) {
             DPPR_CUDA(cudaMemcpyAsync(&h, ctrl_.ptr, sizeof(PushCtrl), cudaMemcpyDeviceToHost, st_));
             DPPR_CUDA(cudaStreamSynchronize(st_));
-            if (h.cnt[it % 3] == 0 && h.hcnt[(it + 2) % 3] == 0) break;
+            if (h.cnt[it % 3] == 0 && h.hpk[(it + 2) % 3] == 0) break;
             if ((int)it >= a.max_iters) throw CapacityError("push did not converge within DPPR_MAX_ITERS iterations");
             const int level = step_level_ + (int)it + 1;
             switch (var) {
@@ -523,6 +537,23 @@ void Engine::set_state(int32_t s, const double *p, const double *r) {
     if (r) DPPR_CUDA(cudaMemcpy(r_.ptr + (size_t)s * Vp_, r, sizeof(double) * (size_t)V_, cudaMemcpyHostToDevice));
     solved_ = true;
     if (meta_.empty()) meta_.emplace_back();
+}
+
+int Engine::get_iterlog(uint32_t *out, int cap) {
+    if (!iterlog_.ptr || meta_.empty()) return 0;
+    sync();
+    const BatchRecord *rec = record_slot(meta_.size() - 1);
+    int n = (int)std::min<unsigned long long>(rec->ctrl.iters, (unsigned long long)std::min(cap, kIterLogCap));
+    if (n > 0) DPPR_CUDA(cudaMemcpy(out, iterlog_.ptr, sizeof(uint4) * (size_t)n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+int Engine::get_ctalog(unsigned long long *out, int cap_rows) {
+    if (!ctalog_.ptr) return 0;
+    sync();
+    int rows = std::min(cap_rows, coop_grid_[cfg_.variant]);
+    DPPR_CUDA(cudaMemcpy(out, ctalog_.ptr, sizeof(unsigned long long) * 8 * (size_t)rows, cudaMemcpyDeviceToHost));
+    return rows;
 }
 
 // canonical CSR: rows ascending, duplicates kept.  Device sort, test/validation path.

@@ -45,6 +45,8 @@ public:
     void set_state(int32_t source_index, const double *p, const double *r);
     void export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_deg);
     int64_t csr_entries() const { return Ew_; }
+    int get_iterlog(uint32_t *out, int cap);
+    int get_ctalog(unsigned long long *out, int cap_rows);  // debug: 8 stamps per CTA of the probed iteration  // debug: 4 uint32 per iteration of the last refresh
 
     std::string last_error;
 
@@ -104,6 +106,9 @@ private:
     uint32_t qcap_ = 0, hcap_ = 0;
     DevBuf<PushCtrl> ctrl_;
     DevBuf<BatchRecord> dev_record_;
+    DevBuf<uint4> iterlog_;
+    DevBuf<unsigned long long> ctalog_;
+    static constexpr int kIterLogCap = 4096;
     // host staging
     static constexpr int kStageSlots = 4;
     PinnedBuf<int2> hstage_[kStageSlots];

@@ -43,14 +43,18 @@
 namespace dppr {
 
 constexpr int kStage = 1024;            // staged next-frontier items per CTA
-constexpr int kHubChunk = 4 * kThreads; // edges of a hub one CTA takes at a time
+#ifndef DPPR_MIN_BLOCKS
+#define DPPR_MIN_BLOCKS 4
+#endif
+constexpr int kEdgeUnroll = 4;          // in-edges per thread per round: independent load/atomic chains in flight
+constexpr int kHubChunk = kEdgeUnroll * kThreads;  // edges of a hub one CTA takes at a time
+constexpr int kHubSmem = 1024;          // hub chunk offsets cached in shared memory for the owner search
 
 // device-resident control block.  [0, kCtrlZeroBytes) is cleared before every refresh.
 struct PushCtrl {
     unsigned int cnt[3];    // frontier sizes, slot it % 3 is consumed in iteration `it`
-    unsigned int hcnt[3];   // hub list sizes, slot it % 3 is produced in iteration `it`
     unsigned int bar;       // grid barrier arrivals (monotone within a launch)
-    unsigned int pad0;
+    unsigned long long hpk[3];  // hub lists, slot it % 3 is produced in iteration `it`: (hubs << 32) | edge chunks
     unsigned long long iters, pops, edges, hubs;
     // ---- persistent across launches ----
     int errflags;
@@ -58,9 +62,11 @@ struct PushCtrl {
 };
 constexpr size_t kCtrlZeroBytes = offsetof(PushCtrl, errflags);
 
-struct HubItem {            // 16 bytes
+struct HubItem {            // 32 bytes
     unsigned long long item;
     double ru;
+    uint32_t chunk0;        // index of this hub's first edge chunk in the iteration-wide chunk numbering
+    uint32_t pad[3];
 };
 
 struct PushArgs {
@@ -85,22 +91,36 @@ struct PushArgs {
     int32_t hub_degree;
     int32_t init_mode;           // 1: seed = the sources themselves, phase 0 only (initial solve)
     int32_t max_iters;
+    uint4 *iterlog;              // debug: per iteration (frontier size, hubs, globaltimer lo, hi) of the last refresh
+    int32_t iterlog_cap;
+    unsigned long long *ctalog;  // debug: [grid][8] globaltimer stamps of iteration `probe_iter`
+    int32_t probe_iter;
 };
+
+constexpr int kItemsPerThread = 4;                      // frontier items a thread pops per tile, at most
+constexpr int kTileMax = kThreads * kItemsPerThread;    // 1024 items per tile
 
 struct PushSmem {
     unsigned long long stage[kStage];
-    double t_ru[kThreads];
-    unsigned long long t_sb[kThreads];
-    uint32_t t_off[kThreads];
-    uint32_t t_base[kThreads];
-    uint32_t t_head[kThreads];
-    uint32_t t_mask[kThreads];
-    uint32_t t_s[kThreads];
+    double t_ru[kTileMax];      // (1-alpha) * claimed residual of the item
+    uint32_t t_off[kTileMax];   // exclusive prefix of in-degrees over the tile
+    uint32_t t_base[kTileMax];  // ring geometry of the item's in-list
+    uint32_t t_head[kTileMax];
+    uint32_t t_mask[kTileMax];
+    uint32_t t_s[kTileMax];     // source index of the item
+    uint32_t h_c0[kHubSmem];
     uint32_t scan[kWarps + 1];
     unsigned int stage_cnt;
     unsigned int gbase;
     int abort_flag;
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define DPPR_TL(tl, slot) do { if ((tl) && threadIdx.x == 0) (tl)[slot] = global_ns(); } while (0)
 
 __device__ __forceinline__ bool legal_push(double x, int phase, double eps) {  // gpu/PPRCommon.cuh:6-11
     return phase == 0 ? (x > eps) : (x < -eps);
@@ -156,20 +176,58 @@ __device__ __forceinline__ void stage_flush(PushSmem &sm, unsigned long long *qo
     __syncthreads();
 }
 
-// ---- one traversed in-edge --------------------------------------------------------------------
-template <int VAR>
-__device__ __forceinline__ bool push_edge(const PushArgs &a, uint32_t nbr, double ru_scaled, unsigned long long sb,
-                                          int phase, int level) {
-    const int32_t dv = __ldg(&a.outdeg[nbr]);
-    const double add = ru_scaled / (double)(dv + 1);  // (1-alpha)*ru/(outdeg(v)+1), gpu/ExpandRev.cuh:71-72
-    const unsigned long long ridx = sb + nbr;
-    const double old = atomicAdd(&a.r[ridx], add);
-    const double cur = old + add;
-    if (VAR == 0 || VAR == 1) {  // threshold crossing, gpu/ExpandRev.cuh:75
-        return !legal_push(old, phase, a.eps) && legal_push(cur, phase, a.eps);
-    } else {                     // status stamp, gpu/ExpandRev.cuh:254-257
-        if (!legal_push(cur, phase, a.eps)) return false;
-        return atomicExch(&a.status[ridx], level) < level;
+// ---- traversed in-edges, kEdgeUnroll per thread ------------------------------------------------
+// The push is bound by dependent memory round trips (slot -> out-degree -> atomic), not by bandwidth:
+// every thread therefore keeps kEdgeUnroll independent chains in flight.  Stage 1 issues all slot
+// loads, stage 2 all out-degree loads, stage 3 all FP64 atomics, stage 4 consumes the returned old
+// values for the enqueue rule.
+// Owner accessors keep per-slot register state down to (neighbour id, owner index): the per-owner
+// values (scaled residual, source row base) are re-read from shared memory / uniform registers.
+struct TileOwner {
+    const PushSmem &sm;
+    uint32_t lo[kEdgeUnroll];
+    __device__ __forceinline__ double ru_scaled(int k) const { return sm.t_ru[lo[k]]; }
+    long long Vp;
+    __device__ __forceinline__ unsigned long long sb(int k) const { return (unsigned long long)sm.t_s[lo[k]] * Vp; }
+    __device__ __forceinline__ uint32_t s(int k) const { return sm.t_s[lo[k]]; }
+};
+struct HubOwner {
+    double ru_scaled_;
+    unsigned long long sb_;
+    uint32_t s_;
+    __device__ __forceinline__ double ru_scaled(int) const { return ru_scaled_; }
+    __device__ __forceinline__ unsigned long long sb(int) const { return sb_; }
+    __device__ __forceinline__ uint32_t s(int) const { return s_; }
+};
+
+template <int VAR, class Owner>
+__device__ __forceinline__ void push_edges(const PushArgs &a, PushSmem &sm, const Owner &ow,
+                                           const uint32_t (&nbr)[kEdgeUnroll], const bool (&active)[kEdgeUnroll],
+                                           unsigned long long *qout, unsigned int *cnt_out, int phase, int level) {
+    int32_t dv[kEdgeUnroll];
+    double add[kEdgeUnroll], old[kEdgeUnroll];
+#pragma unroll
+    for (int k = 0; k < kEdgeUnroll; ++k) dv[k] = active[k] ? __ldg(&a.outdeg[nbr[k]]) : 0;
+#pragma unroll
+    for (int k = 0; k < kEdgeUnroll; ++k) {
+        old[k] = 0.0; add[k] = 0.0;
+        if (active[k]) {
+            add[k] = ow.ru_scaled(k) / (double)(dv[k] + 1);  // (1-alpha)*ru/(outdeg(v)+1), gpu/ExpandRev.cuh:71-72
+            old[k] = atomicAdd(&a.r[ow.sb(k) + nbr[k]], add[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kEdgeUnroll; ++k) {
+        bool want = false;
+        if (active[k]) {
+            const double cur = old[k] + add[k];
+            if (VAR == 0 || VAR == 1) {  // threshold crossing, gpu/ExpandRev.cuh:75
+                want = !legal_push(old[k], phase, a.eps) && legal_push(cur, phase, a.eps);
+            } else if (legal_push(cur, phase, a.eps)) {  // status stamp, gpu/ExpandRev.cuh:254-257
+                want = atomicExch(&a.status[ow.sb(k) + nbr[k]], level) < level;
+            }
+        }
+        stage_push(want, ((unsigned long long)ow.s(k) << 32) | nbr[k], sm, qout, cnt_out, a.qcap, a.ctrl);
     }
 }
 
@@ -207,7 +265,7 @@ __device__ void pre_pass(const PushArgs &a, const unsigned long long *qin, doubl
         if (VAR == 1 || VAR == 3) {
             const double x = __ldcg(&a.r[idx]);
             __stcg(&qr[i], x);
-            __stcg(&a.p[idx], __ldcg(&a.p[idx]) + a.alpha * x);
+            atomicAdd(&a.p[idx], a.alpha * x);  // RED: result unused
             __stcg(&a.r[idx], 0.0);
         } else if (VAR == 2) {
             __stcg(&a.status[idx], level);
@@ -237,128 +295,199 @@ __device__ void post_pass(const PushArgs &a, PushSmem &sm, const unsigned long l
     stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
 }
 
-// ---- hubs popped in the previous iteration: every CTA takes chunks of every hub ---------------------
+// ---- hubs popped in the previous iteration: their edge chunks are dealt round-robin to all CTAs -------
+// Producers number the chunks with one packed 64-bit atomic ((hubs << 32) | chunks), so hub k's
+// chunk0 is non-decreasing in k and the owner of chunk c is found by binary search.
 template <int VAR>
-__device__ void expand_hubs(const PushArgs &a, PushSmem &sm, const HubItem *hin, uint32_t nh, unsigned long long *qout,
-                            unsigned int *cnt_out, int phase, int level, unsigned long long &edges_acc) {
-    for (uint32_t h = 0; h < nh; ++h) {
-        const unsigned long long item = __ldcg(&hin[h].item);
-        const double ru_scaled = (1.0 - a.alpha) * __ldcg(&hin[h].ru);
+__device__ void expand_hubs(const PushArgs &a, PushSmem &sm, const HubItem *hin, unsigned long long hpk,
+                            unsigned long long *qout, unsigned int *cnt_out, int phase, int level,
+                            unsigned long long &edges_acc) {
+    const uint32_t nh = (uint32_t)(hpk >> 32), nchunks = (uint32_t)hpk;
+    if (nh == 0) return;
+    const bool cached = nh <= (uint32_t)kHubSmem;
+    if (cached) {
+        for (uint32_t h = threadIdx.x; h < nh; h += kThreads) sm.h_c0[h] = __ldcg(&hin[h].chunk0);
+        __syncthreads();
+    }
+    for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        uint32_t lo = 0, hi = nh;  // last hub with chunk0 <= c
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint32_t v = cached ? sm.h_c0[mid] : __ldcg(&hin[mid].chunk0);
+            if (v <= c) lo = mid; else hi = mid;
+        }
+        const unsigned long long item = __ldcg(&hin[lo].item);
+        const double ru_scaled = (1.0 - a.alpha) * __ldcg(&hin[lo].ru);
+        const uint32_t c0 = cached ? sm.h_c0[lo] : __ldcg(&hin[lo].chunk0);
         const uint32_t s = (uint32_t)(item >> 32), v = (uint32_t)item;
-        const unsigned long long sb = (unsigned long long)s * a.Vp;
         const uint4 m = __ldg(&a.vmeta[v]);
         const uint32_t deg = m.z, mask = m.w - 1u;
-        for (uint32_t c0 = blockIdx.x * kHubChunk; c0 < deg; c0 += gridDim.x * kHubChunk) {
+        const uint32_t e0 = (c - c0) * (uint32_t)kHubChunk;
+        uint32_t nbr[kEdgeUnroll];
+        bool active[kEdgeUnroll];
 #pragma unroll
-            for (int k = 0; k < kHubChunk / kThreads; ++k) {
-                const uint32_t e = c0 + k * kThreads + threadIdx.x;
-                bool want = false;
-                uint32_t nbr = 0;
-                if (e < deg) {
-                    nbr = (uint32_t)__ldg(&a.pool[m.x + ((m.y + e) & mask)]);
-                    want = push_edge<VAR>(a, nbr, ru_scaled, sb, phase, level);
-                }
-                stage_push(want, ((unsigned long long)s << 32) | nbr, sm, qout, cnt_out, a.qcap, a.ctrl);
-            }
-            if (threadIdx.x == 0) edges_acc += min(deg - c0, (uint32_t)kHubChunk);
-            stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
+        for (int k = 0; k < kEdgeUnroll; ++k) {
+            const uint32_t e = e0 + k * kThreads + threadIdx.x;
+            active[k] = e < deg;
+            nbr[k] = active[k] ? (uint32_t)__ldg(&a.pool[m.x + ((m.y + e) & mask)]) : 0u;
         }
+        const HubOwner ow{ru_scaled, (unsigned long long)s * a.Vp, s};
+        push_edges<VAR>(a, sm, ow, nbr, active, qout, cnt_out, phase, level);
+        if (threadIdx.x == 0) edges_acc += min(deg - e0, (uint32_t)kHubChunk);
+        stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
     }
+    __syncthreads();  // h_c0 is reused by the next call
 }
 
 // ---- frontier tiles: pop, edge-balanced expansion -----------------------------------------------------
+// A tile is the contiguous slice of the frontier one CTA handles at a time: at most kTileMax items,
+// and no more than ceil(n / grid) so that one pass of the grid covers the frontier whenever
+// n <= grid * kTileMax.  Threads pop up to kItemsPerThread items each with all loads of a stage in
+// flight together; the in-degrees are prefix-summed in shared memory and the concatenated edge range
+// is walked kEdgeUnroll edges per thread per round.
 template <int VAR>
 __device__ void expand_tiles(const PushArgs &a, PushSmem &sm, const unsigned long long *qin, double *qr, uint32_t n,
-                             unsigned long long *qout, unsigned int *cnt_out, HubItem *hout, unsigned int *hcnt_out,
-                             int phase, int level, unsigned long long &edges_acc) {
+                             unsigned long long *qout, unsigned int *cnt_out, HubItem *hout,
+                             unsigned long long *hpk_out, int phase, int level, unsigned long long &edges_acc,
+                             unsigned long long *tl = nullptr) {
     if (n == 0) return;
-    // spread small frontiers over the grid: fewer items per tile, more CTAs with atomics in flight
     uint32_t tile_items = (n + gridDim.x - 1) / gridDim.x;
-    tile_items = tile_items < 8u ? 8u : (tile_items > (uint32_t)kThreads ? (uint32_t)kThreads : tile_items);
+    tile_items = tile_items < 8u ? 8u : (tile_items > (uint32_t)kTileMax ? (uint32_t)kTileMax : tile_items);
     const uint32_t ntiles = (n + tile_items - 1) / tile_items;
+    const uint32_t ipt = (tile_items + kThreads - 1) / kThreads;  // 1..kItemsPerThread
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint32_t i = tile * tile_items + threadIdx.x;
-        uint32_t deg = 0;
-        if (threadIdx.x < tile_items && i < n) {
-            const unsigned long long item = __ldcg(&qin[i]);
-            const uint32_t s = (uint32_t)(item >> 32), v = (uint32_t)item;
-            const unsigned long long sb = (unsigned long long)s * a.Vp;
-            const unsigned long long idx = sb + v;
-            const uint4 m = __ldg(&a.vmeta[v]);
-            double ru;
-            if (VAR == 0) {
-                ru = __longlong_as_double((long long)atomicExch((unsigned long long *)&a.r[idx], 0ull));
-                __stcg(&a.p[idx], __ldcg(&a.p[idx]) + a.alpha * ru);
-            } else if (VAR == 2) {
-                ru = __ldcg(&a.r[idx]);            // live read, kept until the post pass subtracts it
-                __stcg(&qr[i], ru);
-                __stcg(&a.p[idx], __ldcg(&a.p[idx]) + a.alpha * ru);
-            } else {
-                ru = __ldcg(&qr[i]);               // taken by the snapshot pass
-            }
-            deg = m.z;
-            if (deg >= (uint32_t)a.hub_degree) {
-                const unsigned hp = atomicAdd(hcnt_out, 1u);
-                if (hp < a.hcap) {
-                    __stcg(&hout[hp].item, item);
-                    __stcg(&hout[hp].ru, ru);
-                } else {
-                    atomicOr(&a.ctrl->errflags, kErrHubQ);
+        const uint32_t tbase = tile * tile_items;
+        // ---- pop: stage 1 items, stage 2 ring metadata + residual claim, stage 3 estimate update ----
+        unsigned long long item[kItemsPerThread];
+        bool have[kItemsPerThread];
+#pragma unroll
+        for (int k = 0; k < kItemsPerThread; ++k) {
+            const uint32_t j = k * kThreads + threadIdx.x;
+            have[k] = j < tile_items && tbase + j < n;
+            item[k] = have[k] ? __ldcg(&qin[tbase + j]) : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < kItemsPerThread; ++k) {
+            const uint32_t j = k * kThreads + threadIdx.x;
+            if (j < tile_items) {
+                uint32_t deg = 0;
+                if (have[k]) {
+                    const uint32_t s = (uint32_t)(item[k] >> 32), v = (uint32_t)item[k];
+                    const unsigned long long idx = (unsigned long long)s * a.Vp + v;
+                    const uint4 m = __ldg(&a.vmeta[v]);
+                    double ru;
+                    if (VAR == 0) {
+                        ru = __longlong_as_double((long long)atomicExch((unsigned long long *)&a.r[idx], 0ull));
+                        atomicAdd(&a.p[idx], a.alpha * ru);  // result unused: fire-and-forget RED, no extra round trip
+                    } else if (VAR == 2) {
+                        ru = __ldcg(&a.r[idx]);            // live read, kept until the post pass subtracts it
+                        __stcg(&qr[tbase + j], ru);
+                        atomicAdd(&a.p[idx], a.alpha * ru);
+                    } else {
+                        ru = __ldcg(&qr[tbase + j]);       // taken by the snapshot pass
+                    }
+                    deg = m.z;
+                    if (deg >= (uint32_t)a.hub_degree) {
+                        const uint32_t nch = (deg + kHubChunk - 1) / kHubChunk;
+                        const unsigned long long old = atomicAdd(hpk_out, (1ull << 32) | nch);
+                        const uint32_t hp = (uint32_t)(old >> 32);
+                        if (hp < a.hcap) {
+                            __stcg(&hout[hp].item, item[k]);
+                            __stcg(&hout[hp].ru, ru);
+                            __stcg(&hout[hp].chunk0, (uint32_t)old);
+                        } else {
+                            atomicOr(&a.ctrl->errflags, kErrHubQ);
+                        }
+                        deg = 0;
+                    }
+                    sm.t_ru[j] = (1.0 - a.alpha) * ru;
+                    sm.t_base[j] = m.x;
+                    sm.t_head[j] = m.y;
+                    sm.t_mask[j] = m.w - 1u;
+                    sm.t_s[j] = s;
                 }
-                deg = 0;
+                sm.t_off[j] = deg;
             }
-            sm.t_ru[threadIdx.x] = (1.0 - a.alpha) * ru;
-            sm.t_sb[threadIdx.x] = sb;
-            sm.t_base[threadIdx.x] = m.x;
-            sm.t_head[threadIdx.x] = m.y;
-            sm.t_mask[threadIdx.x] = m.w - 1u;
-            sm.t_s[threadIdx.x] = s;
+        }
+        __syncthreads();
+        if (tile == blockIdx.x) DPPR_TL(tl, 2);
+        // ---- exclusive prefix of the degrees (blocked: thread t owns items [t*ipt, t*ipt+ipt)) ----
+        uint32_t d[kItemsPerThread], sum = 0;
+        const uint32_t jb = threadIdx.x * ipt;
+#pragma unroll
+        for (int k = 0; k < kItemsPerThread; ++k) {
+            d[k] = ((uint32_t)k < ipt && jb + k < tile_items) ? sm.t_off[jb + k] : 0u;
+            sum += d[k];
         }
         uint32_t total;
-        const uint32_t off = block_exclusive_sum<uint32_t>(deg, sm.scan, total);
-        sm.t_off[threadIdx.x] = off;
-        __syncthreads();
-        for (uint32_t e0 = 0; e0 < total; e0 += kThreads) {
-            const uint32_t e = e0 + threadIdx.x;
-            bool want = false;
-            unsigned long long item_out = 0;
-            if (e < total) {
-                // owner = last j with t_off[j] <= e   (zero-degree items share an offset with their successor)
-                uint32_t lo = 0, hi = tile_items;
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (sm.t_off[mid] <= e) lo = mid; else hi = mid;
-                }
-                const uint32_t k = e - sm.t_off[lo];
-                const uint32_t nbr = (uint32_t)__ldg(&a.pool[sm.t_base[lo] + ((sm.t_head[lo] + k) & sm.t_mask[lo])]);
-                want = push_edge<VAR>(a, nbr, sm.t_ru[lo], sm.t_sb[lo], phase, level);
-                item_out = ((unsigned long long)sm.t_s[lo] << 32) | nbr;
+        uint32_t off = block_exclusive_sum<uint32_t>(sum, sm.scan, total);
+#pragma unroll
+        for (int k = 0; k < kItemsPerThread; ++k) {
+            if ((uint32_t)k < ipt && jb + k < tile_items) {
+                sm.t_off[jb + k] = off;
+                off += d[k];
             }
-            stage_push(want, item_out, sm, qout, cnt_out, a.qcap, a.ctrl);
+        }
+        __syncthreads();
+        if (tile == blockIdx.x) DPPR_TL(tl, 3);
+        // ---- edges ----
+        for (uint32_t e0 = 0; e0 < total; e0 += kHubChunk) {
+            TileOwner ow{sm, {0u, 0u, 0u, 0u}, a.Vp};
+            uint32_t nbr[kEdgeUnroll];
+            bool active[kEdgeUnroll];
+#pragma unroll
+            for (int k = 0; k < kEdgeUnroll; ++k) {
+                const uint32_t e = e0 + k * kThreads + threadIdx.x;
+                active[k] = e < total;
+                nbr[k] = 0;
+                if (active[k]) {
+                    // owner = last j with t_off[j] <= e   (zero-degree items share an offset with their successor)
+                    uint32_t lo = 0, hi = tile_items;
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (sm.t_off[mid] <= e) lo = mid; else hi = mid;
+                    }
+                    ow.lo[k] = lo;
+                    const uint32_t kk = e - sm.t_off[lo];
+                    nbr[k] = (uint32_t)__ldg(&a.pool[sm.t_base[lo] + ((sm.t_head[lo] + kk) & sm.t_mask[lo])]);
+                }
+            }
+            push_edges<VAR>(a, sm, ow, nbr, active, qout, cnt_out, phase, level);
         }
         if (threadIdx.x == 0) edges_acc += total;
+        if (tile == blockIdx.x) DPPR_TL(tl, 4);
         stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
+        if (tile == blockIdx.x) DPPR_TL(tl, 5);
     }
 }
 
 // ---- software grid barrier (all CTAs co-resident: cooperative launch) --------------------------------
+// bar.sync orders the CTA's earlier global writes before thread 0's release-add (cumulativity); the
+// acquire-load that observes the last arrival makes every other CTA's writes visible, and the
+// trailing bar.sync passes that on to the rest of the CTA.
+__device__ __forceinline__ void bar_arrive_release(unsigned *addr) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(addr) : "memory");
+}
+__device__ __forceinline__ unsigned bar_load_acquire(const unsigned *addr) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ bool grid_barrier(PushCtrl *c, unsigned &gen, PushSmem &sm) {
     __syncthreads();
     if (threadIdx.x == 0) {
         ++gen;
         const unsigned target = gen * gridDim.x;
-        __threadfence();
-        atomicAdd(&c->bar, 1u);
+        bar_arrive_release(&c->bar);
         const long long t0 = clock64();
         bool ok = true;
-        while (*(volatile unsigned *)&c->bar < target) {
+        while (bar_load_acquire(&c->bar) < target) {
             if (clock64() - t0 > 8000000000ll) {  // ~4 s: a CTA is missing, give up loudly instead of hanging
                 atomicOr(&c->errflags, kErrWatchdog);
                 ok = false;
                 break;
             }
         }
-        __threadfence();
         sm.abort_flag = ok ? 0 : 1;
     }
     __syncthreads();
@@ -367,7 +496,7 @@ __device__ __forceinline__ bool grid_barrier(PushCtrl *c, unsigned &gen, PushSme
 
 // ---- the persistent kernel ----------------------------------------------------------------------------
 template <int VAR>
-__global__ void __launch_bounds__(kThreads) push_persistent(const PushArgs a) {
+__global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(const PushArgs a) {
     __shared__ PushSmem sm;
     PushCtrl *c = a.ctrl;
     if (threadIdx.x == 0) { sm.stage_cnt = 0; sm.abort_flag = 0; }
@@ -375,15 +504,27 @@ __global__ void __launch_bounds__(kThreads) push_persistent(const PushArgs a) {
     unsigned gen = 0;
     unsigned long long edges_acc = 0, pops_acc = 0, hubs_acc = 0;
     const int level0 = __ldcg(&c->level);
-    uint32_t it = 0;
+    uint32_t it = 0, iters_done = 0;  // `it` indexes the rotating slots (skips one value per phase change)
     const int nphases = a.init_mode ? 1 : 2;
     bool alive = true;
     for (int phase = 0; phase < nphases && alive; ++phase) {
+        if (phase > 0) {
+            // Phase change.  Slow CTAs may still be polling cnt[it % 3] (== 0) to leave the loop below,
+            // so the new seeds must not land in that slot: skip one iteration index.  The slots the
+            // skipped iteration would have cleared are cleared here -- their last readers passed the
+            // barrier that ended iteration it-1, their next writers run after the barrier below.
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                c->cnt[(it + 2) % 3] = 0;
+                c->hpk[(it + 1) % 3] = 0;
+            }
+            ++it;
+        }
         seed_pass(a, sm, phase, a.q[it & 1], &c->cnt[it % 3]);
         if (!(alive = grid_barrier(c, gen, sm))) break;
         while (true) {
             const uint32_t n = __ldcg(&c->cnt[it % 3]);
-            const uint32_t nh = __ldcg(&c->hcnt[(it + 2) % 3]);
+            const unsigned long long hpk = __ldcg(&c->hpk[(it + 2) % 3]);
+            const uint32_t nh = (uint32_t)(hpk >> 32);
             if (n == 0 && nh == 0) break;
             if ((int)it >= a.max_iters) {
                 if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&c->errflags, kErrWatchdog);
@@ -392,32 +533,43 @@ __global__ void __launch_bounds__(kThreads) push_persistent(const PushArgs a) {
             }
             if (blockIdx.x == 0 && threadIdx.x == 0) {  // slots nobody reads or writes during this iteration
                 c->cnt[(it + 2) % 3] = 0;
-                c->hcnt[(it + 1) % 3] = 0;
+                c->hpk[(it + 1) % 3] = 0;
                 pops_acc += n;
                 hubs_acc += nh;
+                if (a.iterlog && (int)iters_done < a.iterlog_cap) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    a.iterlog[iters_done] = make_uint4(n, (uint32_t)hpk, (uint32_t)t, (uint32_t)(t >> 32));
+                }
             }
             const int level = level0 + (int)it + 1;
+            unsigned long long *tl = (a.ctalog && (int)iters_done == a.probe_iter) ? a.ctalog + (size_t)blockIdx.x * 8 : nullptr;
+            DPPR_TL(tl, 0);
             const unsigned long long *qin = a.q[it & 1];
             unsigned long long *qout = a.q[(it + 1) & 1];
             if (VAR != 0) {
                 pre_pass<VAR>(a, qin, a.qr[it & 1], n, level);
                 if (!(alive = grid_barrier(c, gen, sm))) break;
             }
-            expand_hubs<VAR>(a, sm, a.hub[(it + 1) & 1], nh, qout, &c->cnt[(it + 1) % 3], phase, level, edges_acc);
+            expand_hubs<VAR>(a, sm, a.hub[(it + 1) & 1], hpk, qout, &c->cnt[(it + 1) % 3], phase, level, edges_acc);
+            DPPR_TL(tl, 1);
             expand_tiles<VAR>(a, sm, qin, a.qr[it & 1], n, qout, &c->cnt[(it + 1) % 3], a.hub[it & 1],
-                              &c->hcnt[it % 3], phase, level, edges_acc);
+                              &c->hpk[it % 3], phase, level, edges_acc, tl);
+            DPPR_TL(tl, 6);
             if (VAR == 2) {
                 if (!(alive = grid_barrier(c, gen, sm))) break;
                 post_pass(a, sm, qin, a.qr[it & 1], n, qout, &c->cnt[(it + 1) % 3], phase);
             }
             if (!(alive = grid_barrier(c, gen, sm))) break;
+            DPPR_TL(tl, 7);
             ++it;
+            ++iters_done;
         }
     }
     if (threadIdx.x == 0) {
         if (edges_acc) atomicAdd(&c->edges, edges_acc);
         if (blockIdx.x == 0) {
-            c->iters = it;
+            c->iters = iters_done;
             c->pops = pops_acc;
             c->hubs = hubs_acc;
             c->level = level0 + (int)it + 2;
@@ -444,18 +596,20 @@ __global__ void __launch_bounds__(kThreads) push_step_expand(const PushArgs a, u
     if (threadIdx.x == 0) { sm.stage_cnt = 0; sm.abort_flag = 0; }
     __syncthreads();
     PushCtrl *c = a.ctrl;
-    const uint32_t n = c->cnt[it % 3], nh = c->hcnt[(it + 2) % 3];
+    const uint32_t n = c->cnt[it % 3];
+    const unsigned long long hpk = c->hpk[(it + 2) % 3];
+    const uint32_t nh = (uint32_t)(hpk >> 32);
     unsigned long long edges_acc = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         c->cnt[(it + 2) % 3] = 0;
-        c->hcnt[(it + 1) % 3] = 0;
+        c->hpk[(it + 1) % 3] = 0;
         c->pops += n;
         c->hubs += nh;
         c->iters += 1;
     }
-    expand_hubs<VAR>(a, sm, a.hub[(it + 1) & 1], nh, a.q[(it + 1) & 1], &c->cnt[(it + 1) % 3], phase, level, edges_acc);
+    expand_hubs<VAR>(a, sm, a.hub[(it + 1) & 1], hpk, a.q[(it + 1) & 1], &c->cnt[(it + 1) % 3], phase, level, edges_acc);
     expand_tiles<VAR>(a, sm, a.q[it & 1], a.qr[it & 1], n, a.q[(it + 1) & 1], &c->cnt[(it + 1) % 3], a.hub[it & 1],
-                      &c->hcnt[it % 3], phase, level, edges_acc);
+                      &c->hpk[it % 3], phase, level, edges_acc);
     if (threadIdx.x == 0 && edges_acc) atomicAdd(&c->edges, edges_acc);
 }
 

@@ -65,7 +65,7 @@ typedef struct dppr_config {
     int32_t record_timing;      /* 1: bracket every batch phase with CUDA events (see dppr_batch_stats) */
     double pool_factor;         /* adjacency pool slots per window CSR entry; <=0 -> default (8.0) */
     int64_t frontier_capacity;  /* (source, vertex) items per frontier queue; <=0 -> default */
-    int32_t hub_degree;         /* in-degree at/above which a vertex is expanded grid-wide; <=0 -> 4096 */
+    int32_t hub_degree;         /* in-degree at/above which a vertex is expanded grid-wide; <=0 -> 1024 */
     int32_t reserved0;
 } dppr_config;
 
@@ -161,6 +161,11 @@ int64_t dppr_window_csr_entries(const dppr_engine *e); /* E_w = D*W */
 int dppr_set_state(dppr_engine *e, int32_t source_index, const double *p, const double *r);
 /* residual repair only (no push): the closed form checked against the sequential oracle */
 int dppr_repair_only(dppr_engine *e);
+/* debug: with DPPR_ITERLOG=1 in the environment at dppr_create, (frontier size, hub chunks, globaltimer lo, hi)
+ * of every push iteration of the most recent refresh; out holds 4*cap uint32 */
+int dppr_debug_iterlog(dppr_engine *e, uint32_t *out, int32_t cap, int32_t *n_out);
+/* debug: 8 globaltimer stamps per CTA for push iteration DPPR_PROBE_ITER of the most recent refresh */
+int dppr_debug_ctalog(dppr_engine *e, unsigned long long *out, int32_t cap_rows, int32_t *n_out);
 /* stable LSD radix sort of (key, value) pairs on the device, host in / host out */
 int dppr_test_sort_pairs(int32_t device, uint32_t *keys, uint32_t *vals, int64_t n, int32_t key_bits);
 /* exclusive prefix sum on the device, host in / host out; returns the total in *total */

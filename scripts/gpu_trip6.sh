@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 300 -x > gpurun_out/t6_parity.log 2>&1
+echo "parity exit $?" >> gpurun_out/t6_parity.log
+tail -5 gpurun_out/t6_parity.log
+for args in "--shape dblp" "--shape youtube" "--shape youtube --variant 1" "--shape youtube --variant 2" "--shape youtube --variant 3" "--shape livejournal --scale 0.25 --per-batch 100 --batches 100" "--shape orkut --scale 0.25 --batches 20"; do
+  echo "=== probe $args"; timeout 600 python scripts/probe.py $args --show 0 2>&1 | tail -9
+done > gpurun_out/t6_probe.log 2>&1
+for c in 2 3; do echo "=== youtube CTAS_PER_SM=$c"; DPPR_CTAS_PER_SM=$c timeout 600 python scripts/probe.py --shape youtube --show 0 2>&1 | tail -6; done >> gpurun_out/t6_probe.log 2>&1
+echo "=== iterlog youtube" >> gpurun_out/t6_probe.log
+DPPR_ITERLOG=1 timeout 600 python scripts/probe.py --shape youtube --show 0 --batches 5 2>&1 | tail -12 >> gpurun_out/t6_probe.log
+cat gpurun_out/t6_probe.log
