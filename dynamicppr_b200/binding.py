@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "dppr_slide_device_pairs", "dppr_sync", "dppr_get_batch_stats", "dppr_batches_done",
     "dppr_get_estimates", "dppr_get_residuals", "dppr_copy_estimates_device", "dppr_export_window_csr",
     "dppr_window_csr_entries", "dppr_set_state", "dppr_repair_only", "dppr_test_sort_pairs",
-    "dppr_test_exclusive_scan", "dppr_debug_iterlog", "dppr_debug_ctalog",
+    "dppr_test_exclusive_scan", "dppr_debug_iterlog", "dppr_debug_ctalog", "dppr_kernel_launches",
 ]
 
 
@@ -93,6 +93,7 @@ def load_library():
     L.dppr_window_csr_entries.argtypes = [vp]; L.dppr_window_csr_entries.restype = C.c_int64
     L.dppr_set_state.argtypes = [vp, C.c_int32, f64p, f64p]
     L.dppr_repair_only.argtypes = [vp]
+    L.dppr_kernel_launches.restype = C.c_uint64
     L.dppr_debug_ctalog.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_int32)]
     L.dppr_debug_iterlog.argtypes = [vp, C.POINTER(C.c_uint32), C.c_int32, C.POINTER(C.c_int32)]
     L.dppr_test_sort_pairs.argtypes = [C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int64, C.c_int32]
@@ -249,6 +250,10 @@ class DynamicPPR:
         self._check(self.L.dppr_set_state(self.h, source_index,
                                           pp.ctypes.data_as(f64p) if pp is not None else None,
                                           rr.ctypes.data_as(f64p) if rr is not None else None))
+
+
+def kernel_launches() -> int:
+    return int(load_library().dppr_kernel_launches())
 
 
 def test_sort_pairs(keys, vals, key_bits, device=0):

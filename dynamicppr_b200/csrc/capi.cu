@@ -149,6 +149,8 @@ int dppr_debug_ctalog(dppr_engine *e, unsigned long long *out, int32_t cap_rows,
     return guarded(e, [&](dppr::Engine &g) { *n_out = g.get_ctalog(out, cap_rows); });
 }
 
+unsigned long long dppr_kernel_launches(void) { return dppr::launch_counter(); }
+
 // ---- primitive test hooks ------------------------------------------------------------------------
 int dppr_test_sort_pairs(int32_t device, uint32_t *keys, uint32_t *vals, int64_t n, int32_t key_bits) {
     using namespace dppr;

@@ -35,6 +35,12 @@ struct CapacityError : std::runtime_error {
                                       std::to_string(__LINE__) + ": " + cudaGetErrorString(err__));   \
     } while (0)
 
+// number of kernels this library has launched from the calling thread (bench.py reports it)
+inline unsigned long long &launch_counter() {
+    static thread_local unsigned long long c = 0;
+    return c;
+}
+
 inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // owning device buffer

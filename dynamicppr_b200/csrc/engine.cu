@@ -191,8 +191,8 @@ BatchRecord *Engine::record_slot(size_t k) {
 }
 
 void Engine::finish_record() {
-    fold_window_errors<<<1, 1, 0, st_>>>(ctrl_.ptr, (int *)(counters_.ptr + 3));
-    gather_record<<<1, 1, 0, st_>>>(dev_record_.ptr, ctrl_.ptr, counters_.ptr, pool_top_.ptr);
+    fold_window_errors<<<1, 1, 0, st_>>>(ctrl_.ptr, (int *)(counters_.ptr + 3)); ++launch_counter();
+    gather_record<<<1, 1, 0, st_>>>(dev_record_.ptr, ctrl_.ptr, counters_.ptr, pool_top_.ptr); ++launch_counter();
     DPPR_CUDA(cudaGetLastError());
     DPPR_CUDA(cudaMemcpyAsync(record_slot(meta_.size() - 1), dev_record_.ptr, sizeof(BatchRecord),
                               cudaMemcpyDeviceToHost, st_));
@@ -248,13 +248,13 @@ void Engine::init_window_pairs(const int32_t *pairs, int64_t n) {
     int *werr = (int *)(counters_.ptr + 3);
 
     win_init_entries<<<grid_for(W_), kThreads, 0, st_>>>(log_.ptr, W_, D_ == 1, V_, key[0].ptr, val[0].ptr, indeg.ptr,
-                                                        outdeg_.ptr, werr);
-    win_init_caps<<<grid_for(V_), kThreads, 0, st_>>>(indeg.ptr, caps.ptr, V_);
+                                                        outdeg_.ptr, werr); ++launch_counter();
+    win_init_caps<<<grid_for(V_), kThreads, 0, st_>>>(indeg.ptr, caps.ptr, V_); ++launch_counter();
     exclusive_scan<uint32_t>(indeg.ptr, rowptr.ptr, V_, scratch.ptr, nullptr, st_);
     exclusive_scan<uint32_t>(caps.ptr, capbase.ptr, V_, scratch.ptr, total.ptr, st_);
     const int res = sort_pairs(key[0].ptr, val[0].ptr, key[1].ptr, val[1].ptr, Ew_, key_bits_, scratch.ptr, st_);
-    win_init_fill<<<grid_for(Ew_), kThreads, 0, st_>>>(key[res].ptr, val[res].ptr, Ew_, rowptr.ptr, capbase.ptr, pool_.ptr);
-    win_init_meta<<<grid_for(V_), kThreads, 0, st_>>>(indeg.ptr, caps.ptr, capbase.ptr, vmeta_.ptr, V_);
+    win_init_fill<<<grid_for(Ew_), kThreads, 0, st_>>>(key[res].ptr, val[res].ptr, Ew_, rowptr.ptr, capbase.ptr, pool_.ptr); ++launch_counter();
+    win_init_meta<<<grid_for(V_), kThreads, 0, st_>>>(indeg.ptr, caps.ptr, capbase.ptr, vmeta_.ptr, V_); ++launch_counter();
     DPPR_CUDA(cudaGetLastError());
     uint32_t htotal = 0;
     int herr = 0;
@@ -305,6 +305,7 @@ void Engine::launch_push(bool init_mode) {
         default: kern = persistent_kernel<3>(); break;
     }
     DPPR_CUDA(cudaLaunchCooperativeKernel(kern, dim3(coop_grid_[cfg_.variant]), dim3(kThreads), params, 0, st_));
+    ++launch_counter();
 }
 
 // Debug / profiling mode with the reference's structure: one launch per sub-pass and a blocking
@@ -321,7 +322,7 @@ void Engine::launch_push_stepwise(PushArgs &a) {
             DPPR_CUDA(cudaMemsetAsync(&ctrl_.ptr->hpk[(it + 1) % 3], 0, sizeof(unsigned long long), st_));
             ++it;
         }
-        push_step_seed<<<grid, kThreads, 0, st_>>>(a, it, phase);
+        push_step_seed<<<grid, kThreads, 0, st_>>>(a, it, phase); ++launch_counter();
         while (true) {
             DPPR_CUDA(cudaMemcpyAsync(&h, ctrl_.ptr, sizeof(PushCtrl), cudaMemcpyDeviceToHost, st_));
             DPPR_CUDA(cudaStreamSynchronize(st_));
@@ -329,19 +330,19 @@ void Engine::launch_push_stepwise(PushArgs &a) {
             if ((int)it >= a.max_iters) throw CapacityError("push did not converge within DPPR_MAX_ITERS iterations");
             const int level = step_level_ + (int)it + 1;
             switch (var) {
-                case 0: push_step_expand<0><<<grid, kThreads, 0, st_>>>(a, it, phase, level); break;
+                case 0: push_step_expand<0><<<grid, kThreads, 0, st_>>>(a, it, phase, level); ++launch_counter(); break;
                 case 1:
-                    push_step_pre<1><<<grid, kThreads, 0, st_>>>(a, it, level);
-                    push_step_expand<1><<<grid, kThreads, 0, st_>>>(a, it, phase, level);
+                    push_step_pre<1><<<grid, kThreads, 0, st_>>>(a, it, level); ++launch_counter();
+                    push_step_expand<1><<<grid, kThreads, 0, st_>>>(a, it, phase, level); ++launch_counter();
                     break;
                 case 2:
-                    push_step_pre<2><<<grid, kThreads, 0, st_>>>(a, it, level);
-                    push_step_expand<2><<<grid, kThreads, 0, st_>>>(a, it, phase, level);
-                    push_step_post<<<grid, kThreads, 0, st_>>>(a, it, phase);
+                    push_step_pre<2><<<grid, kThreads, 0, st_>>>(a, it, level); ++launch_counter();
+                    push_step_expand<2><<<grid, kThreads, 0, st_>>>(a, it, phase, level); ++launch_counter();
+                    push_step_post<<<grid, kThreads, 0, st_>>>(a, it, phase); ++launch_counter();
                     break;
                 default:
-                    push_step_pre<3><<<grid, kThreads, 0, st_>>>(a, it, level);
-                    push_step_expand<3><<<grid, kThreads, 0, st_>>>(a, it, phase, level);
+                    push_step_pre<3><<<grid, kThreads, 0, st_>>>(a, it, level); ++launch_counter();
+                    push_step_expand<3><<<grid, kThreads, 0, st_>>>(a, it, phase, level); ++launch_counter();
                     break;
             }
             DPPR_CUDA(cudaGetLastError());
@@ -360,7 +361,7 @@ void Engine::solve_initial() {
     meta_.clear();
     meta_.emplace_back();
     record(0);
-    state_init<<<grid_for(Vp_ * S_), kThreads, 0, st_>>>(p_.ptr, r_.ptr, status_.ptr, Vp_, S_, src_.ptr);
+    state_init<<<grid_for(Vp_ * S_), kThreads, 0, st_>>>(p_.ptr, r_.ptr, status_.ptr, Vp_, S_, src_.ptr); ++launch_counter();
     DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, sizeof(PushCtrl), st_));
     DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, counters_.bytes(), st_));
     step_level_ = 0;
@@ -424,32 +425,32 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
     int *werr = (int *)(counters_.ptr + 3);
     DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, sizeof(uint32_t) * 3, st_));
     win_batch_entries<<<grid_for(B), kThreads, 0, st_>>>(log_.ptr, W_, log_start_, arriving, B, D_ == 1, V_,
-                                                        akey_[0].ptr, aval_[0].ptr, bkey_[0].ptr, bval_[0].ptr, werr);
+                                                        akey_[0].ptr, aval_[0].ptr, bkey_[0].ptr, bval_[0].ptr, werr); ++launch_counter();
     log_start_ = (log_start_ + B) % W_;
     uint32_t *scan_scratch = sort_scratch_.ptr + sort_scratch_elems(Nb_);
 
     // group A: keyed by destination -> in-lists
     int res = sort_pairs(akey_[0].ptr, aval_[0].ptr, akey_[1].ptr, aval_[1].ptr, nA, key_bits_, sort_scratch_.ptr, st_);
     sa_key_ = akey_[res].ptr; sa_val_ = aval_[res].ptr;
-    rle_heads<<<grid_for(nA), kThreads, 0, st_>>>(sa_key_, nA, flags_.ptr);
+    rle_heads<<<grid_for(nA), kThreads, 0, st_>>>(sa_key_, nA, flags_.ptr); ++launch_counter();
     exclusive_scan<uint32_t>(flags_.ptr, segA_.segof, nA, scan_scratch, nullptr, st_);
-    rle_fill<<<grid_for(nA), kThreads, 0, st_>>>(sa_key_, sa_val_, nA, segA_);
+    rle_fill<<<grid_for(nA), kThreads, 0, st_>>>(sa_key_, sa_val_, nA, segA_); ++launch_counter();
     WindowView wv{V_, vmeta_.ptr, pool_.ptr, outdeg_.ptr, pool_top_.ptr, pool_cap_, werr};
-    win_plan<<<grid_for(nA), kThreads, 0, st_>>>(segA_, wv, ins_pos_.ptr, jobs_.ptr, counters_.ptr + 2);
-    win_relocate<<<std::min(grid_for(nA), 4 * sm_count_), kThreads, 0, st_>>>(jobs_.ptr, counters_.ptr + 2, pool_.ptr);
-    win_insert<<<grid_for(nA), kThreads, 0, st_>>>(sa_key_, sa_val_, nA, segA_, ins_pos_.ptr, wv);
+    win_plan<<<grid_for(nA), kThreads, 0, st_>>>(segA_, wv, ins_pos_.ptr, jobs_.ptr, counters_.ptr + 2); ++launch_counter();
+    win_relocate<<<std::min(grid_for(nA), 4 * sm_count_), kThreads, 0, st_>>>(jobs_.ptr, counters_.ptr + 2, pool_.ptr); ++launch_counter();
+    win_insert<<<grid_for(nA), kThreads, 0, st_>>>(sa_key_, sa_val_, nA, segA_, ins_pos_.ptr, wv); ++launch_counter();
 
     // group B: keyed by source -> out-degrees + residual repair (undirected: same runs as group A)
     if (D_ == 1) {
         res = sort_pairs(bkey_[0].ptr, bval_[0].ptr, bkey_[1].ptr, bval_[1].ptr, nA, key_bits_, sort_scratch_.ptr, st_);
         sb_key_ = bkey_[res].ptr; sb_val_ = bval_[res].ptr;
-        rle_heads<<<grid_for(nA), kThreads, 0, st_>>>(sb_key_, nA, flags_.ptr);
+        rle_heads<<<grid_for(nA), kThreads, 0, st_>>>(sb_key_, nA, flags_.ptr); ++launch_counter();
         exclusive_scan<uint32_t>(flags_.ptr, segB_.segof, nA, scan_scratch, nullptr, st_);
-        rle_fill<<<grid_for(nA), kThreads, 0, st_>>>(sb_key_, sb_val_, nA, segB_);
+        rle_fill<<<grid_for(nA), kThreads, 0, st_>>>(sb_key_, sb_val_, nA, segB_); ++launch_counter();
     } else {
         sb_key_ = sa_key_; sb_val_ = sa_val_;
     }
-    win_out_degrees<<<grid_for(nA), kThreads, 0, st_>>>(segB_, outdeg_.ptr, seg_d0_.ptr);
+    win_out_degrees<<<grid_for(nA), kThreads, 0, st_>>>(segB_, outdeg_.ptr, seg_d0_.ptr); ++launch_counter();
     DPPR_CUDA(cudaGetLastError());
     record(2);
     batch_pending_ = true;
@@ -463,9 +464,9 @@ void Engine::refresh(bool repair_only) {
     DPPR_CUDA(cudaSetDevice(dev_));
     const int64_t n = cur().entries;
     dim3 g((unsigned)std::min(grid_for(n), 8 * sm_count_), (unsigned)S_);
-    repair_accumulate<<<g, kThreads, 0, st_>>>(sb_val_, n, segB_.segof, p_.ptr, Vp_, delta_.ptr, Nb_);
+    repair_accumulate<<<g, kThreads, 0, st_>>>(sb_val_, n, segB_.segof, p_.ptr, Vp_, delta_.ptr, Nb_); ++launch_counter();
     repair_finalize<<<grid_for(n * S_), kThreads, 0, st_>>>(segB_, seg_d0_.ptr, src_.ptr, S_, p_.ptr, r_.ptr, Vp_,
-                                                          delta_.ptr, Nb_, cfg_.alpha);
+                                                          delta_.ptr, Nb_, cfg_.alpha); ++launch_counter();
     DPPR_CUDA(cudaGetLastError());
     record(3);
     if (!repair_only) launch_push(false);
@@ -565,7 +566,7 @@ void Engine::export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_d
     for (int i = 0; i < 2; ++i) { key[i].alloc((size_t)Ew_); val[i].alloc((size_t)Ew_); }
     scratch.alloc(std::max(sort_scratch_elems(Ew_), scan_scratch_elems(V_)));
     total.alloc(1);
-    win_export_len<<<grid_for(V_), kThreads, 0, st_>>>(vmeta_.ptr, len.ptr, V_);
+    win_export_len<<<grid_for(V_), kThreads, 0, st_>>>(vmeta_.ptr, len.ptr, V_); ++launch_counter();
     exclusive_scan<uint32_t>(len.ptr, rowptr.ptr, V_, scratch.ptr, total.ptr, st_);
     DPPR_CUDA(cudaMemcpyAsync(rowptr.ptr + V_, total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st_));
     uint32_t htotal = 0;
@@ -574,7 +575,7 @@ void Engine::export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_d
     if ((int64_t)htotal != Ew_)
         throw StateError("window graph holds " + std::to_string(htotal) + " entries, expected " + std::to_string(Ew_));
     win_export_entries<<<grid_for((int64_t)V_ * 32), kThreads, 0, st_>>>(vmeta_.ptr, pool_.ptr, rowptr.ptr, key[0].ptr,
-                                                                      val[0].ptr, V_);
+                                                                      val[0].ptr, V_); ++launch_counter();
     // sort by (dst, src): LSD over the pair = stable sort by src, then stable sort by dst
     int res = sort_pairs(val[0].ptr, key[0].ptr, val[1].ptr, key[1].ptr, Ew_, key_bits_, scratch.ptr, st_);
     uint32_t *k0 = key[res].ptr, *v0 = val[res].ptr, *k1 = key[1 - res].ptr, *v1 = val[1 - res].ptr;

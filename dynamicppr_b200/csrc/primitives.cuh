@@ -71,13 +71,13 @@ void exclusive_scan(const T *in, T *out, int64_t n, T *scratch, T *total_out, cu
         return;
     }
     if (n <= kScanTile) {
-        scan_tiles<T><<<1, kThreads, 0, st>>>(in, out, nullptr, n, total_out);
+        scan_tiles<T><<<1, kThreads, 0, st>>>(in, out, nullptr, n, total_out); ++launch_counter();
         return;
     }
     const int tiles = div_up(n, kScanTile);
-    scan_tile_sums<T><<<tiles, kThreads, 0, st>>>(in, scratch, n);
+    scan_tile_sums<T><<<tiles, kThreads, 0, st>>>(in, scratch, n); ++launch_counter();
     exclusive_scan<T>(scratch, scratch, tiles, scratch + tiles, nullptr, st);
-    scan_tiles<T><<<tiles, kThreads, 0, st>>>(in, out, scratch, n, total_out);
+    scan_tiles<T><<<tiles, kThreads, 0, st>>>(in, out, scratch, n, total_out); ++launch_counter();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -175,9 +175,9 @@ inline int sort_pairs(uint32_t *k0, uint32_t *v0, uint32_t *k1, uint32_t *v1, in
     uint32_t *kin = k0, *vin = v0, *kout = k1, *vout = v1;
     for (int p = 0; p < passes; ++p) {
         const int shift = 8 * p;
-        radix_hist<<<tiles, kThreads, 0, st>>>(kin, hist, n, shift, tiles);
+        radix_hist<<<tiles, kThreads, 0, st>>>(kin, hist, n, shift, tiles); ++launch_counter();
         exclusive_scan<uint32_t>(hist, hist, (int64_t)kRadix * tiles, scan_scratch, nullptr, st);
-        radix_scatter<<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, hist, n, shift, tiles);
+        radix_scatter<<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, hist, n, shift, tiles); ++launch_counter();
         uint32_t *t;
         t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;

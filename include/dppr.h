@@ -136,6 +136,8 @@ int dppr_slide_pairs(dppr_engine *e, const int32_t *pairs, int64_t B);
 int dppr_slide_device_pairs(dppr_engine *e, const int32_t *device_pairs, int64_t B);
 
 int dppr_sync(dppr_engine *e);
+/* kernels launched by this library from the calling thread so far (reported by bench.py as gpu_launches) */
+unsigned long long dppr_kernel_launches(void);
 
 /* stats of batch `batch_index` (0 = initial solve); -1 = most recent.  Synchronises. */
 int dppr_get_batch_stats(dppr_engine *e, int64_t batch_index, dppr_batch_stats *out);

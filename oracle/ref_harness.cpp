@@ -23,6 +23,8 @@
 //                     (the line the reference keeps commented at
 //                     cpu/PPRCPUMTCilk.h:126) so PPR always runs on the true window
 //   --quiet           silence the reference's std::cout chatter
+//   --times <file>    one line per batch: "<batch> <ppr_us> <iteration_id>" (cheap; used by bench.py's
+//                     reference arm to drop warm-up batches -- the reference itself only prints a mean)
 //
 // Dump format (native little-endian):
 //   char[8] "DPPRDMP1"; int32 V; int32 directed; int64 W; int64 B; int32 has_pow; int32 nsnap
@@ -108,11 +110,12 @@ int CountIncRowsDiffer(SlidingGraphVec *dg, const std::vector<int32_t> &row_ptr,
 }  // namespace
 
 int main(int argc, char *argv[]) {
-    std::string dump_path;
+    std::string dump_path, times_path;
     bool want_pow = false, scratch_graph = false, quiet = false;
     for (int i = 1; i < argc; ++i) {
         std::string a(argv[i]);
         if (a == "--dump" && i + 1 < argc) dump_path = argv[i + 1];
+        if (a == "--times" && i + 1 < argc) times_path = argv[i + 1];
         if (a == "--pow") want_pow = true;
         if (a == "--scratch-graph") scratch_graph = true;
         if (a == "--quiet") quiet = true;
@@ -178,13 +181,17 @@ int main(int argc, char *argv[]) {
         ++nsnap;
     };
 
+    FILE *times = times_path.empty() ? NULL : fopen(times_path.c_str(), "w");
     // initial solve on the first window (cpu/PPRCPUMTCilk.h:74-91)
     TimeMeasurer t0;
     t0.StartTimer();
     ppr->ExecuteImpl();
     t0.EndTimer();
-    ScratchWindowCSR(dg, row_ptr, col, outdeg);
-    snapshot(0, (double)t0.GetElapsedMicroSeconds(), CountIncRowsDiffer(dg, row_ptr, col, outdeg));
+    if (times) fprintf(times, "0 %lld %d\n", (long long)t0.GetElapsedMicroSeconds(), (int)ppr->iteration_id);
+    if (out) {
+        ScratchWindowCSR(dg, row_ptr, col, outdeg);
+        snapshot(0, (double)t0.GetElapsedMicroSeconds(), CountIncRowsDiffer(dg, row_ptr, col, outdeg));
+    }
 
     // streaming loop (cpu/PPRCPUMTCilk.h:101-145)
     size_t stream_batch_count = 0;
@@ -194,8 +201,11 @@ int main(int argc, char *argv[]) {
         bool over = dg->StreamUpdates(gStreamUpdateCountPerBatch);
         if (over) break;
         dg->IncConstructWindowGraph();
-        ScratchWindowCSR(dg, row_ptr, col, outdeg);
-        int differ = CountIncRowsDiffer(dg, row_ptr, col, outdeg);
+        int differ = 0;
+        if (out) {  // the window comparison is O(E_w) per batch: only when dumping
+            ScratchWindowCSR(dg, row_ptr, col, outdeg);
+            differ = CountIncRowsDiffer(dg, row_ptr, col, outdeg);
+        }
         total_inc_rows_differ += differ;
         if (scratch_graph) dg->ConstructGraph();
         TimeMeasurer timer;
@@ -203,8 +213,10 @@ int main(int argc, char *argv[]) {
         ppr->IncExecuteImpl();
         timer.EndTimer();
         ppr_time += timer.GetElapsedMicroSeconds();
+        if (times) fprintf(times, "%d %lld %d\n", (int)stream_batch_count, (long long)timer.GetElapsedMicroSeconds(), (int)ppr->iteration_id);
         snapshot((int)stream_batch_count, (double)timer.GetElapsedMicroSeconds(), differ);
     }
+    if (times) fclose(times);
     if (out) {
         fseek(out, nsnap_pos, SEEK_SET);
         fwrite(&nsnap, 4, 1, out);
