@@ -324,7 +324,7 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                "ms_per_step": dev_total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
-               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * wl.B, "d2h_bytes_per_step": 104,
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * wl.B, "d2h_bytes_per_step": 128,
                        "ms_per_step": e2e_total_s * 1e3 / K},
                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                "p50_ms": float(np.median(step_ms)), "p95_ms": float(np.percentile(step_ms, 95)),

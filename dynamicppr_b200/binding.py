@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 OPTIMIZED, FAST_FRONTIER, EAGER, VANILLA = 0, 1, 2, 3
-ENGINE_PERSISTENT, ENGINE_STEPWISE = 0, 1
+ENGINE_AUTO, ENGINE_STEPWISE, ENGINE_ASYNC, ENGINE_LEVELSYNC = 0, 1, 2, 3
 
 # every symbol include/dppr.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = [
@@ -110,7 +110,7 @@ class DynamicPPR:
     """One engine = one GPU.  Mirrors the C ABI call for call."""
 
     def __init__(self, vertex_count, directed, window_edges, max_batch_edges, sources, epsilon=1e-9, variant=0,
-                 device=0, engine_mode=ENGINE_PERSISTENT, record_timing=True, alpha=0.15, pool_factor=0.0,
+                 device=0, engine_mode=ENGINE_AUTO, record_timing=True, alpha=0.15, pool_factor=0.0,
                  frontier_capacity=0, hub_degree=0):
         self.L = load_library()
         self.V = int(vertex_count)

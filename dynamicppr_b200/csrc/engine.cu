@@ -49,13 +49,23 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     if (cfg.variant < DPPR_OPTIMIZED || cfg.variant > DPPR_VANILLA)
         throw InvalidArgument("variant must be 0..3 (Meta.h:11-17)");
     if (cfg.n_sources < 1 || cfg.sources == nullptr) throw InvalidArgument("at least one source vertex is required");
-    if (cfg.engine_mode != DPPR_ENGINE_PERSISTENT && cfg.engine_mode != DPPR_ENGINE_STEPWISE)
-        throw InvalidArgument("engine_mode must be DPPR_ENGINE_PERSISTENT or DPPR_ENGINE_STEPWISE");
+    if (cfg.engine_mode < DPPR_ENGINE_AUTO || cfg.engine_mode > DPPR_ENGINE_LEVELSYNC)
+        throw InvalidArgument("engine_mode must be one of DPPR_ENGINE_{AUTO,STEPWISE,ASYNC,LEVELSYNC}");
+    if (cfg.engine_mode == DPPR_ENGINE_ASYNC && cfg.variant != DPPR_OPTIMIZED)
+        throw InvalidArgument("DPPR_ENGINE_ASYNC implements variant 0 (optimized) only");
+    mode_ = cfg.engine_mode;
+    if (mode_ == DPPR_ENGINE_AUTO) mode_ = DPPR_ENGINE_LEVELSYNC;  // measured fastest for every variant so far (profiles/README.md)
+    if (const char *force = std::getenv("DPPR_FORCE_ENGINE")) {  // tuning / A-B runs without touching the caller
+        const int f = std::atoi(force);
+        if (f >= DPPR_ENGINE_STEPWISE && f <= DPPR_ENGINE_LEVELSYNC && !(f == DPPR_ENGINE_ASYNC && cfg.variant != 0)) mode_ = f;
+    }
+    if (mode_ == DPPR_ENGINE_ASYNC && cfg.n_sources > kMaxAsyncSources)
+        throw InvalidArgument("DPPR_ENGINE_ASYNC supports at most 4096 sources per engine");
     if (cfg_.alpha <= 0.0) cfg_.alpha = 0.15;
     if (cfg_.alpha >= 1.0) throw InvalidArgument("alpha must be in (0, 1)");
     if (cfg_.epsilon <= 0.0) cfg_.epsilon = 1e-9;
     if (cfg_.pool_factor <= 0.0) cfg_.pool_factor = 8.0;
-    if (cfg_.hub_degree <= 0) cfg_.hub_degree = kHubChunk;
+    if (cfg_.hub_degree <= 0) cfg_.hub_degree = env_int("DPPR_HUB_DEGREE", 64);
     V_ = cfg.vertex_count;
     D_ = cfg.directed ? 1 : 2;
     W_ = cfg.window_edges;
@@ -93,6 +103,12 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
         DPPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern[v], kThreads, 0));
         if (per_sm < 1) throw CudaFailure("push kernel does not fit on an SM");
         coop_grid_[v] = std::min(per_sm, std::max(want_per_sm, 1)) * sm_count_;
+    }
+    {
+        int per_sm = 0;
+        DPPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (void *)push_async, kThreads, 0));
+        if (per_sm < 1) throw CudaFailure("async push kernel does not fit on an SM");
+        async_grid_ = std::min(per_sm, std::max(env_int("DPPR_ASYNC_CTAS_PER_SM", 4), 1)) * sm_count_;
     }
 
     // window
@@ -143,10 +159,29 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     if (qc > 0xfffffff0ll) qc = 0xfffffff0ll;
     qcap_ = (uint32_t)qc;
     hcap_ = (uint32_t)std::min<int64_t>(qc, std::max<int64_t>(1024, (Ew_ / cfg_.hub_degree + 1) * S_));
-    for (int i = 0; i < 2; ++i) {
-        q_[i].alloc(qcap_);
-        if (cfg_.variant != DPPR_OPTIMIZED) qr_[i].alloc(qcap_);
-        hub_[i].alloc(hcap_);
+    if (use_async()) {
+        // ticket rings (one per phase): at most one outstanding entry per (source, vertex) plus hub chunks
+        // ... plus the tickets idle warps hold ahead of `tail`: two live tickets must never share a slot
+        const unsigned long long worst = 2ull * (unsigned long long)V_ * S_ + (unsigned long long)Ew_ / kHubChunk * S_ +
+                                         64ull * (unsigned long long)async_grid_ * kWarps;
+        unsigned long long want = cfg_.frontier_capacity > 0 ? (unsigned long long)cfg_.frontier_capacity
+                                                             : std::min<unsigned long long>(worst, 1ull << 30);
+        ring_cap_ = 1ull << 16;
+        while (ring_cap_ < want) ring_cap_ <<= 1;
+        guard_slots_ = ring_cap_ < worst ? 1 : 0;
+        for (int i = 0; i < 2; ++i) {
+            q_[i].alloc(ring_cap_);
+            qr_[i].alloc(ring_cap_);
+            DPPR_CUDA(cudaMemsetAsync(q_[i].ptr, 0xff, q_[i].bytes(), st_));  // every slot EMPTY
+        }
+        async_ctr_.alloc(10 * 16);
+        DPPR_CUDA(cudaMemsetAsync(async_ctr_.ptr, 0, async_ctr_.bytes(), st_));
+    } else {
+        for (int i = 0; i < 2; ++i) {
+            q_[i].alloc(qcap_);
+            if (cfg_.variant != DPPR_OPTIMIZED) qr_[i].alloc(qcap_);
+            hub_[i].alloc(hcap_);
+        }
     }
     ctrl_.alloc(1);
     DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, sizeof(PushCtrl), st_));
@@ -288,12 +323,23 @@ void Engine::launch_push(bool init_mode) {
     a.hub_degree = cfg_.hub_degree;
     a.init_mode = init_mode ? 1 : 0;
     a.max_iters = env_int("DPPR_MAX_ITERS", 400000);
+    {
+        const char *g = std::getenv("DPPR_CARRY_GAMMA"), *sc = std::getenv("DPPR_CARRY_SCALE");
+        // off by default: on the L2-resident BASELINE configs the extra (latency-bound) iterations cost more than
+        // the saved traversals (profiles/README.md); DPPR_CARRY_GAMMA=0.7 enables the threshold schedule
+        a.carry_gamma = g ? std::atof(g) : 1.0;
+        a.carry_scale = sc ? std::atof(sc) : 0.01;
+    }
     a.iterlog = iterlog_.ptr;
     a.iterlog_cap = iterlog_.ptr ? kIterLogCap : 0;
     a.ctalog = ctalog_.ptr;
     a.probe_iter = env_int("DPPR_PROBE_ITER", 10);
-    if (cfg_.engine_mode == DPPR_ENGINE_STEPWISE) {
+    if (mode_ == DPPR_ENGINE_STEPWISE) {
         launch_push_stepwise(a);
+        return;
+    }
+    if (mode_ == DPPR_ENGINE_ASYNC) {
+        launch_push_async(a);
         return;
     }
     void *params[] = {(void *)&a};
@@ -305,6 +351,37 @@ void Engine::launch_push(bool init_mode) {
         default: kern = persistent_kernel<3>(); break;
     }
     DPPR_CUDA(cudaLaunchCooperativeKernel(kern, dim3(coop_grid_[cfg_.variant]), dim3(kThreads), params, 0, st_));
+    ++launch_counter();
+}
+
+void Engine::launch_push_async(PushArgs &b) {
+    AsyncArgs a{};
+    a.base = b;
+    for (int i = 0; i < 2; ++i) {
+        a.q[i].slots = q_[i].ptr;
+        a.q[i].slot_ru = qr_[i].ptr;
+        a.q[i].mask = ring_cap_ - 1;
+        a.q[i].tail = async_ctr_.ptr + (3 * i + 0) * 16;
+        a.q[i].head = async_ctr_.ptr + (3 * i + 1) * 16;
+        a.q[i].done = async_ctr_.ptr + (3 * i + 2) * 16;
+        a.q[i].fence = async_ctr_.ptr + (6 + 2 * i) * 16;
+        a.q[i].theta0 = async_ctr_.ptr + (7 + 2 * i) * 16;
+    }
+    a.guard_slots = 0;
+    a.dbg = iterlog_.ptr ? (unsigned long long *)ctalog_.ptr : nullptr;
+    if (a.dbg) {
+        DPPR_CUDA(cudaMemsetAsync(a.dbg, 0, 128, st_));
+        DPPR_CUDA(cudaMemsetAsync(a.dbg + 10, 0xff, 8, st_));
+        DPPR_CUDA(cudaMemsetAsync(a.dbg + 12, 0xff, 8, st_));
+    }
+    {
+        const char *g = std::getenv("DPPR_CARRY_GAMMA"), *sc = std::getenv("DPPR_CARRY_SCALE");
+        a.carry_gamma = g ? std::atof(g) : 0.7;
+        a.carry_scale = sc ? std::atof(sc) : 0.01;
+    }
+    DPPR_CUDA(cudaMemsetAsync(async_ctr_.ptr, 0, async_ctr_.bytes(), st_));
+    void *params[] = {(void *)&a};
+    DPPR_CUDA(cudaLaunchCooperativeKernel((void *)push_async, dim3(async_grid_), dim3(kThreads), params, 0, st_));
     ++launch_counter();
 }
 
@@ -323,26 +400,35 @@ void Engine::launch_push_stepwise(PushArgs &a) {
             ++it;
         }
         push_step_seed<<<grid, kThreads, 0, st_>>>(a, it, phase); ++launch_counter();
+        double theta = -1.0;
         while (true) {
             DPPR_CUDA(cudaMemcpyAsync(&h, ctrl_.ptr, sizeof(PushCtrl), cudaMemcpyDeviceToHost, st_));
             DPPR_CUDA(cudaStreamSynchronize(st_));
             if (h.cnt[it % 3] == 0 && h.hpk[(it + 2) % 3] == 0) break;
             if ((int)it >= a.max_iters) throw CapacityError("push did not converge within DPPR_MAX_ITERS iterations");
             const int level = step_level_ + (int)it + 1;
+            if (theta < 0.0) {  // first iteration of the phase: the seeds' largest residual is known now
+                double t0;
+                std::memcpy(&t0, &h.theta0[phase], sizeof(double));
+                const bool carrying = var == 0 && a.carry_gamma > 0.0 && a.carry_gamma < 1.0;
+                theta = carrying ? t0 * a.carry_scale : a.eps;
+            }
+            const double th = std::max(theta, a.eps);
+            theta *= a.carry_gamma;
             switch (var) {
-                case 0: push_step_expand<0><<<grid, kThreads, 0, st_>>>(a, it, phase, level); ++launch_counter(); break;
+                case 0: push_step_expand<0><<<grid, kThreads, 0, st_>>>(a, it, phase, level, th); ++launch_counter(); break;
                 case 1:
                     push_step_pre<1><<<grid, kThreads, 0, st_>>>(a, it, level); ++launch_counter();
-                    push_step_expand<1><<<grid, kThreads, 0, st_>>>(a, it, phase, level); ++launch_counter();
+                    push_step_expand<1><<<grid, kThreads, 0, st_>>>(a, it, phase, level, th); ++launch_counter();
                     break;
                 case 2:
                     push_step_pre<2><<<grid, kThreads, 0, st_>>>(a, it, level); ++launch_counter();
-                    push_step_expand<2><<<grid, kThreads, 0, st_>>>(a, it, phase, level); ++launch_counter();
+                    push_step_expand<2><<<grid, kThreads, 0, st_>>>(a, it, phase, level, th); ++launch_counter();
                     push_step_post<<<grid, kThreads, 0, st_>>>(a, it, phase); ++launch_counter();
                     break;
                 default:
                     push_step_pre<3><<<grid, kThreads, 0, st_>>>(a, it, level); ++launch_counter();
-                    push_step_expand<3><<<grid, kThreads, 0, st_>>>(a, it, phase, level); ++launch_counter();
+                    push_step_expand<3><<<grid, kThreads, 0, st_>>>(a, it, phase, level, th); ++launch_counter();
                     break;
             }
             DPPR_CUDA(cudaGetLastError());
@@ -496,7 +582,7 @@ void Engine::get_stats(int64_t batch_index, dppr_batch_stats *out) {
     out->batch_entries = m.entries;  // N_b = 2*D*B
     out->touched_vertices = (D_ == 1) ? rec->nseg_out : rec->nseg_in;
     out->iterations = (int64_t)rec->ctrl.iters;
-    out->frontier_pops = (int64_t)rec->ctrl.pops;
+    out->frontier_pops = (int64_t)rec->ctrl.pops - (int64_t)rec->ctrl.carried;  // carried items are not pushed
     out->traversed_edges = (int64_t)rec->ctrl.edges;
     out->hub_pops = (int64_t)rec->ctrl.hubs;
     out->relocations = rec->njobs;
@@ -553,6 +639,7 @@ int Engine::get_ctalog(unsigned long long *out, int cap_rows) {
     if (!ctalog_.ptr) return 0;
     sync();
     int rows = std::min(cap_rows, coop_grid_[cfg_.variant]);
+    if (use_async()) rows = 2;
     DPPR_CUDA(cudaMemcpy(out, ctalog_.ptr, sizeof(unsigned long long) * 8 * (size_t)rows, cudaMemcpyDeviceToHost));
     return rows;
 }

@@ -15,6 +15,7 @@
 #include "window.cuh"
 #include "repair.cuh"
 #include "push.cuh"
+#include "push_async.cuh"
 
 namespace dppr {
 
@@ -59,6 +60,8 @@ private:
     void apply_batch_common(const int2 *arriving, int64_t B);
     void launch_push(bool init_mode);
     void launch_push_stepwise(PushArgs &a);
+    void launch_push_async(PushArgs &a);
+    bool use_async() const { return mode_ == DPPR_ENGINE_ASYNC; }
     void record(int which);
     void finish_record();
     BatchMeta &cur() { return meta_.back(); }
@@ -68,7 +71,7 @@ private:
 
     dppr_config cfg_;
     std::vector<int32_t> sources_;
-    int dev_ = 0, sm_count_ = 0, coop_grid_[4] = {0, 0, 0, 0};
+    int dev_ = 0, sm_count_ = 0, coop_grid_[4] = {0, 0, 0, 0}, async_grid_ = 0, mode_ = 0;
     cudaStream_t st_ = nullptr;
     int32_t V_ = 0;
     int64_t Vp_ = 0, W_ = 0, Ew_ = 0, Bmax_ = 0, Nb_ = 0;
@@ -104,6 +107,9 @@ private:
     DevBuf<double> qr_[2];
     DevBuf<HubItem> hub_[2];
     uint32_t qcap_ = 0, hcap_ = 0;
+    unsigned long long ring_cap_ = 0;           // async: slots per ring (power of two)
+    DevBuf<unsigned long long> async_ctr_;      // async: tail/head/done of both rings, one 128-byte line each
+    int guard_slots_ = 0;
     DevBuf<PushCtrl> ctrl_;
     DevBuf<BatchRecord> dev_record_;
     DevBuf<uint4> iterlog_;

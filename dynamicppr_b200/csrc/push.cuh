@@ -56,6 +56,8 @@ struct PushCtrl {
     unsigned int bar;       // grid barrier arrivals (monotone within a launch)
     unsigned long long hpk[3];  // hub lists, slot it % 3 is produced in iteration `it`: (hubs << 32) | edge chunks
     unsigned long long iters, pops, edges, hubs;
+    unsigned long long theta0[2];  // bits of max |r| over the seeds of phase 0 / 1 (positive doubles order like integers)
+    unsigned long long carried;    // frontier items carried over untouched (variant 0 threshold schedule)
     // ---- persistent across launches ----
     int errflags;
     int level;              // last status stamp handed out (variants 2, 3)
@@ -95,6 +97,8 @@ struct PushArgs {
     int32_t iterlog_cap;
     unsigned long long *ctalog;  // debug: [grid][8] globaltimer stamps of iteration `probe_iter`
     int32_t probe_iter;
+    double carry_gamma;          // variant 0: iteration k of a phase only pushes items with |r| > max(eps, theta0*scale*gamma^k);
+    double carry_scale;          // the rest is put back and carried to the next frontier.  gamma >= 1 disables carrying.
 };
 
 constexpr int kItemsPerThread = 4;                      // frontier items a thread pops per tile, at most
@@ -238,6 +242,7 @@ __device__ void seed_pass(const PushArgs &a, PushSmem &sm, int phase, unsigned l
     const unsigned long long total = (unsigned long long)ncand * (unsigned)a.S;
     const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
     const unsigned long long rounds = (total + stride - 1) / stride;
+    double mx = 0.0;
     for (unsigned long long rd = 0; rd < rounds; ++rd) {
         const unsigned long long j = rd * stride + (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
         bool want = false;
@@ -249,11 +254,15 @@ __device__ void seed_pass(const PushArgs &a, PushSmem &sm, int phase, unsigned l
             const double x = __ldcg(&a.r[(unsigned long long)s * a.Vp + u]);
             want = legal_push(x, phase, a.eps);
             item = ((unsigned long long)s << 32) | u;
+            if (want) mx = fmax(mx, fabs(x));
         }
         stage_push(want, item, sm, qout, cnt_out, a.qcap, a.ctrl);
         if ((rd & 3) == 3) stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
     }
     stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, off));
+    if (lane_id() == 0 && mx > 0.0) atomicMax(&a.ctrl->theta0[phase], (unsigned long long)__double_as_longlong(mx));
 }
 
 // ---- pre pass: variants 1,3 snapshot + zero (gpu/Inspect.cuh:52-65); variant 2 status stamp ------
@@ -348,8 +357,8 @@ __device__ void expand_hubs(const PushArgs &a, PushSmem &sm, const HubItem *hin,
 template <int VAR>
 __device__ void expand_tiles(const PushArgs &a, PushSmem &sm, const unsigned long long *qin, double *qr, uint32_t n,
                              unsigned long long *qout, unsigned int *cnt_out, HubItem *hout,
-                             unsigned long long *hpk_out, int phase, int level, unsigned long long &edges_acc,
-                             unsigned long long *tl = nullptr) {
+                             unsigned long long *hpk_out, int phase, int level, double theta, unsigned long long &edges_acc,
+                             unsigned long long &carried_acc, unsigned long long *tl = nullptr) {
     if (n == 0) return;
     uint32_t tile_items = (n + gridDim.x - 1) / gridDim.x;
     tile_items = tile_items < 8u ? 8u : (tile_items > (uint32_t)kTileMax ? (uint32_t)kTileMax : tile_items);
@@ -359,11 +368,12 @@ __device__ void expand_tiles(const PushArgs &a, PushSmem &sm, const unsigned lon
         const uint32_t tbase = tile * tile_items;
         // ---- pop: stage 1 items, stage 2 ring metadata + residual claim, stage 3 estimate update ----
         unsigned long long item[kItemsPerThread];
-        bool have[kItemsPerThread];
+        bool have[kItemsPerThread], carry[kItemsPerThread];
 #pragma unroll
         for (int k = 0; k < kItemsPerThread; ++k) {
             const uint32_t j = k * kThreads + threadIdx.x;
             have[k] = j < tile_items && tbase + j < n;
+            carry[k] = false;
             item[k] = have[k] ? __ldcg(&qin[tbase + j]) : 0ull;
         }
 #pragma unroll
@@ -378,7 +388,14 @@ __device__ void expand_tiles(const PushArgs &a, PushSmem &sm, const unsigned lon
                     double ru;
                     if (VAR == 0) {
                         ru = __longlong_as_double((long long)atomicExch((unsigned long long *)&a.r[idx], 0ull));
-                        atomicAdd(&a.p[idx], a.alpha * ru);  // result unused: fire-and-forget RED, no extra round trip
+                        if (fabs(ru) <= theta && fabs(ru) > a.eps) {
+                            // threshold schedule: too small to be worth a push yet -- put it back (RED) and carry the
+                            // vertex to the next frontier, where it will have collected more mass
+                            atomicAdd(&a.r[idx], ru);
+                            carry[k] = true;
+                        } else {
+                            atomicAdd(&a.p[idx], a.alpha * ru);  // result unused: fire-and-forget RED, no extra round trip
+                        }
                     } else if (VAR == 2) {
                         ru = __ldcg(&a.r[idx]);            // live read, kept until the post pass subtracts it
                         __stcg(&qr[tbase + j], ru);
@@ -386,7 +403,7 @@ __device__ void expand_tiles(const PushArgs &a, PushSmem &sm, const unsigned lon
                     } else {
                         ru = __ldcg(&qr[tbase + j]);       // taken by the snapshot pass
                     }
-                    deg = m.z;
+                    deg = (carry[k] || ru == 0.0) ? 0u : m.z;  // (an exact zero: a duplicate whose twin took everything)
                     if (deg >= (uint32_t)a.hub_degree) {
                         const uint32_t nch = (deg + kHubChunk - 1) / kHubChunk;
                         const unsigned long long old = atomicAdd(hpk_out, (1ull << 32) | nch);
@@ -407,6 +424,13 @@ __device__ void expand_tiles(const PushArgs &a, PushSmem &sm, const unsigned lon
                     sm.t_s[j] = s;
                 }
                 sm.t_off[j] = deg;
+            }
+        }
+        if (VAR == 0) {
+#pragma unroll
+            for (int k = 0; k < kItemsPerThread; ++k) {  // uniform: every lane takes part in the ballots
+                stage_push(carry[k], item[k], sm, qout, cnt_out, a.qcap, a.ctrl);
+                carried_acc += carry[k] ? 1 : 0;
             }
         }
         __syncthreads();
@@ -473,7 +497,12 @@ __device__ __forceinline__ unsigned bar_load_acquire(const unsigned *addr) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ bool grid_barrier(PushCtrl *c, unsigned &gen, PushSmem &sm) {
+__device__ __forceinline__ unsigned bar_load_relaxed(const unsigned *addr) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool grid_barrier(PushCtrl *c, unsigned &gen, int &abort_flag) {
     __syncthreads();
     if (threadIdx.x == 0) {
         ++gen;
@@ -481,17 +510,21 @@ __device__ __forceinline__ bool grid_barrier(PushCtrl *c, unsigned &gen, PushSme
         bar_arrive_release(&c->bar);
         const long long t0 = clock64();
         bool ok = true;
-        while (bar_load_acquire(&c->bar) < target) {
+        // poll with a relaxed load: ld.acquire makes ptxas emit CCTL.IVALL (whole-L1 invalidate) after EVERY
+        // poll, which stalls the poller and flushes the L1 of the CTAs still working on this SM (ncu: 31 % of
+        // all stall samples).  One acquire after the last arrival is enough.
+        while (bar_load_relaxed(&c->bar) < target) {
             if (clock64() - t0 > 8000000000ll) {  // ~4 s: a CTA is missing, give up loudly instead of hanging
                 atomicOr(&c->errflags, kErrWatchdog);
                 ok = false;
                 break;
             }
         }
-        sm.abort_flag = ok ? 0 : 1;
+        (void)bar_load_acquire(&c->bar);
+        abort_flag = ok ? 0 : 1;
     }
     __syncthreads();
-    return sm.abort_flag == 0;
+    return abort_flag == 0;
 }
 
 // ---- the persistent kernel ----------------------------------------------------------------------------
@@ -502,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(con
     if (threadIdx.x == 0) { sm.stage_cnt = 0; sm.abort_flag = 0; }
     __syncthreads();
     unsigned gen = 0;
-    unsigned long long edges_acc = 0, pops_acc = 0, hubs_acc = 0;
+    unsigned long long edges_acc = 0, pops_acc = 0, hubs_acc = 0, carried_acc = 0;
     const int level0 = __ldcg(&c->level);
     uint32_t it = 0, iters_done = 0;  // `it` indexes the rotating slots (skips one value per phase change)
     const int nphases = a.init_mode ? 1 : 2;
@@ -520,7 +553,9 @@ __global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(con
             ++it;
         }
         seed_pass(a, sm, phase, a.q[it & 1], &c->cnt[it % 3]);
-        if (!(alive = grid_barrier(c, gen, sm))) break;
+        if (!(alive = grid_barrier(c, gen, sm.abort_flag))) break;
+        const bool carrying = VAR == 0 && a.carry_gamma > 0.0 && a.carry_gamma < 1.0;
+        double theta = carrying ? __longlong_as_double((long long)__ldcg(&c->theta0[phase])) * a.carry_scale : a.eps;
         while (true) {
             const uint32_t n = __ldcg(&c->cnt[it % 3]);
             const unsigned long long hpk = __ldcg(&c->hpk[(it + 2) % 3]);
@@ -549,23 +584,28 @@ __global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(con
             unsigned long long *qout = a.q[(it + 1) & 1];
             if (VAR != 0) {
                 pre_pass<VAR>(a, qin, a.qr[it & 1], n, level);
-                if (!(alive = grid_barrier(c, gen, sm))) break;
+                if (!(alive = grid_barrier(c, gen, sm.abort_flag))) break;
             }
             expand_hubs<VAR>(a, sm, a.hub[(it + 1) & 1], hpk, qout, &c->cnt[(it + 1) % 3], phase, level, edges_acc);
             DPPR_TL(tl, 1);
             expand_tiles<VAR>(a, sm, qin, a.qr[it & 1], n, qout, &c->cnt[(it + 1) % 3], a.hub[it & 1],
-                              &c->hpk[it % 3], phase, level, edges_acc, tl);
+                              &c->hpk[it % 3], phase, level, fmax(theta, a.eps), edges_acc, carried_acc, tl);
+            theta *= a.carry_gamma;
             DPPR_TL(tl, 6);
             if (VAR == 2) {
-                if (!(alive = grid_barrier(c, gen, sm))) break;
+                if (!(alive = grid_barrier(c, gen, sm.abort_flag))) break;
                 post_pass(a, sm, qin, a.qr[it & 1], n, qout, &c->cnt[(it + 1) % 3], phase);
             }
-            if (!(alive = grid_barrier(c, gen, sm))) break;
+            if (!(alive = grid_barrier(c, gen, sm.abort_flag))) break;
             DPPR_TL(tl, 7);
             ++it;
             ++iters_done;
         }
     }
+    // carried_acc is per thread: fold it over the CTA with one atomic per warp
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) carried_acc += __shfl_xor_sync(kFull, carried_acc, off);
+    if (lane_id() == 0 && carried_acc) atomicAdd(&c->carried, carried_acc);
     if (threadIdx.x == 0) {
         if (edges_acc) atomicAdd(&c->edges, edges_acc);
         if (blockIdx.x == 0) {
@@ -591,7 +631,7 @@ __global__ void __launch_bounds__(kThreads) push_step_pre(const PushArgs a, uint
 }
 
 template <int VAR>
-__global__ void __launch_bounds__(kThreads) push_step_expand(const PushArgs a, uint32_t it, int phase, int level) {
+__global__ void __launch_bounds__(kThreads) push_step_expand(const PushArgs a, uint32_t it, int phase, int level, double theta) {
     __shared__ PushSmem sm;
     if (threadIdx.x == 0) { sm.stage_cnt = 0; sm.abort_flag = 0; }
     __syncthreads();
@@ -599,7 +639,7 @@ __global__ void __launch_bounds__(kThreads) push_step_expand(const PushArgs a, u
     const uint32_t n = c->cnt[it % 3];
     const unsigned long long hpk = c->hpk[(it + 2) % 3];
     const uint32_t nh = (uint32_t)(hpk >> 32);
-    unsigned long long edges_acc = 0;
+    unsigned long long edges_acc = 0, carried_acc = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         c->cnt[(it + 2) % 3] = 0;
         c->hpk[(it + 1) % 3] = 0;
@@ -609,7 +649,10 @@ __global__ void __launch_bounds__(kThreads) push_step_expand(const PushArgs a, u
     }
     expand_hubs<VAR>(a, sm, a.hub[(it + 1) & 1], hpk, a.q[(it + 1) & 1], &c->cnt[(it + 1) % 3], phase, level, edges_acc);
     expand_tiles<VAR>(a, sm, a.q[it & 1], a.qr[it & 1], n, a.q[(it + 1) & 1], &c->cnt[(it + 1) % 3], a.hub[it & 1],
-                      &c->hpk[it % 3], phase, level, edges_acc);
+                      &c->hpk[it % 3], phase, level, theta, edges_acc, carried_acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) carried_acc += __shfl_xor_sync(kFull, carried_acc, off);
+    if (lane_id() == 0 && carried_acc) atomicAdd(&c->carried, carried_acc);
     if (threadIdx.x == 0 && edges_acc) atomicAdd(&c->edges, edges_acc);
 }
 

@@ -52,7 +52,7 @@ public:
         c.device = s.device;
         c.n_sources = (int32_t)sources_.size();
         c.sources = sources_.data();
-        c.engine_mode = s.stepwise ? DPPR_ENGINE_STEPWISE : DPPR_ENGINE_PERSISTENT;
+        c.engine_mode = s.stepwise ? DPPR_ENGINE_STEPWISE : DPPR_ENGINE_AUTO;
         c.record_timing = 1;
         std::cout << "init sliding graph.." << std::endl;
         int rc = dppr_create(&c, &eng_);

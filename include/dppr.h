@@ -43,9 +43,13 @@ enum { DPPR_OPTIMIZED = 0, DPPR_FAST_FRONTIER = 1, DPPR_EAGER = 2, DPPR_VANILLA 
 
 /* how the push loop is driven */
 enum {
-    DPPR_ENGINE_PERSISTENT = 0, /* one cooperative kernel per refresh, device-side loop + grid barrier */
-    DPPR_ENGINE_STEPWISE = 1    /* one launch per push iteration, host reads the frontier count
-                                   (the reference's structure, gpu/PPRRevPushGPU.cuh:97-131) */
+    DPPR_ENGINE_AUTO = 0,      /* fastest measured: currently LEVELSYNC for every variant */
+    DPPR_ENGINE_STEPWISE = 1,  /* one launch per push sub-pass, host reads the frontier count every iteration
+                                  (the reference's structure, gpu/PPRRevPushGPU.cuh:97-131); debugging / profiling */
+    DPPR_ENGINE_ASYNC = 2,     /* variant 0 only: one cooperative launch per refresh, device-wide ticket queue,
+                                  no barrier between pushes (csrc/push_async.cuh) */
+    DPPR_ENGINE_LEVELSYNC = 3  /* one cooperative launch per refresh, level-synchronous iterations separated by a
+                                  software grid barrier (csrc/push.cuh) */
 };
 
 typedef struct dppr_engine dppr_engine;
@@ -65,7 +69,7 @@ typedef struct dppr_config {
     int32_t record_timing;      /* 1: bracket every batch phase with CUDA events (see dppr_batch_stats) */
     double pool_factor;         /* adjacency pool slots per window CSR entry; <=0 -> default (8.0) */
     int64_t frontier_capacity;  /* (source, vertex) items per frontier queue; <=0 -> default */
-    int32_t hub_degree;         /* in-degree at/above which a vertex is expanded grid-wide; <=0 -> 1024 */
+    int32_t hub_degree;         /* in-degree at/above which a vertex is expanded grid-wide; <=0 -> 64 */
     int32_t reserved0;
 } dppr_config;
 
