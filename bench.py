@@ -156,6 +156,10 @@ def run_port_cpu(V, directed, edges, wl, source, n_batches):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: libraries that chat on fd 1 (NCCL prints its version there) are
+    # diverted to stderr, the JSON goes to the saved descriptor
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -199,7 +203,7 @@ def main():
                                           else f"{res['steps']} batches, single-threaded C restatement"},
                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=real_stdout, flush=True)
         return
 
     # ------------------------------------------------------------------ our arm (GPU)
@@ -334,7 +338,7 @@ def main():
                             "traversed_edges": float(T.mean()), "ms_window": float(f("ms_window").mean()),
                             "ms_repair": float(f("ms_repair").mean()), "ms_push": float(f("ms_push").mean())},
                "wall_ms_per_step_incl_flush": t_wall * 1e3 / K, "estimates_gathered": gathered_rows}
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

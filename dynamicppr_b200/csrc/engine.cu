@@ -510,6 +510,26 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
     m.has_window = true;
     int *werr = (int *)(counters_.ptr + 3);
     DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, sizeof(uint32_t) * 3, st_));
+    WindowView wv{V_, vmeta_.ptr, pool_.ptr, outdeg_.ptr, pool_top_.ptr, pool_cap_, werr};
+    if (nA <= kFusedMaxEntries && env_int("DPPR_FUSED_WINDOW", 1)) {
+        // small batch: the whole update in one single-CTA launch (window_fused.cuh)
+        FusedArgs f{};
+        f.log = log_.ptr; f.W = W_; f.log_start = log_start_; f.arriving = arriving; f.B = B;
+        f.directed = D_ == 1; f.key_bits = key_bits_;
+        for (int i = 0; i < 2; ++i) { f.akey[i] = akey_[i].ptr; f.aval[i] = aval_[i].ptr; f.bkey[i] = bkey_[i].ptr; f.bval[i] = bval_[i].ptr; }
+        f.segA = segA_; f.segB = segB_; f.w = wv;
+        f.ins_pos = ins_pos_.ptr; f.jobs = jobs_.ptr; f.njobs = counters_.ptr + 2; f.seg_d0 = seg_d0_.ptr;
+        win_fused_small<<<1, kFusedThreads, 0, st_>>>(f); ++launch_counter();
+        const int res = ((key_bits_ + 7) / 8) & 1;  // same parity rule as sort_pairs
+        sa_key_ = akey_[res].ptr; sa_val_ = aval_[res].ptr;
+        if (D_ == 1) { sb_key_ = bkey_[res].ptr; sb_val_ = bval_[res].ptr; }
+        else { sb_key_ = sa_key_; sb_val_ = sa_val_; }
+        log_start_ = (log_start_ + B) % W_;
+        DPPR_CUDA(cudaGetLastError());
+        record(2);
+        batch_pending_ = true;
+        return;
+    }
     win_batch_entries<<<grid_for(B), kThreads, 0, st_>>>(log_.ptr, W_, log_start_, arriving, B, D_ == 1, V_,
                                                         akey_[0].ptr, aval_[0].ptr, bkey_[0].ptr, bval_[0].ptr, werr); ++launch_counter();
     log_start_ = (log_start_ + B) % W_;
@@ -521,7 +541,6 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
     rle_heads<<<grid_for(nA), kThreads, 0, st_>>>(sa_key_, nA, flags_.ptr); ++launch_counter();
     exclusive_scan<uint32_t>(flags_.ptr, segA_.segof, nA, scan_scratch, nullptr, st_);
     rle_fill<<<grid_for(nA), kThreads, 0, st_>>>(sa_key_, sa_val_, nA, segA_); ++launch_counter();
-    WindowView wv{V_, vmeta_.ptr, pool_.ptr, outdeg_.ptr, pool_top_.ptr, pool_cap_, werr};
     win_plan<<<grid_for(nA), kThreads, 0, st_>>>(segA_, wv, ins_pos_.ptr, jobs_.ptr, counters_.ptr + 2); ++launch_counter();
     win_relocate<<<std::min(grid_for(nA), 4 * sm_count_), kThreads, 0, st_>>>(jobs_.ptr, counters_.ptr + 2, pool_.ptr); ++launch_counter();
     win_insert<<<grid_for(nA), kThreads, 0, st_>>>(sa_key_, sa_val_, nA, segA_, ins_pos_.ptr, wv); ++launch_counter();

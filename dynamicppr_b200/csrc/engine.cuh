@@ -14,6 +14,7 @@
 #include "primitives.cuh"
 #include "window.cuh"
 #include "repair.cuh"
+#include "window_fused.cuh"
 #include "push.cuh"
 #include "push_async.cuh"
 

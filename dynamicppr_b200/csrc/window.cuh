@@ -114,32 +114,38 @@ __global__ void __launch_bounds__(kThreads)
 //   directed  : group A keyed by dst (in-lists), group B keyed by src (out-degree + residual repair)
 //   undirected: the entry set is symmetric, one group keyed by u serves both roles
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void batch_entries_one(int64_t i, int2 *log, int64_t W, int64_t log_start,
+                                                  const int2 *arriving, int64_t B, int directed, int32_t V,
+                                                  uint32_t *akey, uint32_t *aval,
+                                                  uint32_t *bkey, uint32_t *bval, int *errflags) {
+    int64_t slot = log_start + i;
+    if (slot >= W) slot -= W;
+    const int2 old = log[slot];
+    int2 nw = arriving[i];
+    if ((uint32_t)nw.x >= (uint32_t)V || (uint32_t)nw.y >= (uint32_t)V) {
+        atomicOr(errflags, kErrBadId);
+        nw.x = 0; nw.y = 0;
+    }
+    log[slot] = nw;
+    if (directed) {
+        akey[i] = (uint32_t)old.y;     aval[i] = ((uint32_t)old.x << 1);
+        akey[B + i] = (uint32_t)nw.y;  aval[B + i] = ((uint32_t)nw.x << 1) | 1u;
+        bkey[i] = (uint32_t)old.x;     bval[i] = ((uint32_t)old.y << 1);
+        bkey[B + i] = (uint32_t)nw.x;  bval[B + i] = ((uint32_t)nw.y << 1) | 1u;
+    } else {
+        akey[2 * i] = (uint32_t)old.y;              aval[2 * i] = ((uint32_t)old.x << 1);
+        akey[2 * i + 1] = (uint32_t)old.x;          aval[2 * i + 1] = ((uint32_t)old.y << 1);
+        akey[2 * B + 2 * i] = (uint32_t)nw.y;       aval[2 * B + 2 * i] = ((uint32_t)nw.x << 1) | 1u;
+        akey[2 * B + 2 * i + 1] = (uint32_t)nw.x;   aval[2 * B + 2 * i + 1] = ((uint32_t)nw.y << 1) | 1u;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
     win_batch_entries(int2 *__restrict__ log, int64_t W, int64_t log_start, const int2 *__restrict__ arriving, int64_t B,
                       int directed, int32_t V, uint32_t *__restrict__ akey, uint32_t *__restrict__ aval,
                       uint32_t *__restrict__ bkey, uint32_t *__restrict__ bval, int *errflags) {
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < B; i += (int64_t)gridDim.x * kThreads) {
-        int64_t slot = log_start + i;
-        if (slot >= W) slot -= W;
-        const int2 old = log[slot];
-        int2 nw = arriving[i];
-        if ((uint32_t)nw.x >= (uint32_t)V || (uint32_t)nw.y >= (uint32_t)V) {
-            atomicOr(errflags, kErrBadId);
-            nw.x = 0; nw.y = 0;
-        }
-        log[slot] = nw;
-        if (directed) {
-            akey[i] = (uint32_t)old.y;     aval[i] = ((uint32_t)old.x << 1);
-            akey[B + i] = (uint32_t)nw.y;  aval[B + i] = ((uint32_t)nw.x << 1) | 1u;
-            bkey[i] = (uint32_t)old.x;     bval[i] = ((uint32_t)old.y << 1);
-            bkey[B + i] = (uint32_t)nw.x;  bval[B + i] = ((uint32_t)nw.y << 1) | 1u;
-        } else {
-            akey[2 * i] = (uint32_t)old.y;              aval[2 * i] = ((uint32_t)old.x << 1);
-            akey[2 * i + 1] = (uint32_t)old.x;          aval[2 * i + 1] = ((uint32_t)old.y << 1);
-            akey[2 * B + 2 * i] = (uint32_t)nw.y;       aval[2 * B + 2 * i] = ((uint32_t)nw.x << 1) | 1u;
-            akey[2 * B + 2 * i + 1] = (uint32_t)nw.x;   aval[2 * B + 2 * i + 1] = ((uint32_t)nw.y << 1) | 1u;
-        }
-    }
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < B; i += (int64_t)gridDim.x * kThreads)
+        batch_entries_one(i, log, W, log_start, arriving, B, directed, V, akey, aval, bkey, bval, errflags);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -160,73 +166,83 @@ __global__ void __launch_bounds__(kThreads)
         flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
 }
 
-// `scanned` holds the exclusive scan of the head flags on entry and the run index on exit.
+// entry i of the sorted batch belongs to run s (head = first entry of its run).
+// (no __restrict__ on the *_one helpers: the fused single-CTA kernel reads what it wrote earlier in the same
+// launch, so their loads must not be turned into non-coherent LDG.NC)
+__device__ __forceinline__ void rle_fill_one(int64_t i, uint32_t s, bool head, const uint32_t *key,
+                                             const uint32_t *val, int64_t n, const Segments &sg) {
+    const uint32_t k = key[i];
+    const bool last = (i == n - 1) || (key[i + 1] != k);
+    const bool ins = val[i] & 1u;
+    if (head) {
+        sg.vertex[s] = k;
+        sg.start[s] = (uint32_t)i;
+    }
+    if (ins && (head || !(val[i - 1] & 1u))) sg.first_ins[s] = (uint32_t)i;
+    if (last && !ins) sg.first_ins[s] = (uint32_t)i + 1u;
+    if (i == n - 1) {
+        sg.start[s + 1] = (uint32_t)n;
+        *sg.count = s + 1u;
+    }
+    sg.segof[i] = s;
+}
+
+// `sg.segof` holds the exclusive scan of the head flags on entry and the run index on exit.
 __global__ void __launch_bounds__(kThreads)
     rle_fill(const uint32_t *__restrict__ key, const uint32_t *__restrict__ val, int64_t n, Segments sg) {
-    uint32_t *scanned = sg.segof;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-        const uint32_t k = key[i];
-        const bool head = (i == 0) || (key[i - 1] != k);
-        const bool last = (i == n - 1) || (key[i + 1] != k);
-        const uint32_t s = scanned[i] + (head ? 1u : 0u) - 1u;
-        const bool ins = val[i] & 1u;
-        if (head) {
-            sg.vertex[s] = k;
-            sg.start[s] = (uint32_t)i;
-        }
-        if (ins && (head || !(val[i - 1] & 1u))) sg.first_ins[s] = (uint32_t)i;
-        if (last && !ins) sg.first_ins[s] = (uint32_t)i + 1u;
-        if (i == n - 1) {
-            sg.start[s + 1] = (uint32_t)n;
-            *sg.count = s + 1u;
-        }
-        scanned[i] = s;  // each thread rewrites only its own slot, after reading it
+        const bool head = (i == 0) || (key[i - 1] != key[i]);
+        rle_fill_one(i, sg.segof[i] + (head ? 1u : 0u) - 1u, head, key, val, n, sg);  // each thread rewrites only its own slot
     }
 }
 
 // one thread per touched vertex: expire (advance head), reserve room for the inserts, grow the ring
+__device__ __forceinline__ void plan_one(uint32_t s, const Segments &sg, const WindowView &w, uint32_t *ins_pos,
+                                         RelocJob *jobs, uint32_t *njobs) {
+    const uint32_t v = sg.vertex[s];
+    const uint32_t st = sg.start[s], fi = sg.first_ins[s], en = sg.start[s + 1];
+    uint32_t ndel = fi - st;
+    const uint32_t nins = en - fi;
+    uint4 q = w.vmeta[v];
+    VMeta m{q.x, q.y, q.z, q.w};
+    if (ndel > m.len) {  // the caller slid edges the window never held
+        atomicOr(w.errflags, kErrUnderflow);
+        ndel = m.len;
+    }
+    if (ndel) {
+        m.head = (m.head + ndel) & (m.cap - 1u);
+        m.len -= ndel;
+    }
+    uint32_t pos = m.len;
+    if (nins) {
+        const uint32_t need = m.len + nins;
+        if (need > m.cap) {
+            const uint32_t ncap = ring_capacity_for(need);
+            const unsigned long long nb = atomicAdd(w.pool_top, (unsigned long long)ncap);
+            if (nb + ncap > w.pool_cap) {
+                atomicOr(w.errflags, kErrPool);
+                pos = 0xffffffffu;  // inserts of this run are dropped; engine is flagged unhealthy
+            } else {
+                if (m.len) {
+                    const uint32_t j = atomicAdd(njobs, 1u);
+                    jobs[j] = RelocJob{m.base, m.head, m.cap, m.len, (uint32_t)nb, 0u};
+                }
+                m.base = (uint32_t)nb;
+                m.head = 0u;
+                m.cap = ncap;
+            }
+        }
+        if (pos != 0xffffffffu) m.len += nins;
+    }
+    ins_pos[s] = pos;
+    w.vmeta[v] = make_uint4(m.base, m.head, m.len, m.cap);
+}
+
 __global__ void __launch_bounds__(kThreads)
     win_plan(Segments sg, WindowView w, uint32_t *__restrict__ ins_pos, RelocJob *__restrict__ jobs, uint32_t *njobs) {
     const uint32_t nseg = *sg.count;
-    for (uint32_t s = blockIdx.x * kThreads + threadIdx.x; s < nseg; s += gridDim.x * kThreads) {
-        const uint32_t v = sg.vertex[s];
-        const uint32_t st = sg.start[s], fi = sg.first_ins[s], en = sg.start[s + 1];
-        uint32_t ndel = fi - st;
-        const uint32_t nins = en - fi;
-        uint4 q = w.vmeta[v];
-        VMeta m{q.x, q.y, q.z, q.w};
-        if (ndel > m.len) {  // the caller slid edges the window never held
-            atomicOr(w.errflags, kErrUnderflow);
-            ndel = m.len;
-        }
-        if (ndel) {
-            m.head = (m.head + ndel) & (m.cap - 1u);
-            m.len -= ndel;
-        }
-        uint32_t pos = m.len;
-        if (nins) {
-            const uint32_t need = m.len + nins;
-            if (need > m.cap) {
-                const uint32_t ncap = ring_capacity_for(need);
-                const unsigned long long nb = atomicAdd(w.pool_top, (unsigned long long)ncap);
-                if (nb + ncap > w.pool_cap) {
-                    atomicOr(w.errflags, kErrPool);
-                    pos = 0xffffffffu;  // inserts of this run are dropped; engine is flagged unhealthy
-                } else {
-                    if (m.len) {
-                        const uint32_t j = atomicAdd(njobs, 1u);
-                        jobs[j] = RelocJob{m.base, m.head, m.cap, m.len, (uint32_t)nb, 0u};
-                    }
-                    m.base = (uint32_t)nb;
-                    m.head = 0u;
-                    m.cap = ncap;
-                }
-            }
-            if (pos != 0xffffffffu) m.len += nins;
-        }
-        ins_pos[s] = pos;
-        w.vmeta[v] = make_uint4(m.base, m.head, m.len, m.cap);
-    }
+    for (uint32_t s = blockIdx.x * kThreads + threadIdx.x; s < nseg; s += gridDim.x * kThreads)
+        plan_one(s, sg, w, ins_pos, jobs, njobs);
 }
 
 // one CTA per relocated ring (grid-stride over jobs)
@@ -241,32 +257,40 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // one thread per entry: inserts take slot head + (len before inserts) + rank within the run
+__device__ __forceinline__ void insert_one(int64_t i, const uint32_t *key, const uint32_t *val,
+                                           const Segments &sg, const uint32_t *ins_pos, const WindowView &w) {
+    const uint32_t x = val[i];
+    if (!(x & 1u)) return;
+    const uint32_t s = sg.segof[i];
+    const uint32_t pos = ins_pos[s];
+    if (pos == 0xffffffffu) return;
+    const uint4 m = w.vmeta[key[i]];
+    const uint32_t rank = (uint32_t)i - sg.first_ins[s];
+    w.pool[m.x + ((m.y + pos + rank) & (m.w - 1u))] = (int32_t)(x >> 1);
+}
+
 __global__ void __launch_bounds__(kThreads)
     win_insert(const uint32_t *__restrict__ key, const uint32_t *__restrict__ val, int64_t n, Segments sg,
                const uint32_t *__restrict__ ins_pos, WindowView w) {
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-        const uint32_t x = val[i];
-        if (!(x & 1u)) continue;
-        const uint32_t s = sg.segof[i];
-        const uint32_t pos = ins_pos[s];
-        if (pos == 0xffffffffu) continue;
-        const uint4 m = w.vmeta[key[i]];
-        const uint32_t rank = (uint32_t)i - sg.first_ins[s];
-        w.pool[m.x + ((m.y + pos + rank) & (m.w - 1u))] = (int32_t)(x >> 1);
-    }
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+        insert_one(i, key, val, sg, ins_pos, w);
 }
 
 // out-degree side (group keyed by src): remember the pre-batch degree for the repair, store the new one
+__device__ __forceinline__ void out_degree_one(uint32_t s, const Segments &sg, int32_t *outdeg,
+                                               int32_t *seg_d0) {
+    const uint32_t u = sg.vertex[s];
+    const uint32_t st = sg.start[s], fi = sg.first_ins[s], en = sg.start[s + 1];
+    const int32_t d0 = outdeg[u];
+    seg_d0[s] = d0;
+    outdeg[u] = d0 + (int32_t)(en - fi) - (int32_t)(fi - st);
+}
+
 __global__ void __launch_bounds__(kThreads)
     win_out_degrees(Segments sg, int32_t *__restrict__ outdeg, int32_t *__restrict__ seg_d0) {
     const uint32_t nseg = *sg.count;
-    for (uint32_t s = blockIdx.x * kThreads + threadIdx.x; s < nseg; s += gridDim.x * kThreads) {
-        const uint32_t u = sg.vertex[s];
-        const uint32_t st = sg.start[s], fi = sg.first_ins[s], en = sg.start[s + 1];
-        const int32_t d0 = outdeg[u];
-        seg_d0[s] = d0;
-        outdeg[u] = d0 + (int32_t)(en - fi) - (int32_t)(fi - st);
-    }
+    for (uint32_t s = blockIdx.x * kThreads + threadIdx.x; s < nseg; s += gridDim.x * kThreads)
+        out_degree_one(s, sg, outdeg, seg_d0);
 }
 
 // ---------------------------------------------------------------------------------------------
