@@ -246,7 +246,7 @@ __device__ void async_switcher(const AsyncArgs &a, const AsyncQueue &q, int phas
     gens_out = __shfl_sync(kFull, gen, 0);
 }
 
-__device__ void async_worker(const AsyncArgs &a, const AsyncQueue &q, AsyncWarpSmem &ws, volatile unsigned long long *cta_fence,
+__device__ void async_worker(const AsyncArgs &a, const AsyncQueue &q, AsyncWarpSmem &ws, unsigned long long *cta_fence,
                              int phase, unsigned long long &edges_acc, unsigned long long &pops_acc,
                              unsigned long long &hubs_acc) {
     const PushArgs &b = a.base;
@@ -266,11 +266,11 @@ __device__ void async_worker(const AsyncArgs &a, const AsyncQueue &q, AsyncWarpS
         }
         // the CTA shares one cached copy of the fence word; an idle warp refreshes it from global memory
         unsigned long long fw = 0;
-        if (lane == 0) {
-            fw = *cta_fence;
+        if (lane == 0) {  // fence words only grow (generation and position are monotone), so the cache is a max
+            fw = atomicMax(cta_fence, 0ull);
             if (idle != 0 && (idle & 1u)) {
                 const unsigned long long g = ld_relaxed_u64(q.fence);
-                if (g > fw || (g & kFenceOver)) { fw = g; *cta_fence = g; }
+                if (g > fw) { fw = g; atomicMax(cta_fence, g); }
             }
         }
         fw = __shfl_sync(kFull, fw, 0);
