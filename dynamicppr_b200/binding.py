@@ -14,7 +14,7 @@ ENGINE_AUTO, ENGINE_STEPWISE, ENGINE_ASYNC, ENGINE_LEVELSYNC = 0, 1, 2, 3
 # every symbol include/dppr.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = [
     "dppr_version", "dppr_last_error", "dppr_create", "dppr_destroy", "dppr_init_window",
-    "dppr_init_window_pairs", "dppr_solve_initial", "dppr_apply_batch", "dppr_apply_batch_pairs",
+    "dppr_init_window_pairs", "dppr_init_window_device_pairs", "dppr_generate_rmat_device", "dppr_solve_initial", "dppr_apply_batch", "dppr_apply_batch_pairs",
     "dppr_apply_batch_device_pairs", "dppr_refresh", "dppr_slide", "dppr_slide_pairs",
     "dppr_slide_device_pairs", "dppr_sync", "dppr_get_batch_stats", "dppr_batches_done",
     "dppr_get_estimates", "dppr_get_residuals", "dppr_copy_estimates_device", "dppr_export_window_csr",
@@ -75,6 +75,8 @@ def load_library():
     L.dppr_destroy.argtypes = [vp]; L.dppr_destroy.restype = None
     L.dppr_init_window.argtypes = [vp, i32p, i32p, C.c_int64]
     L.dppr_init_window_pairs.argtypes = [vp, i32p, C.c_int64]
+    L.dppr_init_window_device_pairs.argtypes = [vp, vp, C.c_int64]
+    L.dppr_generate_rmat_device.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_uint64, vp]
     L.dppr_solve_initial.argtypes = [vp]
     for name in ("dppr_apply_batch", "dppr_slide"):
         getattr(L, name).argtypes = [vp, i32p, i32p, C.c_int64]
@@ -165,6 +167,9 @@ class DynamicPPR:
         a = np.ascontiguousarray(edge1, np.int32); b = np.ascontiguousarray(edge2, np.int32)
         self._check(self.L.dppr_init_window(self.h, _i32(a), _i32(b), len(a)))
 
+    def init_window_device_pairs(self, device_ptr, n):
+        self._check(self.L.dppr_init_window_device_pairs(self.h, C.c_void_p(int(device_ptr)), int(n)))
+
     def solve_initial(self):
         self._check(self.L.dppr_solve_initial(self.h))
 
@@ -250,6 +255,14 @@ class DynamicPPR:
         self._check(self.L.dppr_set_state(self.h, source_index,
                                           pp.ctypes.data_as(f64p) if pp is not None else None,
                                           rr.ctypes.data_as(f64p) if rr is not None else None))
+
+
+def generate_rmat_device(V, M, seed, device_ptr, device=0):
+    """fill M int32 pairs of device memory with a seeded R-MAT stream (see include/dppr.h)"""
+    L = load_library()
+    rc = L.dppr_generate_rmat_device(device, int(V), int(M), int(seed), C.c_void_p(int(device_ptr)))
+    if rc != 0:
+        raise DpprError(rc, L.dppr_last_error(None).decode())
 
 
 def kernel_launches() -> int:

@@ -90,6 +90,9 @@ int dppr_init_window(dppr_engine *e, const int32_t *e1, const int32_t *e2, int64
 int dppr_init_window_pairs(dppr_engine *e, const int32_t *pairs, int64_t n) {
     return guarded(e, [&](dppr::Engine &g) { g.init_window_pairs(pairs, n); });
 }
+int dppr_init_window_device_pairs(dppr_engine *e, const int32_t *dpairs, int64_t n) {
+    return guarded(e, [&](dppr::Engine &g) { g.init_window_device_pairs(dpairs, n); });
+}
 int dppr_solve_initial(dppr_engine *e) {
     return guarded(e, [&](dppr::Engine &g) { g.solve_initial(); });
 }
@@ -150,6 +153,59 @@ int dppr_debug_ctalog(dppr_engine *e, unsigned long long *out, int32_t cap_rows,
 }
 
 unsigned long long dppr_kernel_launches(void) { return dppr::launch_counter(); }
+
+// ---- synthetic stream generator on the device -------------------------------------------
+namespace {
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {  // splitmix64 finaliser
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+// R-MAT (a, b, c, d) with `scale` levels, counter-based: edge i is a pure function of (seed, i)
+__global__ void rmat_kernel(int2 *out, long long M, int V, int scale, unsigned long long seed, unsigned ta, unsigned tab,
+                            unsigned tabc, unsigned long long mult, unsigned long long add) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long src = 0, dst = 0;
+        unsigned long long h = 0;
+        for (int l = 0; l < scale; ++l) {
+            if ((l & 1) == 0) h = mix64(seed ^ ((unsigned long long)i * 0x100000001b3ull + (unsigned long long)(l >> 1)));
+            const unsigned r = (l & 1) ? (unsigned)(h >> 32) : (unsigned)h;  // 32 uniform bits per level
+            const unsigned sbit = r >= tab, dbit = (r >= ta && r < tab) || r >= tabc;
+            src = (src << 1) | sbit;
+            dst = (dst << 1) | dbit;
+        }
+        src %= (unsigned long long)V; dst %= (unsigned long long)V;
+        out[i] = make_int2((int)((src * mult + add) % (unsigned long long)V), (int)((dst * mult + add) % (unsigned long long)V));
+    }
+}
+}  // namespace
+
+int dppr_generate_rmat_device(int32_t device, int32_t V, int64_t M, uint64_t seed, int32_t *device_pairs) {
+    using namespace dppr;
+    try {
+        if (V <= 1 || M < 0 || !device_pairs) throw InvalidArgument("bad arguments");
+        DPPR_CUDA(cudaSetDevice(device));
+        int scale = 1;
+        while ((1ll << scale) < (long long)V) ++scale;
+        unsigned long long mult = 2654435761ull % (unsigned long long)V;
+        auto gcd = [](unsigned long long a, unsigned long long b) { while (b) { unsigned long long t = a % b; a = b; b = t; } return a; };
+        while (gcd(mult, (unsigned long long)V) != 1) ++mult;
+        const double a = 0.57, b = 0.19, c = 0.19;
+        const unsigned ta = (unsigned)(a * 4294967296.0), tab = (unsigned)((a + b) * 4294967296.0),
+                       tabc = (unsigned)((a + b + c) * 4294967296.0);
+        rmat_kernel<<<148 * 8, 256>>>((int2 *)device_pairs, M, V, scale, seed, ta, tab, tabc, mult, mix64(seed) % (unsigned long long)V);
+        DPPR_CUDA(cudaGetLastError());
+        DPPR_CUDA(cudaDeviceSynchronize());
+        return DPPR_OK;
+    } catch (const InvalidArgument &x) {
+        g_create_error = x.what();
+        return DPPR_E_INVALID;
+    } catch (const std::exception &x) {
+        g_create_error = x.what();
+        return DPPR_E_CUDA;
+    }
+}
 
 // ---- primitive test hooks ------------------------------------------------------------------------
 int dppr_test_sort_pairs(int32_t device, uint32_t *keys, uint32_t *vals, int64_t n, int32_t key_bits) {

@@ -267,6 +267,18 @@ void Engine::init_window_pairs(const int32_t *pairs, int64_t n) {
     if (n != W_) throw InvalidArgument("init_window needs exactly window_edges edges (InitWindowStream asserts the same)");
     DPPR_CUDA(cudaSetDevice(dev_));
     DPPR_CUDA(cudaMemcpyAsync(log_.ptr, pairs, sizeof(int2) * (size_t)W_, cudaMemcpyHostToDevice, st_));
+    build_initial_window();
+}
+
+void Engine::init_window_device_pairs(const int32_t *dpairs, int64_t n) {
+    if (!dpairs) throw InvalidArgument("null device edge array");
+    if (n != W_) throw InvalidArgument("init_window needs exactly window_edges edges (InitWindowStream asserts the same)");
+    DPPR_CUDA(cudaSetDevice(dev_));
+    DPPR_CUDA(cudaMemcpyAsync(log_.ptr, dpairs, sizeof(int2) * (size_t)W_, cudaMemcpyDeviceToDevice, st_));
+    build_initial_window();
+}
+
+void Engine::build_initial_window() {
     log_start_ = 0;
 
     DevBuf<uint32_t> key[2], val[2], indeg, caps, rowptr, capbase, scratch, total;

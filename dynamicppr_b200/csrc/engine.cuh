@@ -34,6 +34,7 @@ public:
 
     void init_window_pairs(const int32_t *pairs, int64_t n);
     void init_window_soa(const int32_t *e1, const int32_t *e2, int64_t n);
+    void init_window_device_pairs(const int32_t *dpairs, int64_t n);
     void solve_initial();
     void apply_batch_host_pairs(const int32_t *pairs, int64_t B);
     void apply_batch_host_soa(const int32_t *e1, const int32_t *e2, int64_t B);
@@ -59,6 +60,7 @@ private:
         bool has_upload = false, has_window = false;
     };
     void apply_batch_common(const int2 *arriving, int64_t B);
+    void build_initial_window();
     void launch_push(bool init_mode);
     void launch_push_stepwise(PushArgs &a);
     void launch_push_async(PushArgs &a);

@@ -116,6 +116,8 @@ void dppr_destroy(dppr_engine *e);
  * (EdgeBatch.h:6-30); the pairs form takes the .bin payload as it lies in the file. */
 int dppr_init_window(dppr_engine *e, const int32_t *edge1, const int32_t *edge2, int64_t n);
 int dppr_init_window_pairs(dppr_engine *e, const int32_t *pairs, int64_t n);
+/* same, the W edges already resident in device memory (W x int32 pairs) */
+int dppr_init_window_device_pairs(dppr_engine *e, const int32_t *device_pairs, int64_t n);
 
 /* Replaces: Init<<<>>> + ExecuteMainLoop(0) of PPRGPU::DynamicExecute (gpu/PPRGPU.cuh:84-89):
  * r[s]=1, p=0, push phase 0 to exhaustion on the initial window, for every source. */
@@ -161,6 +163,11 @@ int dppr_copy_estimates_device(dppr_engine *e, int32_t source_index, void *devic
  * sorts on the device; not part of the hot path. */
 int dppr_export_window_csr(dppr_engine *e, int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_deg);
 int64_t dppr_window_csr_entries(const dppr_engine *e); /* E_w = D*W */
+
+/* Synthetic directed R-MAT stream (a,b,c,d = 0.57,0.19,0.19,0.05; ids folded and relabelled into [0,V)) written as
+ * M int32 pairs into caller-owned DEVICE memory.  Counter-based: edge i depends on (seed, i) only.  Stands in for
+ * the reference's offline encoder (encoder/GraphEncoder.h:20-98) for shapes too large to ship. */
+int dppr_generate_rmat_device(int32_t device, int32_t vertex_count, int64_t n_edges, uint64_t seed, int32_t *device_pairs);
 
 /* ---- test hooks (used by tests/ only) ---------------------------------------------------- */
 /* overwrite (p, r) of one source (V doubles each; either may be NULL) */

@@ -1,0 +1,60 @@
+"""GPU: BASELINE.json configs at FULL size, checked through size-independent properties (no oracle run needed):
+  * canonical window CSR bit-exact against a numpy lexsort of the same window of the stream,
+  * residual bound |r| <= eps,
+  * the push invariant  p[u] + a r[u] = a [u==s] + (1-a)/(outdeg(u)+1) * sum_{w in out(u)} p[w]  for EVERY vertex
+     -- together with the residual bound it implies |p - pi| <= eps, i.e. the 2-eps parity criterion.
+Config 1 (dblp-shaped) and config 2 (youtube-shaped) run here; configs 3-5 are driven by scripts/run_config.py."""
+import numpy as np
+import pytest
+
+from dynamicppr_b200 import DynamicPPR, graphgen, stream
+
+pytestmark = pytest.mark.gpu
+ALPHA = 0.15
+
+
+def numpy_window_csr(V, directed, win):
+    dst, src = win[:, 1].astype(np.int64), win[:, 0].astype(np.int64)
+    if not directed:
+        dst, src = np.concatenate([dst, win[:, 0]]), np.concatenate([src, win[:, 1]])
+    order = np.lexsort((src, dst))
+    rp = np.zeros(V + 1, np.int64)
+    np.cumsum(np.bincount(dst, minlength=V), out=rp[1:])
+    return rp.astype(np.int32), src[order].astype(np.int32), np.bincount(src, minlength=V).astype(np.int32)
+
+
+def invariant_defect(V, rp, ci, od, p, r, source):
+    """max_u | p + a r - a e_s - (1-a)/(d+1) * sum_{w in out(u)} p[w] |  from the exported in-CSR"""
+    indeg = np.diff(rp)
+    acc = np.bincount(ci, weights=np.repeat(p, indeg), minlength=V)  # edge u->w sits in row w, column u
+    lhs = p + ALPHA * r
+    lhs[source] -= ALPHA
+    return np.abs(lhs - (1 - ALPHA) * acc / (od + 1.0)).max()
+
+
+@pytest.mark.parametrize("shape,source_kind,batches", [("dblp", "s1", 100), ("youtube", "top", 100)])
+def test_baseline_config_full_size(shape, source_kind, batches):
+    V, M, directed = graphgen.SHAPES[shape]
+    edges = graphgen.powerlaw_undirected(V, M, graphgen.BASE_SEED + list(graphgen.SHAPES).index(shape))
+    wl = stream.workload(M, 0.1, 0, 0.01, batches)
+    src = 1 if source_kind == "s1" else int(graphgen.top_out_degree(V, edges, directed, 1)[0])
+    eps = 1e-9
+    with DynamicPPR(V, directed, wl.W, wl.B, [src], epsilon=eps) as eng:
+        eng.init_window_pairs(edges[: wl.W])
+        eng.solve_initial()
+        for k in range(batches + 1):
+            if k > 0:
+                lo = wl.W + (k - 1) * wl.B
+                eng.slide_pairs(edges[lo: lo + wl.B])
+            if k not in (0, 1, batches // 2, batches):
+                continue
+            assert eng.stats().error_flags == 0
+            rp, ci, od = eng.export_window_csr()
+            erp, eci, eod = numpy_window_csr(V, directed, edges[k * wl.B: k * wl.B + wl.W])
+            np.testing.assert_array_equal(rp, erp)
+            np.testing.assert_array_equal(ci, eci)
+            np.testing.assert_array_equal(od, eod)
+            p, r = eng.estimates(), eng.residuals()
+            assert np.abs(r).max() <= eps
+            assert invariant_defect(V, rp, ci, od, p, r, src) <= 1e-13
+            assert abs(p.sum()) < 1e6 and np.all(np.isfinite(p))
