@@ -16,7 +16,7 @@ all: lib cli
 lib: $(LIBDIR)/libdppr.so
 $(LIBDIR)/libdppr.so: $(CSRC)/engine.cu $(CSRC)/capi.cu $(HDRS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) $(PTXAS_V) -shared -o $@ $(CSRC)/capi.cu -lcudart
+	$(NVCC) $(NVFLAGS) $(PTXAS_V) $(DPPR_DEFS) -shared -o $@ $(CSRC)/capi.cu -lcudart
 
 cli: $(BINDIR)/pagerank
 $(BINDIR)/pagerank: $(wildcard $(HOST)/*.cpp) $(wildcard $(HOST)/*.h) include/dppr.h $(LIBDIR)/libdppr.so

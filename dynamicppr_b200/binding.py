@@ -54,7 +54,8 @@ class BatchStats(C.Structure):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "lib", "libdppr.so")
+    # DPPR_LIB: A/B runs of differently tuned builds of the same library (development aid)
+    return os.environ.get("DPPR_LIB") or os.path.join(_HERE, "lib", "libdppr.so")
 
 
 def load_library():

@@ -46,7 +46,10 @@ constexpr int kStage = 1024;            // staged next-frontier items per CTA
 #ifndef DPPR_MIN_BLOCKS
 #define DPPR_MIN_BLOCKS 4
 #endif
-constexpr int kEdgeUnroll = 4;          // in-edges per thread per round: independent load/atomic chains in flight
+#ifndef DPPR_EDGE_UNROLL
+#define DPPR_EDGE_UNROLL 4
+#endif
+constexpr int kEdgeUnroll = DPPR_EDGE_UNROLL;          // in-edges per thread per round: independent load/atomic chains in flight
 constexpr int kHubChunk = kEdgeUnroll * kThreads;  // edges of a hub one CTA takes at a time
 constexpr int kHubSmem = 1024;          // hub chunk offsets cached in shared memory for the owner search
 
@@ -456,7 +459,7 @@ __device__ void expand_tiles(const PushArgs &a, PushSmem &sm, const unsigned lon
         if (tile == blockIdx.x) DPPR_TL(tl, 3);
         // ---- edges ----
         for (uint32_t e0 = 0; e0 < total; e0 += kHubChunk) {
-            TileOwner ow{sm, {0u, 0u, 0u, 0u}, a.Vp};
+            TileOwner ow{sm, {}, a.Vp};
             uint32_t nbr[kEdgeUnroll];
             bool active[kEdgeUnroll];
 #pragma unroll

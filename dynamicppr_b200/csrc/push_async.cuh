@@ -346,7 +346,7 @@ __device__ void async_worker(const AsyncArgs &a, const AsyncQueue &q, AsyncWarpS
         __syncwarp();
         // ---- edges: 32 x kEdgeUnroll per round ----
         for (uint32_t e0 = 0; e0 < total; e0 += 32 * kEdgeUnroll) {
-            AsyncTileOwner ow{ws, {0u, 0u, 0u, 0u}, b.Vp};
+            AsyncTileOwner ow{ws, {}, b.Vp};
             uint32_t nbr[kEdgeUnroll];
             bool active[kEdgeUnroll];
 #pragma unroll
