@@ -111,6 +111,11 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
         async_grid_ = std::min(per_sm, std::max(env_int("DPPR_ASYNC_CTAS_PER_SM", 4), 1)) * sm_count_;
     }
 
+    {
+        int per_sm = 0;
+        DPPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (void *)win_update_coop, kThreads, 0));
+        coop_win_grid_ = per_sm >= 1 ? std::min(kCoopMaxTiles, per_sm * sm_count_) : 0;
+    }
     // window
     log_.alloc((size_t)W_);
     vmeta_.alloc((size_t)V_);
@@ -133,7 +138,8 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     sort_scratch_.alloc(sort_scratch_elems(Nb_) + scan_scratch_elems(Nb_));
     flags_.alloc((size_t)Nb_);
     segA_vertex_.alloc((size_t)Nb_); segA_start_.alloc((size_t)Nb_ + 1); segA_first_.alloc((size_t)Nb_); segA_of_.alloc((size_t)Nb_);
-    counters_.alloc(4);
+    counters_.alloc(8);
+    tile_heads_.alloc(kCoopMaxTiles);
     segA_ = Segments{segA_vertex_.ptr, segA_start_.ptr, segA_first_.ptr, segA_of_.ptr, counters_.ptr + 0};
     if (D_ == 1) {
         segB_vertex_.alloc((size_t)Nb_); segB_start_.alloc((size_t)Nb_ + 1); segB_first_.alloc((size_t)Nb_); segB_of_.alloc((size_t)Nb_);
@@ -538,6 +544,31 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
         else { sb_key_ = sa_key_; sb_val_ = sa_val_; }
         log_start_ = (log_start_ + B) % W_;
         DPPR_CUDA(cudaGetLastError());
+        record(2);
+        batch_pending_ = true;
+        return;
+    }
+    if (nA <= kCoopMaxEntries && coop_win_grid_ > 0 && env_int("DPPR_COOP_WINDOW", 1)) {
+        // mid-size batch: the same stages inside one cooperative launch (window_coop.cuh)
+        CoopArgs c{};
+        c.log = log_.ptr; c.W = W_; c.log_start = log_start_; c.arriving = arriving; c.B = B;
+        c.directed = D_ == 1; c.key_bits = key_bits_;
+        for (int i = 0; i < 2; ++i) { c.akey[i] = akey_[i].ptr; c.aval[i] = aval_[i].ptr; c.bkey[i] = bkey_[i].ptr; c.bval[i] = bval_[i].ptr; }
+        c.hist = sort_scratch_.ptr; c.tile_heads = tile_heads_.ptr;
+        c.segA = segA_; c.segB = segB_; c.w = wv;
+        c.ins_pos = ins_pos_.ptr; c.jobs = jobs_.ptr; c.njobs = counters_.ptr + 2; c.seg_d0 = seg_d0_.ptr;
+        c.bar = counters_.ptr + 4;
+        DPPR_CUDA(cudaMemsetAsync(counters_.ptr + 4, 0, sizeof(uint32_t), st_));
+        const int tiles = div_up(nA, kSortTile);
+        const int grid = std::max(1, std::min(coop_win_grid_, std::max(tiles, div_up(nA, kThreads))));
+        void *params[] = {(void *)&c};
+        DPPR_CUDA(cudaLaunchCooperativeKernel((void *)win_update_coop, dim3(grid), dim3(kThreads), params, 0, st_));
+        ++launch_counter();
+        const int res = ((key_bits_ + 7) / 8) & 1;
+        sa_key_ = akey_[res].ptr; sa_val_ = aval_[res].ptr;
+        if (D_ == 1) { sb_key_ = bkey_[res].ptr; sb_val_ = bval_[res].ptr; }
+        else { sb_key_ = sa_key_; sb_val_ = sa_val_; }
+        log_start_ = (log_start_ + B) % W_;
         record(2);
         batch_pending_ = true;
         return;

@@ -15,6 +15,7 @@
 #include "window.cuh"
 #include "repair.cuh"
 #include "window_fused.cuh"
+#include "window_coop.cuh"
 #include "push.cuh"
 #include "push_async.cuh"
 
@@ -94,7 +95,9 @@ private:
     DevBuf<uint32_t> akey_[2], aval_[2], bkey_[2], bval_[2];
     DevBuf<uint32_t> sort_scratch_, flags_;
     DevBuf<uint32_t> segA_vertex_, segA_start_, segA_first_, segA_of_, segB_vertex_, segB_start_, segB_first_, segB_of_;
-    DevBuf<uint32_t> counters_;  // [0]=nsegA [1]=nsegB [2]=njobs
+    DevBuf<uint32_t> counters_;  // [0]=nsegA [1]=nsegB [2]=njobs [3]=window error flags [4]=coop barrier
+    DevBuf<uint32_t> tile_heads_;
+    int coop_win_grid_ = 0;
     DevBuf<uint32_t> ins_pos_;
     DevBuf<RelocJob> jobs_;
     DevBuf<int32_t> seg_d0_;

@@ -88,35 +88,45 @@ constexpr int kSortTile = kThreads * kSortChunks;           // 2048 keys per CTA
 constexpr int kRadix = 256;
 
 // per-tile digit histogram, laid out digit-major: hist[d * tiles + tile]
-__global__ void __launch_bounds__(kThreads)
-    radix_hist(const uint32_t *__restrict__ keys, uint32_t *__restrict__ hist, int64_t n, int shift, int tiles) {
-    __shared__ uint32_t sh[kRadix];
+// (no __restrict__ on the *_tile helpers: the cooperative window kernel reads what other CTAs wrote earlier in
+// the same launch, so these loads must stay ordinary coherent loads)
+__device__ __forceinline__ void radix_hist_tile(const uint32_t *keys, uint32_t *hist, int64_t n, int shift, int tiles,
+                                                int tile, uint32_t *sh /* kRadix */) {
     sh[threadIdx.x] = 0;
     __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+    const int64_t base = (int64_t)tile * kSortTile;
 #pragma unroll
     for (int k = 0; k < kSortChunks; ++k) {
         int64_t i = base + k * kThreads + threadIdx.x;
         if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (kRadix - 1)], 1u);
     }
     __syncthreads();
-    hist[(size_t)threadIdx.x * tiles + blockIdx.x] = sh[threadIdx.x];
+    hist[(size_t)threadIdx.x * tiles + tile] = sh[threadIdx.x];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads)
+    radix_hist(const uint32_t *__restrict__ keys, uint32_t *__restrict__ hist, int64_t n, int shift, int tiles) {
+    __shared__ uint32_t sh[kRadix];
+    radix_hist_tile(keys, hist, n, shift, tiles, blockIdx.x, sh);
 }
 
 // Stable scatter.  Each warp owns a contiguous run of kSortChunks*32 keys and walks it in order;
 // __match_any_sync gives every lane its rank among equal digits of the chunk, per-warp running
 // digit counts give the rank within the warp's run, a prefix over warps gives the rank within the
 // tile, and the scanned histogram gives the tile's base for that digit.
-__global__ void __launch_bounds__(kThreads)
-    radix_scatter(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout,
-                  uint32_t *__restrict__ vout, const uint32_t *__restrict__ hist_scanned, int64_t n, int shift,
-                  int tiles) {
-    __shared__ uint32_t wcnt[kWarps][kRadix];
-    __shared__ uint32_t gbase[kRadix];
+struct RadixScatterSmem {
+    uint32_t wcnt[kWarps][kRadix];
+    uint32_t gbase[kRadix];
+};
+
+__device__ __forceinline__ void radix_scatter_tile(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, uint32_t *vout,
+                                                   const uint32_t *hist_scanned, int64_t n, int shift, int tiles, int tile,
+                                                   RadixScatterSmem &sm) {
     const unsigned w = warp_id(), l = lane_id();
-    for (int i = threadIdx.x; i < kWarps * kRadix; i += kThreads) (&wcnt[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < kWarps * kRadix; i += kThreads) (&sm.wcnt[0][0])[i] = 0;
     __syncthreads();
-    const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)w * (kSortChunks * 32);
+    const int64_t wbase = (int64_t)tile * kSortTile + (int64_t)w * (kSortChunks * 32);
     uint32_t key[kSortChunks], val[kSortChunks], rnk[kSortChunks];
 #pragma unroll
     for (int c = 0; c < kSortChunks; ++c) {
@@ -126,10 +136,10 @@ __global__ void __launch_bounds__(kThreads)
         val[c] = valid ? vin[i] : 0u;
         const uint32_t d = valid ? ((key[c] >> shift) & (kRadix - 1)) : (uint32_t)kRadix;  // invalid lanes group apart
         const unsigned peers = __match_any_sync(kFull, d);
-        const uint32_t before = valid ? wcnt[w][d] : 0u;
+        const uint32_t before = valid ? sm.wcnt[w][d] : 0u;
         __syncwarp();
         rnk[c] = before + __popc(peers & lanemask_lt());
-        if (valid && l == (unsigned)(__ffs(peers) - 1)) wcnt[w][d] = before + __popc(peers);
+        if (valid && l == (unsigned)(__ffs(peers) - 1)) sm.wcnt[w][d] = before + __popc(peers);
         __syncwarp();
     }
     __syncthreads();
@@ -138,11 +148,11 @@ __global__ void __launch_bounds__(kThreads)
         uint32_t run = 0;
 #pragma unroll
         for (int ww = 0; ww < kWarps; ++ww) {
-            uint32_t c = wcnt[ww][d];
-            wcnt[ww][d] = run;
+            uint32_t c = sm.wcnt[ww][d];
+            sm.wcnt[ww][d] = run;
             run += c;
         }
-        gbase[d] = hist_scanned[(size_t)d * tiles + blockIdx.x];
+        sm.gbase[d] = hist_scanned[(size_t)d * tiles + tile];
     }
     __syncthreads();
 #pragma unroll
@@ -150,11 +160,20 @@ __global__ void __launch_bounds__(kThreads)
         const int64_t i = wbase + c * 32 + l;
         if (i < n) {
             const uint32_t d = (key[c] >> shift) & (kRadix - 1);
-            const uint32_t pos = gbase[d] + wcnt[w][d] + rnk[c];
+            const uint32_t pos = sm.gbase[d] + sm.wcnt[w][d] + rnk[c];
             kout[pos] = key[c];
             vout[pos] = val[c];
         }
     }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads)
+    radix_scatter(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout,
+                  uint32_t *__restrict__ vout, const uint32_t *__restrict__ hist_scanned, int64_t n, int shift,
+                  int tiles) {
+    __shared__ RadixScatterSmem sm;
+    radix_scatter_tile(kin, vin, kout, vout, hist_scanned, n, shift, tiles, blockIdx.x, sm);
 }
 
 inline size_t sort_scratch_elems(int64_t n) {
