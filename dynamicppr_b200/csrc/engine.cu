@@ -348,6 +348,7 @@ void Engine::launch_push(bool init_mode) {
         a.carry_gamma = g ? std::atof(g) : 1.0;
         a.carry_scale = sc ? std::atof(sc) : 0.01;
     }
+    a.tile_cap = std::min(std::max(env_int("DPPR_TILE_CAP", 128), 8), kTileMax);
     a.iterlog = iterlog_.ptr;
     a.iterlog_cap = iterlog_.ptr ? kIterLogCap : 0;
     a.ctalog = ctalog_.ptr;
