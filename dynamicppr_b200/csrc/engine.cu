@@ -81,6 +81,7 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     if ((uint64_t)V_ >= (1ull << 31)) throw InvalidArgument("vertex ids must fit in 31 bits");
     if (Ew_ >= (int64_t)0xffffffffll) throw InvalidArgument("window too large for 32-bit CSR offsets");
     key_bits_ = bits_for((uint64_t)(V_ - 1));
+    relabel_ = env_int("DPPR_RELABEL", 1) != 0;
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -299,6 +300,30 @@ void Engine::build_initial_window() {
     DPPR_CUDA(cudaMemsetAsync(outdeg_.ptr, 0, outdeg_.bytes(), st_));
     DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, counters_.bytes(), st_));
     int *werr = (int *)(counters_.ptr + 3);
+
+    if (relabel_) {
+        // internal order = descending out-degree of the initial window (window.cuh, "internal vertex order")
+        DevBuf<uint32_t> deg, rk[2], rv[2], rscratch;
+        deg.alloc((size_t)V_);
+        for (int i = 0; i < 2; ++i) { rk[i].alloc((size_t)V_); rv[i].alloc((size_t)V_); }
+        rscratch.alloc(sort_scratch_elems(V_));
+        perm_.alloc((size_t)V_); inv_.alloc((size_t)V_);
+        DPPR_CUDA(cudaMemsetAsync(deg.ptr, 0, deg.bytes(), st_));
+        relabel_degrees<<<grid_for(W_), kThreads, 0, st_>>>(log_.ptr, W_, D_ == 1, V_, deg.ptr, werr); ++launch_counter();
+        const int dbits = bits_for((uint64_t)Ew_);
+        const uint32_t degmax = (uint32_t)((1ull << dbits) - 1);
+        relabel_keys<<<grid_for(V_), kThreads, 0, st_>>>(deg.ptr, degmax, rk[0].ptr, rv[0].ptr, V_); ++launch_counter();
+        const int rr = sort_pairs(rk[0].ptr, rv[0].ptr, rk[1].ptr, rv[1].ptr, V_, dbits, rscratch.ptr, st_);
+        const uint32_t P = (uint32_t)std::max(1, std::min(env_int("DPPR_RELABEL_BLOCKS", 1024), V_));
+        relabel_assign<<<grid_for(V_), kThreads, 0, st_>>>(rv[rr].ptr, perm_.ptr, inv_.ptr, V_, P); ++launch_counter();
+        relabel_log<<<grid_for(W_), kThreads, 0, st_>>>(log_.ptr, W_, perm_.ptr, V_); ++launch_counter();
+        // the sources, in internal ids
+        std::vector<uint32_t> hp((size_t)S_);
+        DPPR_CUDA(cudaStreamSynchronize(st_));
+        for (int s = 0; s < S_; ++s)
+            DPPR_CUDA(cudaMemcpy(&hp[s], perm_.ptr + sources_[s], sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        DPPR_CUDA(cudaMemcpy(src_.ptr, hp.data(), sizeof(uint32_t) * (size_t)S_, cudaMemcpyHostToDevice));
+    }
 
     win_init_entries<<<grid_for(W_), kThreads, 0, st_>>>(log_.ptr, W_, D_ == 1, V_, key[0].ptr, val[0].ptr, indeg.ptr,
                                                         outdeg_.ptr, werr); ++launch_counter();
@@ -537,7 +562,7 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
         f.directed = D_ == 1; f.key_bits = key_bits_;
         for (int i = 0; i < 2; ++i) { f.akey[i] = akey_[i].ptr; f.aval[i] = aval_[i].ptr; f.bkey[i] = bkey_[i].ptr; f.bval[i] = bval_[i].ptr; }
         f.segA = segA_; f.segB = segB_; f.w = wv;
-        f.ins_pos = ins_pos_.ptr; f.jobs = jobs_.ptr; f.njobs = counters_.ptr + 2; f.seg_d0 = seg_d0_.ptr;
+        f.ins_pos = ins_pos_.ptr; f.jobs = jobs_.ptr; f.njobs = counters_.ptr + 2; f.seg_d0 = seg_d0_.ptr; f.perm = perm_.ptr;
         win_fused_small<<<1, kFusedThreads, 0, st_>>>(f); ++launch_counter();
         const int res = ((key_bits_ + 7) / 8) & 1;  // same parity rule as sort_pairs
         sa_key_ = akey_[res].ptr; sa_val_ = aval_[res].ptr;
@@ -557,7 +582,7 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
         for (int i = 0; i < 2; ++i) { c.akey[i] = akey_[i].ptr; c.aval[i] = aval_[i].ptr; c.bkey[i] = bkey_[i].ptr; c.bval[i] = bval_[i].ptr; }
         c.hist = sort_scratch_.ptr; c.tile_heads = tile_heads_.ptr;
         c.segA = segA_; c.segB = segB_; c.w = wv;
-        c.ins_pos = ins_pos_.ptr; c.jobs = jobs_.ptr; c.njobs = counters_.ptr + 2; c.seg_d0 = seg_d0_.ptr;
+        c.ins_pos = ins_pos_.ptr; c.jobs = jobs_.ptr; c.njobs = counters_.ptr + 2; c.seg_d0 = seg_d0_.ptr; c.perm = perm_.ptr;
         c.bar = counters_.ptr + 4;
         DPPR_CUDA(cudaMemsetAsync(counters_.ptr + 4, 0, sizeof(uint32_t), st_));
         const int tiles = div_up(nA, kSortTile);
@@ -575,7 +600,7 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
         return;
     }
     win_batch_entries<<<grid_for(B), kThreads, 0, st_>>>(log_.ptr, W_, log_start_, arriving, B, D_ == 1, V_,
-                                                        akey_[0].ptr, aval_[0].ptr, bkey_[0].ptr, bval_[0].ptr, werr); ++launch_counter();
+                                                        akey_[0].ptr, aval_[0].ptr, bkey_[0].ptr, bval_[0].ptr, werr, perm_.ptr); ++launch_counter();
     log_start_ = (log_start_ + B) % W_;
     uint32_t *scan_scratch = sort_scratch_.ptr + sort_scratch_elems(Nb_);
 
@@ -669,22 +694,38 @@ void Engine::get_vector(int which, int32_t s, double *out) {
     if (!solved_) throw StateError("no estimates before dppr_solve_initial");
     sync();
     const double *src = (which == 0 ? p_.ptr : r_.ptr) + (size_t)s * Vp_;
-    DPPR_CUDA(cudaMemcpy(out, src, sizeof(double) * (size_t)V_, cudaMemcpyDeviceToHost));
+    if (!perm_.ptr) {
+        DPPR_CUDA(cudaMemcpy(out, src, sizeof(double) * (size_t)V_, cudaMemcpyDeviceToHost));
+        return;
+    }
+    DevBuf<double> tmp;
+    tmp.alloc((size_t)V_);
+    gather_by_perm<double><<<grid_for(V_), kThreads, 0, st_>>>(src, 1, perm_.ptr, tmp.ptr, V_); ++launch_counter();
+    DPPR_CUDA(cudaStreamSynchronize(st_));
+    DPPR_CUDA(cudaMemcpy(out, tmp.ptr, sizeof(double) * (size_t)V_, cudaMemcpyDeviceToHost));
 }
 
 void Engine::copy_estimates_device(int32_t s, void *dptr) {
     if (!dptr) throw InvalidArgument("null device pointer");
     if (s < 0 || s >= S_) throw InvalidArgument("source index out of range");
     DPPR_CUDA(cudaSetDevice(dev_));
-    DPPR_CUDA(cudaMemcpyAsync(dptr, p_.ptr + (size_t)s * Vp_, sizeof(double) * (size_t)V_, cudaMemcpyDeviceToDevice, st_));
+    gather_by_perm<double><<<grid_for(V_), kThreads, 0, st_>>>(p_.ptr + (size_t)s * Vp_, 1, perm_.ptr, (double *)dptr, V_); ++launch_counter();
     DPPR_CUDA(cudaStreamSynchronize(st_));
 }
 
 void Engine::set_state(int32_t s, const double *p, const double *r) {
     if (s < 0 || s >= S_) throw InvalidArgument("source index out of range");
     sync();
-    if (p) DPPR_CUDA(cudaMemcpy(p_.ptr + (size_t)s * Vp_, p, sizeof(double) * (size_t)V_, cudaMemcpyHostToDevice));
-    if (r) DPPR_CUDA(cudaMemcpy(r_.ptr + (size_t)s * Vp_, r, sizeof(double) * (size_t)V_, cudaMemcpyHostToDevice));
+    DevBuf<double> tmp;
+    tmp.alloc((size_t)V_);
+    for (int which = 0; which < 2; ++which) {
+        const double *h = which == 0 ? p : r;
+        if (!h) continue;
+        double *dst = (which == 0 ? p_.ptr : r_.ptr) + (size_t)s * Vp_;
+        DPPR_CUDA(cudaMemcpy(tmp.ptr, h, sizeof(double) * (size_t)V_, cudaMemcpyHostToDevice));
+        scatter_by_perm<double><<<grid_for(V_), kThreads, 0, st_>>>(tmp.ptr, perm_.ptr, dst, V_); ++launch_counter();
+        DPPR_CUDA(cudaStreamSynchronize(st_));
+    }
     solved_ = true;
     if (meta_.empty()) meta_.emplace_back();
 }
@@ -716,7 +757,7 @@ void Engine::export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_d
     for (int i = 0; i < 2; ++i) { key[i].alloc((size_t)Ew_); val[i].alloc((size_t)Ew_); }
     scratch.alloc(std::max(sort_scratch_elems(Ew_), scan_scratch_elems(V_)));
     total.alloc(1);
-    win_export_len<<<grid_for(V_), kThreads, 0, st_>>>(vmeta_.ptr, len.ptr, V_); ++launch_counter();
+    win_export_len<<<grid_for(V_), kThreads, 0, st_>>>(vmeta_.ptr, len.ptr, V_, perm_.ptr); ++launch_counter();
     exclusive_scan<uint32_t>(len.ptr, rowptr.ptr, V_, scratch.ptr, total.ptr, st_);
     DPPR_CUDA(cudaMemcpyAsync(rowptr.ptr + V_, total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st_));
     uint32_t htotal = 0;
@@ -725,7 +766,7 @@ void Engine::export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_d
     if ((int64_t)htotal != Ew_)
         throw StateError("window graph holds " + std::to_string(htotal) + " entries, expected " + std::to_string(Ew_));
     win_export_entries<<<grid_for((int64_t)V_ * 32), kThreads, 0, st_>>>(vmeta_.ptr, pool_.ptr, rowptr.ptr, key[0].ptr,
-                                                                      val[0].ptr, V_); ++launch_counter();
+                                                                      val[0].ptr, V_, perm_.ptr, inv_.ptr); ++launch_counter();
     // sort by (dst, src): LSD over the pair = stable sort by src, then stable sort by dst
     int res = sort_pairs(val[0].ptr, key[0].ptr, val[1].ptr, key[1].ptr, Ew_, key_bits_, scratch.ptr, st_);
     uint32_t *k0 = key[res].ptr, *v0 = val[res].ptr, *k1 = key[1 - res].ptr, *v1 = val[1 - res].ptr;
@@ -735,7 +776,13 @@ void Engine::export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_d
     DPPR_CUDA(cudaStreamSynchronize(st_));
     if (in_row_ptr) DPPR_CUDA(cudaMemcpy(in_row_ptr, rowptr.ptr, sizeof(int32_t) * ((size_t)V_ + 1), cudaMemcpyDeviceToHost));
     if (in_col_ind && Ew_ > 0) DPPR_CUDA(cudaMemcpy(in_col_ind, cols, sizeof(int32_t) * (size_t)Ew_, cudaMemcpyDeviceToHost));
-    if (out_deg) DPPR_CUDA(cudaMemcpy(out_deg, outdeg_.ptr, sizeof(int32_t) * (size_t)V_, cudaMemcpyDeviceToHost));
+    if (out_deg) {
+        DevBuf<int32_t> od;
+        od.alloc((size_t)V_);
+        gather_by_perm<int32_t><<<grid_for(V_), kThreads, 0, st_>>>(outdeg_.ptr, 1, perm_.ptr, od.ptr, V_); ++launch_counter();
+        DPPR_CUDA(cudaStreamSynchronize(st_));
+        DPPR_CUDA(cudaMemcpy(out_deg, od.ptr, sizeof(int32_t) * (size_t)V_, cudaMemcpyDeviceToHost));
+    }
 }
 
 }  // namespace dppr

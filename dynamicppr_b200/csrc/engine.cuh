@@ -89,6 +89,8 @@ private:
     DevBuf<uint4> vmeta_;
     DevBuf<int32_t> pool_, outdeg_;
     DevBuf<unsigned long long> pool_top_;
+    DevBuf<uint32_t> perm_, inv_;   // internal vertex order (empty = identity)
+    bool relabel_ = true;
     unsigned long long pool_cap_ = 0;
     // batch scratch
     DevBuf<int2> arriving_;

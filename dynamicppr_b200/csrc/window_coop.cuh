@@ -31,6 +31,7 @@ struct CoopArgs {
     RelocJob *jobs;
     uint32_t *njobs;
     int32_t *seg_d0;
+    const uint32_t *perm;    // caller id -> internal id (null = identity)
     unsigned *bar;           // grid barrier counter, zero at launch
 };
 
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(kThreads) win_update_coop(const CoopArgs a) {
     const uint32_t gtid = blockIdx.x * kThreads + threadIdx.x, gsize = gridDim.x * kThreads;
     for (uint32_t i = gtid; i < B; i += gsize)
         batch_entries_one(i, a.log, a.W, a.log_start, a.arriving, a.B, a.directed, a.w.V, a.akey[0], a.aval[0], a.bkey[0],
-                          a.bval[0], a.w.errflags);
+                          a.bval[0], a.w.errflags, a.perm);
     if (!coop_barrier(a.bar, gen, sm.abort_flag, a.w.errflags)) return;
     const int ra = coop_sort_and_rle(a, a.akey, a.aval, n, a.segA, sm, gen, alive);
     if (!alive) return;

@@ -133,6 +133,7 @@ struct FusedArgs {
     RelocJob *jobs;
     uint32_t *njobs;
     int32_t *seg_d0;
+    const uint32_t *perm;    // caller id -> internal id (null = identity)
 };
 
 __global__ void __launch_bounds__(kFusedThreads, 1) win_fused_small(const FusedArgs a) {
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) win_fused_small(const FusedA
     const uint32_t n = a.directed ? 2u * B : 4u * B;
     for (uint32_t i = threadIdx.x; i < B; i += kFusedThreads)
         batch_entries_one(i, a.log, a.W, a.log_start, a.arriving, a.B, a.directed, a.w.V, a.akey[0], a.aval[0], a.bkey[0],
-                          a.bval[0], a.w.errflags);
+                          a.bval[0], a.w.errflags, a.perm);
     __syncthreads();
     // group A: keyed by destination -> in-lists
     const int ra = fused_sort_pairs(a.akey[0], a.aval[0], a.akey[1], a.aval[1], n, a.key_bits, sm);
