@@ -17,7 +17,7 @@ ABI_SYMBOLS = [
     "dppr_init_window_pairs", "dppr_init_window_device_pairs", "dppr_generate_rmat_device", "dppr_solve_initial", "dppr_apply_batch", "dppr_apply_batch_pairs",
     "dppr_apply_batch_device_pairs", "dppr_refresh", "dppr_slide", "dppr_slide_pairs",
     "dppr_slide_device_pairs", "dppr_sync", "dppr_get_batch_stats", "dppr_batches_done",
-    "dppr_get_estimates", "dppr_get_residuals", "dppr_copy_estimates_device", "dppr_export_window_csr",
+    "dppr_get_estimates", "dppr_get_residuals", "dppr_copy_estimates_device", "dppr_export_window_csr", "dppr_export_window_out_csr",
     "dppr_window_csr_entries", "dppr_set_state", "dppr_repair_only", "dppr_test_sort_pairs",
     "dppr_test_exclusive_scan", "dppr_debug_iterlog", "dppr_debug_ctalog", "dppr_kernel_launches",
 ]
@@ -46,7 +46,7 @@ class BatchStats(C.Structure):
         ("touched_vertices", C.c_int64), ("iterations", C.c_int64), ("frontier_pops", C.c_int64),
         ("traversed_edges", C.c_int64), ("hub_pops", C.c_int64), ("relocations", C.c_int64),
         ("pool_used", C.c_int64), ("ms_upload", C.c_float), ("ms_window", C.c_float),
-        ("ms_repair", C.c_float), ("ms_push", C.c_float), ("error_flags", C.c_int32), ("reserved0", C.c_int32),
+        ("ms_repair", C.c_float), ("ms_push", C.c_float), ("error_flags", C.c_int32), ("dense_sweeps", C.c_int32),
     ]
 
     def as_dict(self):
@@ -93,6 +93,7 @@ def load_library():
     L.dppr_get_residuals.argtypes = [vp, C.c_int32, f64p]
     L.dppr_copy_estimates_device.argtypes = [vp, C.c_int32, vp]
     L.dppr_export_window_csr.argtypes = [vp, i32p, i32p, i32p]
+    L.dppr_export_window_out_csr.argtypes = [vp, i32p, i32p]
     L.dppr_window_csr_entries.argtypes = [vp]; L.dppr_window_csr_entries.restype = C.c_int64
     L.dppr_set_state.argtypes = [vp, C.c_int32, f64p, f64p]
     L.dppr_repair_only.argtypes = [vp]
@@ -234,6 +235,16 @@ class DynamicPPR:
         rp = np.empty(self.V + 1, np.int32); ci = np.empty(max(E, 1), np.int32); od = np.empty(self.V, np.int32)
         self._check(self.L.dppr_export_window_csr(self.h, _i32(rp), _i32(ci), _i32(od)))
         return rp, ci[:E], od
+
+    def export_window_out_csr(self):
+        """test hook: (row_ptr, col_ind) of the out-lists, or None when the engine keeps none"""
+        E = self.window_csr_entries()
+        rp = np.empty(self.V + 1, np.int32); ci = np.empty(max(E, 1), np.int32)
+        rc = self.L.dppr_export_window_out_csr(self.h, _i32(rp), _i32(ci))
+        if rc == 1:
+            return None
+        self._check(rc)
+        return rp, ci[:E]
 
     def iterlog(self, cap=4096):
         """debug (needs DPPR_ITERLOG=1 at construction): rows (frontier, hub_chunks, t_ns) per push iteration"""

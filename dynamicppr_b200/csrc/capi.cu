@@ -136,6 +136,14 @@ int dppr_copy_estimates_device(dppr_engine *e, int32_t s, void *dptr) {
 int dppr_export_window_csr(dppr_engine *e, int32_t *rp, int32_t *ci, int32_t *od) {
     return guarded(e, [&](dppr::Engine &g) { g.export_csr(rp, ci, od); });
 }
+int dppr_export_window_out_csr(dppr_engine *e, int32_t *rp, int32_t *ci) {
+    bool have = false;
+    const int rc = guarded(e, [&](dppr::Engine &g) {
+        have = g.has_out_lists();
+        if (have) g.export_csr(rp, ci, nullptr, true);
+    });
+    return rc != 0 ? rc : (have ? 0 : 1);
+}
 int64_t dppr_window_csr_entries(const dppr_engine *e) { return (e && e->impl) ? e->impl->csr_entries() : -1; }
 int dppr_set_state(dppr_engine *e, int32_t s, const double *p, const double *r) {
     return guarded(e, [&](dppr::Engine &g) { g.set_state(s, p, r); });

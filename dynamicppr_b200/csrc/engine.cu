@@ -14,7 +14,7 @@ __global__ void gather_record(BatchRecord *rec, const PushCtrl *ctrl, const uint
     rec->ctrl = *ctrl;
     rec->nseg_in = counters[0];
     rec->nseg_out = counters[1];
-    rec->njobs = counters[2];
+    rec->njobs = counters[2] + counters[5];
     rec->pad = 0;
     rec->pool_top = *pool_top;
 }
@@ -28,8 +28,8 @@ int env_int(const char *name, int dflt) {
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-template <int VAR>
-void *persistent_kernel() { return (void *)push_persistent<VAR>; }
+template <int VAR, bool DENSE = false>
+void *persistent_kernel() { return (void *)push_persistent<VAR, DENSE>; }
 
 }  // namespace
 
@@ -82,6 +82,25 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     if (Ew_ >= (int64_t)0xffffffffll) throw InvalidArgument("window too large for 32-bit CSR offsets");
     key_bits_ = bits_for((uint64_t)(V_ - 1));
     relabel_ = env_int("DPPR_RELABEL", 1) != 0;
+    {
+        // dense iterations (pull.cuh): variant 0 of the level-synchronous engine; an iteration runs as a gather sweep
+        // once it is expected to traverse at least (E_w + 2 V) x sources / DPPR_DENSE_DIV in-edges.  0 disables.
+        const char *dd = std::getenv("DPPR_DENSE_DIV");
+        dense_div_ = dd ? std::atof(dd) : 4.0;
+        // Small windows stay with the scatter-only kernel: their iterations are bound by the chain of dependent round
+        // trips, which a sweep does not shorten (BASELINE configs[1]: 43 vs 18 us), and the kernel that can switch
+        // carries more loop state, which costs its scatter iterations +9..+24 % when they are latency-bound (LJ/4,
+        // youtube) and nothing when they are bandwidth-bound (Twitter-shaped).
+        const char *me = std::getenv("DPPR_DENSE_MIN_EDGES");
+        const double min_edges = me ? std::atof(me) : 2.0e7;
+        dense_ = dense_div_ > 0.0 && cfg.variant == DPPR_OPTIMIZED && mode_ == DPPR_ENGINE_LEVELSYNC &&
+                 (double)cfg.window_edges * (cfg.directed ? 1 : 2) * cfg.n_sources >= min_edges;
+        outlists_ = dense_ && D_ == 1;
+        Sp_ = S_ == 1 ? 1 : (S_ + 3) / 4 * 4;
+        pull_warp_min_ = std::max(1, env_int("DPPR_PULL_WARP_MIN", 32));
+        pull_cta_min_ = std::max(pull_warp_min_, env_int("DPPR_PULL_CTA_MIN", 1024));
+        pull_big_min_ = std::max(pull_cta_min_, env_int("DPPR_PULL_BIG_MIN", 65536));
+    }
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -97,7 +116,8 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     DPPR_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
 
     // cooperative grid per variant: every CTA must be co-resident for the software grid barrier
-    void *kern[4] = {persistent_kernel<0>(), persistent_kernel<1>(), persistent_kernel<2>(), persistent_kernel<3>()};
+    void *kern[4] = {dense_ ? persistent_kernel<0, true>() : persistent_kernel<0>(), persistent_kernel<1>(),
+                     persistent_kernel<2>(), persistent_kernel<3>()};
     const int want_per_sm = env_int("DPPR_CTAS_PER_SM", 4);
     for (int v = 0; v < 4; ++v) {
         int per_sm = 0;
@@ -121,7 +141,8 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     log_.alloc((size_t)W_);
     vmeta_.alloc((size_t)V_);
     outdeg_.alloc((size_t)V_);
-    double pc = cfg_.pool_factor * (double)Ew_ + 4096.0;
+    if (outlists_) vmeta_out_.alloc((size_t)V_);
+    double pc = cfg_.pool_factor * (double)Ew_ * (outlists_ ? 2.0 : 1.0) + 4096.0;
     if (pc > 4294967295.0) pc = 4294967295.0;
     pool_cap_ = (unsigned long long)pc;
     pool_.alloc((size_t)pool_cap_);
@@ -150,6 +171,18 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     }
     ins_pos_.alloc((size_t)Nb_);
     jobs_.alloc((size_t)Nb_);
+    if (outlists_) { ins_posB_.alloc((size_t)Nb_); jobsB_.alloc((size_t)Nb_); }
+    if (dense_) {
+        for (int i = 0; i < 2; ++i) {
+            x_[i].alloc((size_t)V_ * Sp_);
+            DPPR_CUDA(cudaMemsetAsync(x_[i].ptr, 0, x_[i].bytes(), st_));  // the padding columns stay zero for good
+        }
+        tile_list_.alloc((size_t)div_up(V_, kThreads) * (Sp_ == 1 ? 1 : Sp_ / 4));
+        bigcap_ = (uint32_t)std::min<int64_t>((Ew_ / pull_big_min_ + 64) * (Sp_ == 1 ? 1 : Sp_ / 4), 1 << 24);
+        big_.alloc(bigcap_);
+        bigacc_.alloc((size_t)bigcap_ * 4);
+        DPPR_CUDA(cudaMemsetAsync(bigacc_.ptr, 0, bigacc_.bytes(), st_));
+    }
     seg_d0_.alloc((size_t)Nb_);
     delta_.alloc((size_t)Nb_ * S_);
     DPPR_CUDA(cudaMemsetAsync(delta_.ptr, 0, delta_.bytes(), st_));
@@ -325,23 +358,30 @@ void Engine::build_initial_window() {
         DPPR_CUDA(cudaMemcpy(src_.ptr, hp.data(), sizeof(uint32_t) * (size_t)S_, cudaMemcpyHostToDevice));
     }
 
-    win_init_entries<<<grid_for(W_), kThreads, 0, st_>>>(log_.ptr, W_, D_ == 1, V_, key[0].ptr, val[0].ptr, indeg.ptr,
-                                                        outdeg_.ptr, werr); ++launch_counter();
-    win_init_caps<<<grid_for(V_), kThreads, 0, st_>>>(indeg.ptr, caps.ptr, V_); ++launch_counter();
-    exclusive_scan<uint32_t>(indeg.ptr, rowptr.ptr, V_, scratch.ptr, nullptr, st_);
-    exclusive_scan<uint32_t>(caps.ptr, capbase.ptr, V_, scratch.ptr, total.ptr, st_);
-    const int res = sort_pairs(key[0].ptr, val[0].ptr, key[1].ptr, val[1].ptr, Ew_, key_bits_, scratch.ptr, st_);
-    win_init_fill<<<grid_for(Ew_), kThreads, 0, st_>>>(key[res].ptr, val[res].ptr, Ew_, rowptr.ptr, capbase.ptr, pool_.ptr); ++launch_counter();
-    win_init_meta<<<grid_for(V_), kThreads, 0, st_>>>(indeg.ptr, caps.ptr, capbase.ptr, vmeta_.ptr, V_); ++launch_counter();
-    DPPR_CUDA(cudaGetLastError());
-    uint32_t htotal = 0;
-    int herr = 0;
-    DPPR_CUDA(cudaMemcpyAsync(&htotal, total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
-    DPPR_CUDA(cudaMemcpyAsync(&herr, werr, sizeof(int), cudaMemcpyDeviceToHost, st_));
-    DPPR_CUDA(cudaStreamSynchronize(st_));
-    if (herr & kErrBadId) throw InvalidArgument("edge endpoint outside [0, vertex_count) (GraphVec.h:55-56 asserts the same)");
-    if ((unsigned long long)htotal > pool_cap_) throw CapacityError("adjacency pool too small for the initial window; raise pool_factor");
-    const unsigned long long top = htotal;
+    // in-lists, then (directed graphs with dense iterations enabled) out-lists behind them in the same pool
+    unsigned long long top = 0;
+    for (int side = 0; side < (outlists_ ? 2 : 1); ++side) {
+        if (side) DPPR_CUDA(cudaMemsetAsync(indeg.ptr, 0, indeg.bytes(), st_));
+        win_init_entries<<<grid_for(W_), kThreads, 0, st_>>>(log_.ptr, W_, D_ == 1, V_, key[0].ptr, val[0].ptr, indeg.ptr,
+                                                            outdeg_.ptr, werr, side); ++launch_counter();
+        win_init_caps<<<grid_for(V_), kThreads, 0, st_>>>(indeg.ptr, caps.ptr, V_); ++launch_counter();
+        exclusive_scan<uint32_t>(indeg.ptr, rowptr.ptr, V_, scratch.ptr, nullptr, st_);
+        exclusive_scan<uint32_t>(caps.ptr, capbase.ptr, V_, scratch.ptr, total.ptr, st_);
+        uint32_t htotal = 0;
+        int herr = 0;
+        DPPR_CUDA(cudaMemcpyAsync(&htotal, total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
+        DPPR_CUDA(cudaMemcpyAsync(&herr, werr, sizeof(int), cudaMemcpyDeviceToHost, st_));
+        DPPR_CUDA(cudaStreamSynchronize(st_));
+        if (herr & kErrBadId) throw InvalidArgument("edge endpoint outside [0, vertex_count) (GraphVec.h:55-56 asserts the same)");
+        if (top + htotal > pool_cap_) throw CapacityError("adjacency pool too small for the initial window; raise pool_factor");
+        const int res = sort_pairs(key[0].ptr, val[0].ptr, key[1].ptr, val[1].ptr, Ew_, key_bits_, scratch.ptr, st_);
+        win_init_fill<<<grid_for(Ew_), kThreads, 0, st_>>>(key[res].ptr, val[res].ptr, Ew_, rowptr.ptr, capbase.ptr, pool_.ptr,
+                                                          (uint32_t)top); ++launch_counter();
+        win_init_meta<<<grid_for(V_), kThreads, 0, st_>>>(indeg.ptr, caps.ptr, capbase.ptr, side ? vmeta_out_.ptr : vmeta_.ptr, V_,
+                                                          (uint32_t)top); ++launch_counter();
+        DPPR_CUDA(cudaGetLastError());
+        top += htotal;
+    }
     DPPR_CUDA(cudaMemcpyAsync(pool_top_.ptr, &top, sizeof(top), cudaMemcpyHostToDevice, st_));
     DPPR_CUDA(cudaStreamSynchronize(st_));
     window_ready_ = true;
@@ -374,6 +414,26 @@ void Engine::launch_push(bool init_mode) {
         a.carry_scale = sc ? std::atof(sc) : 0.01;
     }
     a.tile_cap = std::min(std::max(env_int("DPPR_TILE_CAP", 128), 8), kTileMax);
+    a.V = V_;
+    a.vmeta_out = outlists_ ? vmeta_out_.ptr : vmeta_.ptr;
+    a.x[0] = x_[0].ptr; a.x[1] = x_[1].ptr;
+    a.Sp = Sp_;
+    // cost model: a sweep reads every out-list entry and every vertex row once, whatever the frontier; a scatter
+    // iteration pays one random atomic per traversed in-edge.  Measured ratio ~ DPPR_DENSE_DIV (3): Twitter-shaped
+    // 3.3 ms per sweep vs 17 edges/ns scattered; Orkut/4 97 us vs 40 edges/ns.
+    a.dense_enter_edges = ~0ull;
+    if (dense_) a.dense_enter_edges = (unsigned long long)std::max(1.0, ((double)Ew_ + 2.0 * (double)V_) * (double)S_ / dense_div_);
+    a.dense_exit_edges = a.dense_enter_edges / 2;
+    a.pull_warp_min = pull_warp_min_; a.pull_cta_min = pull_cta_min_; a.pull_big_min = pull_big_min_;
+    a.big = big_.ptr; a.bigcap = bigcap_; a.bigacc = bigacc_.ptr; a.tile_list = tile_list_.ptr;
+    {
+        const uint64_t ntiles = (uint64_t)div_up(V_, kThreads) * (Sp_ == 1 ? 1 : Sp_ / 4);
+        auto gcd = [](uint64_t x, uint64_t y) { while (y) { const uint64_t t = x % y; x = y; y = t; } return x; };
+        uint64_t k = std::max<uint64_t>(1, (uint64_t)(0.6180339887 * (double)ntiles)) | 1ull;
+        while (gcd(k, ntiles) != 1) k += 2;
+        a.pull_tile_mul = (uint32_t)(k % std::max<uint64_t>(ntiles, 1));
+        if (a.pull_tile_mul == 0) a.pull_tile_mul = 1;
+    }
     a.iterlog = iterlog_.ptr;
     a.iterlog_cap = iterlog_.ptr ? kIterLogCap : 0;
     a.ctalog = ctalog_.ptr;
@@ -389,7 +449,7 @@ void Engine::launch_push(bool init_mode) {
     void *params[] = {(void *)&a};
     void *kern = nullptr;
     switch (cfg_.variant) {
-        case 0: kern = persistent_kernel<0>(); break;
+        case 0: kern = dense_ ? persistent_kernel<0, true>() : persistent_kernel<0>(); break;
         case 1: kern = persistent_kernel<1>(); break;
         case 2: kern = persistent_kernel<2>(); break;
         default: kern = persistent_kernel<3>(); break;
@@ -555,6 +615,7 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
     int *werr = (int *)(counters_.ptr + 3);
     DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, sizeof(uint32_t) * 3, st_));
     WindowView wv{V_, vmeta_.ptr, pool_.ptr, outdeg_.ptr, pool_top_.ptr, pool_cap_, werr};
+    WindowView wvo{V_, vmeta_out_.ptr, pool_.ptr, outdeg_.ptr, pool_top_.ptr, pool_cap_, werr};  // vmeta null = no out-lists
     if (nA <= kFusedMaxEntries && env_int("DPPR_FUSED_WINDOW", 1)) {
         // small batch: the whole update in one single-CTA launch (window_fused.cuh)
         FusedArgs f{};
@@ -563,6 +624,7 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
         for (int i = 0; i < 2; ++i) { f.akey[i] = akey_[i].ptr; f.aval[i] = aval_[i].ptr; f.bkey[i] = bkey_[i].ptr; f.bval[i] = bval_[i].ptr; }
         f.segA = segA_; f.segB = segB_; f.w = wv;
         f.ins_pos = ins_pos_.ptr; f.jobs = jobs_.ptr; f.njobs = counters_.ptr + 2; f.seg_d0 = seg_d0_.ptr; f.perm = perm_.ptr;
+        f.wo = wvo; f.ins_posB = ins_posB_.ptr; f.jobsB = jobsB_.ptr; f.njobsB = counters_.ptr + 5;
         win_fused_small<<<1, kFusedThreads, 0, st_>>>(f); ++launch_counter();
         const int res = ((key_bits_ + 7) / 8) & 1;  // same parity rule as sort_pairs
         sa_key_ = akey_[res].ptr; sa_val_ = aval_[res].ptr;
@@ -583,6 +645,7 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
         c.hist = sort_scratch_.ptr; c.tile_heads = tile_heads_.ptr;
         c.segA = segA_; c.segB = segB_; c.w = wv;
         c.ins_pos = ins_pos_.ptr; c.jobs = jobs_.ptr; c.njobs = counters_.ptr + 2; c.seg_d0 = seg_d0_.ptr; c.perm = perm_.ptr;
+        c.wo = wvo; c.ins_posB = ins_posB_.ptr; c.jobsB = jobsB_.ptr; c.njobsB = counters_.ptr + 5;
         c.bar = counters_.ptr + 4;
         DPPR_CUDA(cudaMemsetAsync(counters_.ptr + 4, 0, sizeof(uint32_t), st_));
         const int tiles = div_up(nA, kSortTile);
@@ -625,6 +688,12 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
         sb_key_ = sa_key_; sb_val_ = sa_val_;
     }
     win_out_degrees<<<grid_for(nA), kThreads, 0, st_>>>(segB_, outdeg_.ptr, seg_d0_.ptr); ++launch_counter();
+    if (outlists_) {  // out-lists: the same plan / relocate / insert on the source-sorted entries
+        DPPR_CUDA(cudaMemsetAsync(counters_.ptr + 5, 0, sizeof(uint32_t), st_));
+        win_plan<<<grid_for(nA), kThreads, 0, st_>>>(segB_, wvo, ins_posB_.ptr, jobsB_.ptr, counters_.ptr + 5); ++launch_counter();
+        win_relocate<<<std::min(grid_for(nA), 4 * sm_count_), kThreads, 0, st_>>>(jobsB_.ptr, counters_.ptr + 5, pool_.ptr); ++launch_counter();
+        win_insert<<<grid_for(nA), kThreads, 0, st_>>>(sb_key_, sb_val_, nA, segB_, ins_posB_.ptr, wvo); ++launch_counter();
+    }
     DPPR_CUDA(cudaGetLastError());
     record(2);
     batch_pending_ = true;
@@ -676,6 +745,7 @@ void Engine::get_stats(int64_t batch_index, dppr_batch_stats *out) {
     out->relocations = rec->njobs;
     out->pool_used = (int64_t)rec->pool_top;
     out->error_flags = rec->ctrl.errflags;
+    out->dense_sweeps = (int32_t)rec->ctrl.sweeps;
     auto ms = [&](int a, int b) -> float {
         if (!cfg_.record_timing || !m.ev[a] || !m.ev[b]) return 0.f;
         float t = 0.f;
@@ -749,15 +819,17 @@ int Engine::get_ctalog(unsigned long long *out, int cap_rows) {
 }
 
 // canonical CSR: rows ascending, duplicates kept.  Device sort, test/validation path.
-void Engine::export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_deg) {
+void Engine::export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_deg, bool out_lists) {
     if (!window_ready_) throw StateError("dppr_export_window_csr before dppr_init_window");
+    if (out_lists && !outlists_ && D_ == 1) throw StateError("this engine does not maintain out-lists (dense iterations are off)");
+    const uint4 *vm = (out_lists && outlists_) ? vmeta_out_.ptr : vmeta_.ptr;
     sync();
     DevBuf<uint32_t> len, rowptr, key[2], val[2], scratch, total;
     len.alloc((size_t)V_); rowptr.alloc((size_t)V_ + 1);
     for (int i = 0; i < 2; ++i) { key[i].alloc((size_t)Ew_); val[i].alloc((size_t)Ew_); }
     scratch.alloc(std::max(sort_scratch_elems(Ew_), scan_scratch_elems(V_)));
     total.alloc(1);
-    win_export_len<<<grid_for(V_), kThreads, 0, st_>>>(vmeta_.ptr, len.ptr, V_, perm_.ptr); ++launch_counter();
+    win_export_len<<<grid_for(V_), kThreads, 0, st_>>>(vm, len.ptr, V_, perm_.ptr); ++launch_counter();
     exclusive_scan<uint32_t>(len.ptr, rowptr.ptr, V_, scratch.ptr, total.ptr, st_);
     DPPR_CUDA(cudaMemcpyAsync(rowptr.ptr + V_, total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st_));
     uint32_t htotal = 0;
@@ -765,7 +837,7 @@ void Engine::export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_d
     DPPR_CUDA(cudaStreamSynchronize(st_));
     if ((int64_t)htotal != Ew_)
         throw StateError("window graph holds " + std::to_string(htotal) + " entries, expected " + std::to_string(Ew_));
-    win_export_entries<<<grid_for((int64_t)V_ * 32), kThreads, 0, st_>>>(vmeta_.ptr, pool_.ptr, rowptr.ptr, key[0].ptr,
+    win_export_entries<<<grid_for((int64_t)V_ * 32), kThreads, 0, st_>>>(vm, pool_.ptr, rowptr.ptr, key[0].ptr,
                                                                       val[0].ptr, V_, perm_.ptr, inv_.ptr); ++launch_counter();
     // sort by (dst, src): LSD over the pair = stable sort by src, then stable sort by dst
     int res = sort_pairs(val[0].ptr, key[0].ptr, val[1].ptr, key[1].ptr, Ew_, key_bits_, scratch.ptr, st_);

@@ -47,7 +47,8 @@ public:
     void get_vector(int which, int32_t source_index, double *out);  // 0 = p, 1 = r
     void copy_estimates_device(int32_t source_index, void *dptr);
     void set_state(int32_t source_index, const double *p, const double *r);
-    void export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_deg);
+    void export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_deg, bool out_lists = false);
+    bool has_out_lists() const { return outlists_; }
     int64_t csr_entries() const { return Ew_; }
     int get_iterlog(uint32_t *out, int cap);
     int get_ctalog(unsigned long long *out, int cap_rows);  // debug: 8 stamps per CTA of the probed iteration  // debug: 4 uint32 per iteration of the last refresh
@@ -91,6 +92,18 @@ private:
     DevBuf<unsigned long long> pool_top_;
     DevBuf<uint32_t> perm_, inv_;   // internal vertex order (empty = identity)
     bool relabel_ = true;
+    // dense iterations in gather form (pull.cuh)
+    DevBuf<uint4> vmeta_out_;       // out-lists of a directed graph (undirected: the in-lists serve)
+    DevBuf<uint32_t> ins_posB_;
+    DevBuf<RelocJob> jobsB_;
+    DevBuf<double> x_[2], bigacc_;
+    DevBuf<HubItem> big_;
+    DevBuf<uint32_t> tile_list_;
+    uint32_t bigcap_ = 0;
+    int Sp_ = 1;
+    bool dense_ = false, outlists_ = false;
+    double dense_div_ = 0.0;
+    int pull_warp_min_ = 0, pull_cta_min_ = 0, pull_big_min_ = 0;
     unsigned long long pool_cap_ = 0;
     // batch scratch
     DevBuf<int2> arriving_;

@@ -42,7 +42,10 @@
 
 namespace dppr {
 
-constexpr int kStage = 1024;            // staged next-frontier items per CTA
+#ifndef DPPR_STAGE
+#define DPPR_STAGE 1024
+#endif
+constexpr int kStage = DPPR_STAGE;      // staged next-frontier items per CTA
 #ifndef DPPR_MIN_BLOCKS
 #define DPPR_MIN_BLOCKS 4
 #endif
@@ -51,19 +54,34 @@ constexpr int kStage = 1024;            // staged next-frontier items per CTA
 #endif
 constexpr int kEdgeUnroll = DPPR_EDGE_UNROLL;          // in-edges per thread per round: independent load/atomic chains in flight
 constexpr int kHubChunk = kEdgeUnroll * kThreads;  // edges of a hub one CTA takes at a time
-constexpr int kHubSmem = 1024;          // hub chunk offsets cached in shared memory for the owner search
+#ifndef DPPR_HUB_SMEM
+#define DPPR_HUB_SMEM 1024
+#endif
+constexpr int kHubSmem = DPPR_HUB_SMEM;  // hub chunk offsets cached in shared memory for the owner search
 
 // device-resident control block.  [0, kCtrlZeroBytes) is cleared before every refresh.
 struct PushCtrl {
     unsigned int cnt[3];    // frontier sizes, slot it % 3 is consumed in iteration `it`
-    unsigned int bar;       // grid barrier arrivals (monotone within a launch)
+    unsigned int pad1;
     unsigned long long hpk[3];  // hub lists, slot it % 3 is produced in iteration `it`: (hubs << 32) | edge chunks
+    unsigned long long bar64[2];  // grid barrier words, used alternately: low half = arrivals (monotone within a launch),
+                                  // high half = running sum of the work units the arriving CTAs report
     unsigned long long iters, pops, edges, hubs;
     unsigned long long theta0[2];  // bits of max |r| over the seeds of phase 0 / 1 (positive doubles order like integers)
     unsigned long long carried;    // frontier items carried over untouched (variant 0 threshold schedule)
+    unsigned long long dedges[3];  // dense mode (pull.cuh): in-edges a scatter iteration over the next frontier would traverse
+    unsigned int dcnt[3];          // dense mode: frontier sizes, rotating like cnt
+    unsigned int sweeps;           // dense sweeps of this refresh
+    unsigned int ntiles_active;    // dense mode: length of tile_list
+    unsigned int pad0;
+    unsigned long long bigpk;      // dense mode: grid-tier list of the running sweep, (entries << 32) | chunks
     // ---- persistent across launches ----
     int errflags;
     int level;              // last status stamp handed out (variants 2, 3)
+    // self-calibration of the scatter / gather switch (DENSE kernel): both measured on the device with %globaltimer
+    float sweep_ns;         // duration of one gather sweep in the last dense episode (0 = none measured yet)
+    float rate_ns[2];       // scatter cost per traversed in-edge, written in slot it & 1 during iteration `it`
+    float pad2;
 };
 constexpr size_t kCtrlZeroBytes = offsetof(PushCtrl, errflags);
 
@@ -103,10 +121,28 @@ struct PushArgs {
     double carry_gamma;          // variant 0: iteration k of a phase only pushes items with |r| > max(eps, theta0*scale*gamma^k);
     double carry_scale;          // the rest is put back and carried to the next frontier.  gamma >= 1 disables carrying.
     int32_t tile_cap;            // tile size (frontier items) once a CTA's share of the frontier exceeds 512 items
+    // ---- dense iterations in gather form (pull.cuh), variant 0 ----
+    int32_t V;
+    const uint4 *vmeta_out;      // out-lists (the in-lists themselves when the graph is undirected)
+    double *x[2];                // popped residuals of the running / next sweep, vertex-major [V][Sp]
+    int32_t Sp;                  // sources per vertex row of x: 1, or S rounded up to a multiple of 4
+    unsigned long long dense_enter_edges;  // an iteration expected to traverse at least this many in-edges runs as a sweep
+    unsigned long long dense_exit_edges;   // ... and below this the loop goes back to scatter iterations
+    int32_t pull_warp_min, pull_cta_min, pull_big_min;  // out-degree tiers of a sweep
+    uint32_t pull_tile_mul;      // tile visiting order: tile = (t * mul) mod ntiles, mul coprime to ntiles
+    uint32_t *tile_list;         // active tiles of the running dense episode
+    HubItem *big;                // grid-tier list
+    uint32_t bigcap;
+    double *bigacc;              // [bigcap][4] partial sums of the grid tier (zero between sweeps)
 };
 
-constexpr int kItemsPerThread = 4;                      // frontier items a thread pops per tile, at most
-constexpr int kTileMax = kThreads * kItemsPerThread;    // 1024 items per tile
+#ifndef DPPR_ITEMS_PER_THREAD
+#define DPPR_ITEMS_PER_THREAD 2
+#endif
+// frontier items a thread pops per tile, at most.  2 rather than 4: the tile arrays shrink from 41 KB to 26 KB per CTA,
+// which the SM gives back as L1 (out-degrees and ring slots of popular vertices hit there): -5..-7 % on every probe.
+constexpr int kItemsPerThread = DPPR_ITEMS_PER_THREAD;
+constexpr int kTileMax = kThreads * kItemsPerThread;    // 512 items per tile
 
 struct PushSmem {
     unsigned long long stage[kStage];
@@ -120,6 +156,9 @@ struct PushSmem {
     uint32_t scan[kWarps + 1];
     unsigned int stage_cnt;
     unsigned int gbase;
+    unsigned int pl_n, pl_cnt;   // pull.cuh: CTA-tier list length, legal-count accumulator
+    unsigned long long pl_edges;
+    uint32_t bar_units;          // grid-wide total reported at the last grid barrier
     int abort_flag;
 };
 
@@ -513,40 +552,79 @@ __device__ __forceinline__ unsigned bar_load_relaxed(const unsigned *addr) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ bool grid_barrier(PushCtrl *c, unsigned &gen, int &abort_flag) {
+__device__ __forceinline__ void bar_arrive_release_u64(unsigned long long *addr, unsigned long long inc) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(addr), "l"(inc) : "memory");
+}
+__device__ __forceinline__ unsigned long long bar_load_acquire_u64(const unsigned long long *addr) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long bar_load_relaxed_u64(const unsigned long long *addr) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
+    return v;
+}
+
+// The barrier also SUMS one 32-bit number per CTA (`units`, e.g. the in-edges it traversed in this iteration / 64) at
+// no extra cost: it rides in the high half of the arrival atomic, and every thread finds the grid-wide total of this
+// barrier in sm.bar_units afterwards.  Two words are used alternately, so that the total a slow CTA reads cannot
+// already contain contributions to the next barrier (a CTA reaches barrier g+2 only after everyone has left g+1).
+struct GridBar {
+    unsigned gen = 0;
+    uint32_t prev_hi0 = 0u, prev_hi1 = 0u;  // thread 0: high half of each word at its previous use
+};
+// (Smem: anything with `abort_flag` and `bar_units` members in shared memory)
+// SUM = false: plain barrier (nothing reported, sm.bar_units untouched).
+template <bool SUM = false, class Smem>
+__device__ __forceinline__ bool grid_barrier(PushCtrl *c, GridBar &gb, Smem &sm, uint32_t units = 0) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        ++gen;
-        const unsigned target = gen * gridDim.x;
-        bar_arrive_release(&c->bar);
+        ++gb.gen;
+        const unsigned wsel = gb.gen & 1u;
+        const unsigned target = ((gb.gen + 1u) >> 1) * gridDim.x;
+        unsigned long long *word = &c->bar64[wsel];
+        bar_arrive_release_u64(word, SUM ? (((unsigned long long)units << 32) | 1ull) : 1ull);
         const long long t0 = clock64();
         bool ok = true;
         // poll with a relaxed load: ld.acquire makes ptxas emit CCTL.IVALL (whole-L1 invalidate) after EVERY
         // poll, which stalls the poller and flushes the L1 of the CTAs still working on this SM (ncu: 31 % of
         // all stall samples).  One acquire after the last arrival is enough.
-        while (bar_load_relaxed(&c->bar) < target) {
+        while ((unsigned)bar_load_relaxed_u64(word) < target) {
             if (clock64() - t0 > 8000000000ll) {  // ~4 s: a CTA is missing, give up loudly instead of hanging
                 atomicOr(&c->errflags, kErrWatchdog);
                 ok = false;
                 break;
             }
         }
-        (void)bar_load_acquire(&c->bar);
-        abort_flag = ok ? 0 : 1;
+        const uint32_t hi = (uint32_t)(bar_load_acquire_u64(word) >> 32);
+        if (SUM) {
+            sm.bar_units = hi - (wsel ? gb.prev_hi1 : gb.prev_hi0);
+            if (wsel) gb.prev_hi1 = hi; else gb.prev_hi0 = hi;
+        }
+        sm.abort_flag = ok ? 0 : 1;
     }
     __syncthreads();
-    return abort_flag == 0;
+    return sm.abort_flag == 0;
 }
 
+}  // namespace dppr
+#include "pull.cuh"
+namespace dppr {
+
 // ---- the persistent kernel ----------------------------------------------------------------------------
-template <int VAR>
+// DENSE: with the switch to gather sweeps (variant 0 only).  A separate instantiation, so that the scatter-only
+// kernels keep their register allocation.
+template <int VAR, bool DENSE>
 __global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(const PushArgs a) {
     __shared__ PushSmem sm;
     PushCtrl *c = a.ctrl;
     if (threadIdx.x == 0) { sm.stage_cnt = 0; sm.abort_flag = 0; }
     __syncthreads();
-    unsigned gen = 0;
-    unsigned long long edges_acc = 0, pops_acc = 0, hubs_acc = 0, carried_acc = 0;
+    GridBar gen;
+    unsigned long long edges_acc = 0, pops_acc = 0, hubs_acc = 0, carried_acc = 0, gath_acc = 0;
+    uint32_t sweeps_done = 0;
+    float rate_reg = DENSE ? fmaxf(__ldcg(&c->rate_ns[0]), __ldcg(&c->rate_ns[1])) : 0.f;  // block 0 / thread 0: running estimate
     const int level0 = __ldcg(&c->level);
     uint32_t it = 0, iters_done = 0;  // `it` indexes the rotating slots (skips one value per phase change)
     const int nphases = a.init_mode ? 1 : 2;
@@ -564,62 +642,119 @@ __global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(con
             ++it;
         }
         seed_pass(a, sm, phase, a.q[it & 1], &c->cnt[it % 3]);
-        if (!(alive = grid_barrier(c, gen, sm.abort_flag))) break;
+        if (!(alive = grid_barrier(c, gen, sm))) break;
         const bool carrying = VAR == 0 && a.carry_gamma > 0.0 && a.carry_gamma < 1.0;
         double theta = carrying ? __longlong_as_double((long long)__ldcg(&c->theta0[phase])) * a.carry_scale : a.eps;
-        while (true) {
-            const uint32_t n = __ldcg(&c->cnt[it % 3]);
-            const unsigned long long hpk = __ldcg(&c->hpk[(it + 2) % 3]);
-            const uint32_t nh = (uint32_t)(hpk >> 32);
-            if (n == 0 && nh == 0) break;
-            if ((int)it >= a.max_iters) {
-                if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&c->errflags, kErrWatchdog);
-                alive = false;
-                break;
+        uint32_t n_prev = 0;
+        double t_prev = 0.0;  // in-edges the previous scatter iteration traversed, grid-wide (DENSE)
+        while (alive) {
+            bool want_dense = false;
+            unsigned long long dense_hpk = 0;
+            float dense_rate = 0.f;
+            while (true) {
+                const uint32_t n = __ldcg(&c->cnt[it % 3]);
+                const unsigned long long hpk = __ldcg(&c->hpk[(it + 2) % 3]);
+                // (slot it & 1 was written two iterations ago: the other slot may be being rewritten right now)
+                const float rate = DENSE ? __ldcg(&c->rate_ns[it & 1]) : 0.f, sw = DENSE ? __ldcg(&c->sweep_ns) : 0.f;
+                const uint32_t nh = (uint32_t)(hpk >> 32);
+                if (n == 0 && nh == 0) break;
+                if ((int)it >= a.max_iters) {
+                    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&c->errflags, kErrWatchdog);
+                    alive = false;
+                    break;
+                }
+                if (DENSE && !carrying && n_prev != 0) {
+                    // expected work of this iteration: the tiles the previous one traversed, scaled by the frontier
+                    // growth, plus the hub chunks it left for this one.  Once both costs have been measured on this
+                    // engine (a sweep costs the same whatever the frontier; a scatter iteration pays per edge) the
+                    // measured figures decide, before that the static estimate of the host.
+                    const double pred = t_prev * ((double)n / (double)n_prev) + 0.75 * (double)kHubChunk * (double)(uint32_t)hpk;
+                    const bool enter = (rate > 0.f && sw > 0.f) ? pred * (double)rate > 1.25 * (double)sw
+                                                                 : pred >= (double)a.dense_enter_edges;
+                    if (enter) {  // handled by the outer loop
+                        want_dense = true;
+                        dense_hpk = hpk;
+                        dense_rate = rate;
+                        break;
+                    }
+                }
+                n_prev = n;
+                const unsigned long long edges_before = edges_acc;
+                const unsigned long long t_iter0 = (DENSE && blockIdx.x == 0 && threadIdx.x == 0) ? global_ns() : 0ull;
+                if (blockIdx.x == 0 && threadIdx.x == 0) {  // slots nobody reads or writes during this iteration
+                    c->cnt[(it + 2) % 3] = 0;
+                    c->hpk[(it + 1) % 3] = 0;
+                    hubs_acc += nh;
+                    pops_acc += n;
+                    if (a.iterlog && (int)iters_done < a.iterlog_cap) {
+                        unsigned long long t;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                        a.iterlog[iters_done] = make_uint4(n, (uint32_t)hpk, (uint32_t)t, (uint32_t)(t >> 32));
+                    }
+                }
+                const int level = level0 + (int)it + 1;
+                unsigned long long *tl = (a.ctalog && (int)iters_done == a.probe_iter) ? a.ctalog + (size_t)blockIdx.x * 8 : nullptr;
+                DPPR_TL(tl, 0);
+                const unsigned long long *qin = a.q[it & 1];
+                unsigned long long *qout = a.q[(it + 1) & 1];
+                if (VAR != 0) {
+                    pre_pass<VAR>(a, qin, a.qr[it & 1], n, level);
+                    if (!(alive = grid_barrier(c, gen, sm))) break;
+                }
+                expand_hubs<VAR>(a, sm, a.hub[(it + 1) & 1], hpk, qout, &c->cnt[(it + 1) % 3], phase, level, edges_acc);
+                DPPR_TL(tl, 1);
+                expand_tiles<VAR>(a, sm, qin, a.qr[it & 1], n, qout, &c->cnt[(it + 1) % 3], a.hub[it & 1],
+                                  &c->hpk[it % 3], phase, level, fmax(theta, a.eps), edges_acc, carried_acc, tl);
+                theta *= a.carry_gamma;
+                DPPR_TL(tl, 6);
+                if (VAR == 2) {
+                    if (!(alive = grid_barrier(c, gen, sm))) break;
+                    post_pass(a, sm, qin, a.qr[it & 1], n, qout, &c->cnt[(it + 1) % 3], phase);
+                }
+                if (!(alive = grid_barrier<DENSE>(c, gen, sm, DENSE ? (uint32_t)((edges_acc - edges_before) >> 6) : 0u))) break;
+                if (DENSE) {
+                    const double t_all = 64.0 * (double)sm.bar_units;  // tiles + hub chunks, grid-wide
+                    t_prev = fmax(0.0, t_all - 0.75 * (double)kHubChunk * (double)(uint32_t)hpk);
+                    if (blockIdx.x == 0 && threadIdx.x == 0) {
+                        if (t_all >= 262144.0) {
+                            const float sample = (float)((double)(global_ns() - t_iter0) / t_all);
+                            rate_reg = rate_reg > 0.f ? 0.5f * (rate_reg + sample) : sample;
+                        }
+                        c->rate_ns[it & 1] = rate_reg;
+                    }
+                }
+                DPPR_TL(tl, 7);
+                ++it;
+                ++iters_done;
             }
-            if (blockIdx.x == 0 && threadIdx.x == 0) {  // slots nobody reads or writes during this iteration
+            if (!DENSE || !want_dense || !alive) break;
+            // the frontier is large: this and the following iterations run as gather sweeps (pull.cuh)
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
                 c->cnt[(it + 2) % 3] = 0;
                 c->hpk[(it + 1) % 3] = 0;
-                pops_acc += n;
-                hubs_acc += nh;
-                if (a.iterlog && (int)iters_done < a.iterlog_cap) {
-                    unsigned long long t;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                    a.iterlog[iters_done] = make_uint4(n, (uint32_t)hpk, (uint32_t)t, (uint32_t)(t >> 32));
-                }
+                hubs_acc += (uint32_t)(dense_hpk >> 32);
             }
-            const int level = level0 + (int)it + 1;
-            unsigned long long *tl = (a.ctalog && (int)iters_done == a.probe_iter) ? a.ctalog + (size_t)blockIdx.x * 8 : nullptr;
-            DPPR_TL(tl, 0);
-            const unsigned long long *qin = a.q[it & 1];
-            unsigned long long *qout = a.q[(it + 1) & 1];
-            if (VAR != 0) {
-                pre_pass<VAR>(a, qin, a.qr[it & 1], n, level);
-                if (!(alive = grid_barrier(c, gen, sm.abort_flag))) break;
-            }
-            expand_hubs<VAR>(a, sm, a.hub[(it + 1) & 1], hpk, qout, &c->cnt[(it + 1) % 3], phase, level, edges_acc);
-            DPPR_TL(tl, 1);
-            expand_tiles<VAR>(a, sm, qin, a.qr[it & 1], n, qout, &c->cnt[(it + 1) % 3], a.hub[it & 1],
-                              &c->hpk[it % 3], phase, level, fmax(theta, a.eps), edges_acc, carried_acc, tl);
-            theta *= a.carry_gamma;
-            DPPR_TL(tl, 6);
-            if (VAR == 2) {
-                if (!(alive = grid_barrier(c, gen, sm.abort_flag))) break;
-                post_pass(a, sm, qin, a.qr[it & 1], n, qout, &c->cnt[(it + 1) % 3], phase);
-            }
-            if (!(alive = grid_barrier(c, gen, sm.abort_flag))) break;
-            DPPR_TL(tl, 7);
+            n_prev = 0;  // (no growth estimate for the first scatter iteration after the sweeps)
+            t_prev = 0.0;
+            DenseIO io{edges_acc, gath_acc, pops_acc, iters_done, sweeps_done, gen, dense_rate};
+            alive = a.Sp == 1 ? dense_mode<1>(a, sm, c, phase, it, dense_hpk, io) : dense_mode<4>(a, sm, c, phase, it, dense_hpk, io);
+            edges_acc = io.edges_acc; gath_acc = io.gath; pops_acc = io.pops_acc;
+            iters_done = io.iters_done; sweeps_done = io.sweeps_done; gen = io.gen;
             ++it;
-            ++iters_done;
         }
     }
     // carried_acc is per thread: fold it over the CTA with one atomic per warp
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) carried_acc += __shfl_xor_sync(kFull, carried_acc, off);
+    for (int off = 16; off > 0; off >>= 1) {
+        carried_acc += __shfl_xor_sync(kFull, carried_acc, off);
+        gath_acc += __shfl_xor_sync(kFull, gath_acc, off);
+    }
     if (lane_id() == 0 && carried_acc) atomicAdd(&c->carried, carried_acc);
+    if (lane_id() == 0 && gath_acc) atomicAdd(&c->edges, gath_acc);
     if (threadIdx.x == 0) {
         if (edges_acc) atomicAdd(&c->edges, edges_acc);
         if (blockIdx.x == 0) {
+            c->sweeps = sweeps_done;
             c->iters = iters_done;
             c->pops = pops_acc;
             c->hubs = hubs_acc;

@@ -380,19 +380,20 @@ __device__ void async_worker(const AsyncArgs &a, const AsyncQueue &q, AsyncWarpS
 
 __global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_async(const AsyncArgs a) {
     __shared__ AsyncWarpSmem wsm[kWarps];
-    __shared__ int abort_flag;
+    struct BarSmem { int abort_flag; uint32_t bar_units; };
+    __shared__ BarSmem bsm;
     __shared__ unsigned long long cta_fence;
     AsyncWarpSmem &ws = wsm[warp_id()];
     if (lane_id() == 0) ws.stage_cnt = 0;
-    if (threadIdx.x == 0) abort_flag = 0;
+    if (threadIdx.x == 0) bsm.abort_flag = 0;
     __syncthreads();
     PushCtrl *c = a.base.ctrl;
-    unsigned gen = 0;
+    GridBar gen;
     unsigned long long edges_acc = 0, pops_acc = 0, hubs_acc = 0, gens_acc = 0;
     const int nphases = a.base.init_mode ? 1 : 2;
     for (int phase = 0; phase < nphases; ++phase) {
         async_seed(a, a.q[phase], ws, phase);
-        if (!grid_barrier(c, gen, abort_flag)) break;   // every seed is in the ring and theta0 is final
+        if (!grid_barrier(c, gen, bsm)) break;   // every seed is in the ring and theta0 is final
         if (threadIdx.x == 0) cta_fence = 0;
         __syncthreads();
         if (blockIdx.x == 0 && warp_id() == 0) {

@@ -13,6 +13,10 @@
 //               A ring that fills up moves to a fresh, larger slot range (amortised doubling).
 //   * out-degree: plain int32 per vertex (the reference only ever uses row_ptr differences,
 //               gpu/ExpandRev.cuh:71, gpu/StreamUpdate.cuh:13).
+//   * out-adjacency (directed graphs, when dense iterations are enabled -- pull.cuh): a second set of per-vertex
+//               FIFO rings keyed by the source end, in the same pool, maintained by the same plan / relocate /
+//               insert steps from the batch's source-sorted entries.  Undirected graphs need none: their entry set
+//               is symmetric, the in-lists are the out-lists.
 //
 // Determinism: the batch's directed entries are radix-sorted by vertex (stable => stream order
 // within a vertex), run-length encoded, and every per-vertex quantity is then written by exactly
@@ -128,14 +132,17 @@ __global__ void __launch_bounds__(kThreads)
 __global__ void __launch_bounds__(kThreads)
     win_init_entries(const int2 *__restrict__ log, int64_t W, int directed, int32_t V, uint32_t *__restrict__ key,
                      uint32_t *__restrict__ val, uint32_t *__restrict__ indeg, int32_t *__restrict__ outdeg,
-                     int *errflags) {
+                     int *errflags, int transpose) {
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < W; i += (int64_t)gridDim.x * kThreads) {
         int2 e = log[i];
         if ((uint32_t)e.x >= (uint32_t)V || (uint32_t)e.y >= (uint32_t)V) {
             atomicOr(errflags, kErrBadId);
             e.x = 0; e.y = 0;
         }
-        if (directed) {
+        if (directed && transpose) {  // out-lists of a directed graph (pull.cuh): keyed by the source end
+            key[i] = (uint32_t)e.x; val[i] = (uint32_t)e.y;
+            atomicAdd(&indeg[e.x], 1u);
+        } else if (directed) {
             key[i] = (uint32_t)e.y; val[i] = (uint32_t)e.x;
             atomicAdd(&indeg[e.y], 1u);
             atomicAdd(&outdeg[e.x], 1);
@@ -156,18 +163,19 @@ __global__ void __launch_bounds__(kThreads)
 
 __global__ void __launch_bounds__(kThreads)
     win_init_meta(const uint32_t *__restrict__ indeg, const uint32_t *__restrict__ caps,
-                  const uint32_t *__restrict__ capbase, uint4 *__restrict__ vmeta, int32_t V) {
+                  const uint32_t *__restrict__ capbase, uint4 *__restrict__ vmeta, int32_t V, uint32_t base_off) {
     for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < V; v += (int64_t)gridDim.x * kThreads)
-        vmeta[v] = make_uint4(capbase[v], 0u, indeg[v], caps[v]);
+        vmeta[v] = make_uint4(capbase[v] + base_off, 0u, indeg[v], caps[v]);
 }
 
 // sorted (dst, src) entries -> ring slots; rank within the row = i - rowptr[dst]
 __global__ void __launch_bounds__(kThreads)
     win_init_fill(const uint32_t *__restrict__ key, const uint32_t *__restrict__ val, int64_t n,
-                  const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ capbase, int32_t *__restrict__ pool) {
+                  const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ capbase, int32_t *__restrict__ pool,
+                  uint32_t base_off) {
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
         const uint32_t d = key[i];
-        pool[capbase[d] + ((uint32_t)i - rowptr[d])] = (int32_t)val[i];
+        pool[base_off + capbase[d] + ((uint32_t)i - rowptr[d])] = (int32_t)val[i];
     }
 }
 

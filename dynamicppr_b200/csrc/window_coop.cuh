@@ -33,6 +33,11 @@ struct CoopArgs {
     int32_t *seg_d0;
     const uint32_t *perm;    // caller id -> internal id (null = identity)
     unsigned *bar;           // grid barrier counter, zero at launch
+    // out-lists of a directed graph (null vmeta = not maintained)
+    WindowView wo;
+    uint32_t *ins_posB;
+    RelocJob *jobsB;
+    uint32_t *njobsB;
 };
 
 struct CoopSmem {
@@ -151,30 +156,42 @@ __global__ void __launch_bounds__(kThreads) win_update_coop(const CoopArgs a) {
     const uint32_t B = (uint32_t)a.B;
     const uint32_t n = a.directed ? 2u * B : 4u * B;
     const uint32_t gtid = blockIdx.x * kThreads + threadIdx.x, gsize = gridDim.x * kThreads;
+    const bool outlists = a.directed && a.wo.vmeta != nullptr;
+    if (gtid == 0 && outlists) *a.njobsB = 0;
     for (uint32_t i = gtid; i < B; i += gsize)
         batch_entries_one(i, a.log, a.W, a.log_start, a.arriving, a.B, a.directed, a.w.V, a.akey[0], a.aval[0], a.bkey[0],
                           a.bval[0], a.w.errflags, a.perm);
     if (!coop_barrier(a.bar, gen, sm.abort_flag, a.w.errflags)) return;
     const int ra = coop_sort_and_rle(a, a.akey, a.aval, n, a.segA, sm, gen, alive);
     if (!alive) return;
+    int rb = ra;
     if (a.directed) {
-        coop_sort_and_rle(a, a.bkey, a.bval, n, a.segB, sm, gen, alive);
+        rb = coop_sort_and_rle(a, a.bkey, a.bval, n, a.segB, sm, gen, alive);
         if (!alive) return;
     }
     // expire / reserve / grow per touched vertex; new out-degrees (different arrays: no barrier in between)
     const uint32_t nsegA = *a.segA.count, nsegB = *a.segB.count;
     for (uint32_t s = gtid; s < nsegA; s += gsize) plan_one(s, a.segA, a.w, a.ins_pos, a.jobs, a.njobs);
     for (uint32_t s = gtid; s < nsegB; s += gsize) out_degree_one(s, a.segB, a.w.outdeg, a.seg_d0);
+    if (outlists)
+        for (uint32_t s = gtid; s < nsegB; s += gsize) plan_one(s, a.segB, a.wo, a.ins_posB, a.jobsB, a.njobsB);
     if (!coop_barrier(a.bar, gen, sm.abort_flag, a.w.errflags)) return;
-    const uint32_t nj = *a.njobs;
     const uint32_t gw = gtid >> 5, nw = gsize >> 5;
-    for (uint32_t j = gw; j < nj; j += nw) {  // one warp per relocated ring
-        const RelocJob jb = a.jobs[j];
-        for (uint32_t k = threadIdx.x & 31; k < jb.len; k += 32)
-            a.w.pool[jb.new_base + k] = a.w.pool[jb.old_base + ((jb.old_head + k) & (jb.old_cap - 1u))];
+    for (int side = 0; side < (outlists ? 2 : 1); ++side) {
+        const RelocJob *jobs = side ? a.jobsB : a.jobs;
+        const uint32_t nj = side ? *a.njobsB : *a.njobs;
+        for (uint32_t j = gw; j < nj; j += nw) {  // one warp per relocated ring
+            const RelocJob jb = jobs[j];
+            for (uint32_t k = threadIdx.x & 31; k < jb.len; k += 32)
+                a.w.pool[jb.new_base + k] = a.w.pool[jb.old_base + ((jb.old_head + k) & (jb.old_cap - 1u))];
+        }
     }
     const uint32_t *ka = a.akey[ra], *va = a.aval[ra];
     for (uint32_t i = gtid; i < n; i += gsize) insert_one(i, ka, va, a.segA, a.ins_pos, a.w);
+    if (outlists) {
+        const uint32_t *kb = a.bkey[rb], *vb = a.bval[rb];
+        for (uint32_t i = gtid; i < n; i += gsize) insert_one(i, kb, vb, a.segB, a.ins_posB, a.wo);
+    }
 }
 
 }  // namespace dppr

@@ -134,6 +134,11 @@ struct FusedArgs {
     uint32_t *njobs;
     int32_t *seg_d0;
     const uint32_t *perm;    // caller id -> internal id (null = identity)
+    // out-lists of a directed graph (null vmeta = not maintained)
+    WindowView wo;
+    uint32_t *ins_posB;
+    RelocJob *jobsB;
+    uint32_t *njobsB;
 };
 
 __global__ void __launch_bounds__(kFusedThreads, 1) win_fused_small(const FusedArgs a) {
@@ -167,6 +172,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) win_fused_small(const FusedA
     }
     const uint32_t nsegB = *a.segB.count;
     for (uint32_t s = threadIdx.x; s < nsegB; s += kFusedThreads) out_degree_one(s, a.segB, a.w.outdeg, a.seg_d0);
+    if (a.directed && a.wo.vmeta != nullptr) {  // out-lists: same steps on the source-sorted entries
+        if (threadIdx.x == 0) *a.njobsB = 0;
+        __syncthreads();
+        for (uint32_t s = threadIdx.x; s < nsegB; s += kFusedThreads) plan_one(s, a.segB, a.wo, a.ins_posB, a.jobsB, a.njobsB);
+        __syncthreads();
+        const uint32_t njb = *a.njobsB;
+        for (uint32_t j = threadIdx.x >> 5; j < njb; j += kFusedWarps) {
+            const RelocJob jb = a.jobsB[j];
+            for (uint32_t k = threadIdx.x & 31; k < jb.len; k += 32)
+                a.w.pool[jb.new_base + k] = a.w.pool[jb.old_base + ((jb.old_head + k) & (jb.old_cap - 1u))];
+        }
+        for (uint32_t i = threadIdx.x; i < n; i += kFusedThreads) insert_one(i, a.bkey[rb], a.bval[rb], a.segB, a.ins_posB, a.wo);
+    }
 }
 
 }  // namespace dppr

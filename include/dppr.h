@@ -89,7 +89,7 @@ typedef struct dppr_batch_stats {
     float ms_repair;            /* residual repair   } reference "ppr_time" = ms_repair + ms_push */
     float ms_push;              /* both push phases  } (gpu/PPRGPU.cuh:128-163)                    */
     int32_t error_flags;        /* device-side DPPR_DEVERR_* bits, 0 when healthy */
-    int32_t reserved0;
+    int32_t dense_sweeps;       /* iterations that ran as gather sweeps over the out-lists (counted in `iterations` too) */
 } dppr_batch_stats;
 
 enum {
@@ -163,6 +163,10 @@ int dppr_copy_estimates_device(dppr_engine *e, int32_t source_index, void *devic
  * sorts on the device; not part of the hot path. */
 int dppr_export_window_csr(dppr_engine *e, int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_deg);
 int64_t dppr_window_csr_entries(const dppr_engine *e); /* E_w = D*W */
+/* Test hook: the transposed window graph the dense (gather) iterations read -- out_row_ptr[V+1], out_col_ind[E_w],
+ * rows ascending, duplicates kept.  Returns 1 and fills nothing if this engine keeps no separate out-lists
+ * (undirected graph: the in-lists serve; or dense iterations disabled). */
+int dppr_export_window_out_csr(dppr_engine *e, int32_t *out_row_ptr, int32_t *out_col_ind);
 
 /* Synthetic directed R-MAT stream (a,b,c,d = 0.57,0.19,0.19,0.05; ids folded and relabelled into [0,V)) written as
  * M int32 pairs into caller-owned DEVICE memory.  Counter-based: edge i depends on (seed, i) only.  Stands in for

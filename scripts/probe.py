@@ -46,7 +46,7 @@ T = f('traversed_edges').sum(); F = f('frontier_pops').sum()
 print(f"push algorithmic GB/s: {(24*T+56*F)/ (f('ms_push').sum()*1e-3)/1e9:.1f}; edges/us {T/(f('ms_push').sum()*1e3):.1f}; us/iter {f('ms_push').sum()*1e3/max(f('iterations').sum(),1):.2f}")
 for r in rows[:a.show]:
     print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.as_dict().items()})
-if os.environ.get("DPPR_ITERLOG") and a.mode in (0, 2) and a.variant == 0:
+if os.environ.get("DPPR_ITERLOG") and a.mode == 2 and a.variant == 0:
     dd = eng.ctalog(2).reshape(-1)
     d = dd.astype(np.float64)
     t0 = int(dd[8])

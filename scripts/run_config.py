@@ -44,7 +44,7 @@ out = dict(config=a.config, shape=shape, V=V, M=M, W=wl.W, B=wl.B, batches=nb, s
            ppr_ms_mean=float(ppr.mean()), ppr_ms_p50=float(np.median(ppr)), ppr_ms_p95=float(np.percentile(ppr, 95)),
            e2e_ms_mean=float(e2e.mean()), window_ms_mean=float(f("ms_window").mean()), repair_ms_mean=float(f("ms_repair").mean()),
            edge_updates_per_s=float(wl.B * nb / ppr.sum() * 1e3), source_edge_updates_per_s=float(len(srcs) * wl.B * nb / e2e.sum() * 1e3),
-           iterations=float(f("iterations").mean()), pops=float(F.mean()), traversed=float(T.mean()),
+           iterations=float(f("iterations").mean()), dense_sweeps=float(f("dense_sweeps").mean()), pops=float(F.mean()), traversed=float(T.mean()),
            traversed_per_update=float(T.sum() / (wl.B * nb * len(srcs))),
            push_edges_per_ns=float(T.sum() / (f("ms_push").sum() * 1e6)),
            push_alg_GBps=float((24 * T + 56 * F).sum() / (f("ms_push").sum() * 1e-3) / 1e9),

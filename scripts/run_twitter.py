@@ -23,7 +23,7 @@ t0 = time.time()
 dev = torch.empty((need, 2), dtype=torch.int32, device="cuda")
 binding.generate_rmat_device(V, need, 20261021, dev.data_ptr())
 torch.cuda.synchronize(); tgen = time.time() - t0
-outdeg_all = torch.bincount(dev[:, 0].long(), minlength=V)
+outdeg_all = torch.bincount(dev[: wl.W, 0].long(), minlength=V)  # (initial window only: the choice must not depend on --batches)
 # source buckets of the reference's workload tool (workload/Workload.cpp:47-55): ranks by out-degree
 order = torch.argsort(outdeg_all, descending=True, stable=True)
 pick = lambda lo: order[lo: lo + 8].cpu().numpy().astype(np.int32)
@@ -54,7 +54,7 @@ for kind in a.kinds.split(","):
                window_ms_mean=float(f("ms_window").mean()), repair_ms_mean=float(f("ms_repair").mean()), push_ms_mean=float(f("ms_push").mean()),
                step_ms_p50=float(np.median(step)), step_ms_p95=float(np.percentile(step, 95)),
                edge_updates_per_s_step=float(wl.B * nb_k / step.sum() * 1e3), edge_updates_per_s_ppr_only=float(wl.B * nb_k / ppr.sum() * 1e3),
-               iterations=float(f("iterations").mean()), pops=float(F.mean()), traversed=float(T.mean()),
+               iterations=float(f("iterations").mean()), dense_sweeps=float(f("dense_sweeps").mean()), push_ms_each=[round(float(x), 2) for x in f("ms_push")], pops=float(F.mean()), traversed=float(T.mean()),
                traversed_per_update=float(T.sum() / (wl.B * nb_k * len(srcs))),
                push_edges_per_ns=float(T.sum() / max(f("ms_push").sum() * 1e6, 1e-9)),
                push_alg_GBps=float((24 * T + 56 * F).sum() / max(f("ms_push").sum() * 1e-3, 1e-12) / 1e9),
@@ -76,5 +76,11 @@ for kind in a.kinds.split(","):
         out["invariant_defect"] = float(invariant_defect(V, rp, ci, od, p, r, int(srcs[0])))
         out["check_s"] = round(time.time() - t0, 1)
         del rp, ci, od, rows_ids, p, r
+    if os.environ.get("DPPR_ITERLOG"):
+        lg = eng.iterlog()
+        if len(lg):
+            tt = lg[:, 2].astype(np.int64); dt = np.diff(tt) / 1e3
+            print(f"[{kind}] last batch per-iteration (frontier, hub_chunks|D=dense, us): " + " ".join(
+                f"({int(x)},{'D' if int(y) == 0xffffffff else int(y)},{z:.0f})" for (x, y, _), z in zip(lg[:-1], dt)), file=sys.stderr)
     eng.close()
     print(json.dumps(out), flush=True)
