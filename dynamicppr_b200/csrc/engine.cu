@@ -96,7 +96,14 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
         dense_ = dense_div_ > 0.0 && cfg.variant == DPPR_OPTIMIZED && mode_ == DPPR_ENGINE_LEVELSYNC &&
                  (double)cfg.window_edges * (cfg.directed ? 1 : 2) * cfg.n_sources >= min_edges;
         outlists_ = dense_ && D_ == 1;
-        Sp_ = S_ == 1 ? 1 : (S_ + 3) / 4 * 4;
+        // several sources: rows of x hold 4-source chunks, G = 2^gshift adjacent lanes take G chunks of a vertex (pull.cuh)
+        pull_gshift_ = 0;
+        if (S_ > 1) {
+            const int chunks = (S_ + 3) / 4;
+            const int gmax = std::min(std::max(env_int("DPPR_PULL_GROUP", 8), 1), 8);
+            while ((2 << pull_gshift_) <= std::min(chunks, gmax)) ++pull_gshift_;
+        }
+        Sp_ = S_ == 1 ? 1 : (S_ + (4 << pull_gshift_) - 1) / (4 << pull_gshift_) * (4 << pull_gshift_);
         pull_warp_min_ = std::max(1, env_int("DPPR_PULL_WARP_MIN", 32));
         pull_cta_min_ = std::max(pull_warp_min_, env_int("DPPR_PULL_CTA_MIN", 1024));
         pull_big_min_ = std::max(pull_cta_min_, env_int("DPPR_PULL_BIG_MIN", 65536));
@@ -177,10 +184,10 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
             x_[i].alloc((size_t)V_ * Sp_);
             DPPR_CUDA(cudaMemsetAsync(x_[i].ptr, 0, x_[i].bytes(), st_));  // the padding columns stay zero for good
         }
-        tile_list_.alloc((size_t)div_up(V_, kThreads) * (Sp_ == 1 ? 1 : Sp_ / 4));
+        tile_list_.alloc((size_t)div_up(V_, kThreads >> pull_gshift_) * (Sp_ == 1 ? 1 : (Sp_ / 4) >> pull_gshift_));
         bigcap_ = (uint32_t)std::min<int64_t>((Ew_ / pull_big_min_ + 64) * (Sp_ == 1 ? 1 : Sp_ / 4), 1 << 24);
         big_.alloc(bigcap_);
-        bigacc_.alloc((size_t)bigcap_ * 4);
+        bigacc_.alloc((size_t)bigcap_ * 4 << pull_gshift_);
         DPPR_CUDA(cudaMemsetAsync(bigacc_.ptr, 0, bigacc_.bytes(), st_));
     }
     seg_d0_.alloc((size_t)Nb_);
@@ -417,7 +424,7 @@ void Engine::launch_push(bool init_mode) {
     a.V = V_;
     a.vmeta_out = outlists_ ? vmeta_out_.ptr : vmeta_.ptr;
     a.x[0] = x_[0].ptr; a.x[1] = x_[1].ptr;
-    a.Sp = Sp_;
+    a.Sp = Sp_; a.pull_gshift = pull_gshift_;
     // cost model: a sweep reads every out-list entry and every vertex row once, whatever the frontier; a scatter
     // iteration pays one random atomic per traversed in-edge.  Measured ratio ~ DPPR_DENSE_DIV (3): Twitter-shaped
     // 3.3 ms per sweep vs 17 edges/ns scattered; Orkut/4 97 us vs 40 edges/ns.
@@ -427,7 +434,7 @@ void Engine::launch_push(bool init_mode) {
     a.pull_warp_min = pull_warp_min_; a.pull_cta_min = pull_cta_min_; a.pull_big_min = pull_big_min_;
     a.big = big_.ptr; a.bigcap = bigcap_; a.bigacc = bigacc_.ptr; a.tile_list = tile_list_.ptr;
     {
-        const uint64_t ntiles = (uint64_t)div_up(V_, kThreads) * (Sp_ == 1 ? 1 : Sp_ / 4);
+        const uint64_t ntiles = (uint64_t)div_up(V_, kThreads >> pull_gshift_) * (Sp_ == 1 ? 1 : (Sp_ / 4) >> pull_gshift_);
         auto gcd = [](uint64_t x, uint64_t y) { while (y) { const uint64_t t = x % y; x = y; y = t; } return x; };
         uint64_t k = std::max<uint64_t>(1, (uint64_t)(0.6180339887 * (double)ntiles)) | 1ull;
         while (gcd(k, ntiles) != 1) k += 2;

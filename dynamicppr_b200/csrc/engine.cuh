@@ -100,7 +100,7 @@ private:
     DevBuf<HubItem> big_;
     DevBuf<uint32_t> tile_list_;
     uint32_t bigcap_ = 0;
-    int Sp_ = 1;
+    int Sp_ = 1, pull_gshift_ = 0;
     bool dense_ = false, outlists_ = false;
     double dense_div_ = 0.0;
     int pull_warp_min_ = 0, pull_cta_min_ = 0, pull_big_min_ = 0;

@@ -146,6 +146,28 @@ __device__ __forceinline__ void pull_count_flush(PushSmem &sm, uint32_t mine, un
     }
 }
 
+// Work unit of the dense passes: (vertex w, chunk of SB sources).  With several sources, G = 2^pull_gshift ADJACENT
+// lanes take the G chunks of one chunk group of the same vertex: their 32-byte gathers of a neighbour's row then form one
+// contiguous G*32-byte request (HBM bursts are 64 bytes: a lone 32-byte sector wastes half of one), and the slot loads
+// are a broadcast.  A tile is kThreads / G consecutive vertices x one chunk group.
+struct PullUnit {
+    uint32_t w, s0, g;
+};
+template <int SB>
+__device__ __forceinline__ uint32_t pull_gshift(const PushArgs &a) { return SB == 1 ? 0u : (uint32_t)a.pull_gshift; }
+template <int SB>
+__device__ __forceinline__ uint32_t pull_tiles_per_group(const PushArgs &a) {
+    const uint32_t vpt = (uint32_t)kThreads >> pull_gshift<SB>(a);
+    return ((uint32_t)a.V + vpt - 1) / vpt;
+}
+template <int SB>
+__device__ __forceinline__ PullUnit pull_unit(const PushArgs &a, uint32_t tile, uint32_t tpc, uint32_t &cg) {
+    const uint32_t gs = pull_gshift<SB>(a), G = 1u << gs;
+    cg = tile / tpc;
+    const uint32_t g = threadIdx.x & (G - 1u);
+    return PullUnit{(tile - cg * tpc) * ((uint32_t)kThreads >> gs) + (threadIdx.x >> gs), ((cg << gs) + g) * SB, g};
+}
+
 // entering dense mode: x[0][w] = r[w] where legal, 0 elsewhere; x[1][w] = 0.  Also lists the ACTIVE tiles: a vertex
 // without out-edges receives no adds, so a tile whose 256 vertices have neither out-edges nor a legal residual now
 // stays all-zero in both x buffers for the whole episode and is never visited again.  With the degree-sorted internal
@@ -154,12 +176,14 @@ __device__ __forceinline__ void pull_count_flush(PushSmem &sm, uint32_t mine, un
 // sit at a regular stride, which would otherwise hand all of them to the same few CTAs in the sweeps.
 template <int SB>
 __device__ void pull_build(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, unsigned int *cnt_out) {
-    const uint32_t V = (uint32_t)a.V, nSC = (uint32_t)a.Sp / SB;
-    const uint32_t tpc = (V + kThreads - 1) / kThreads, ntiles = tpc * nSC;
+    const uint32_t V = (uint32_t)a.V, nCG = ((uint32_t)a.Sp / SB) >> pull_gshift<SB>(a);
+    const uint32_t tpc = pull_tiles_per_group<SB>(a), ntiles = tpc * nCG;
     uint32_t legal = 0;
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint32_t tile = (uint32_t)(((unsigned long long)t * a.pull_tile_mul) % ntiles);
-        const uint32_t ch = tile / tpc, w = (tile - ch * tpc) * kThreads + threadIdx.x, s0 = ch * SB;
+        uint32_t cg;
+        const PullUnit un = pull_unit<SB>(a, tile, tpc, cg);
+        const uint32_t w = un.w, s0 = un.s0;
         bool active = false;
         if (w < V) {
             double out[SB];
@@ -201,17 +225,19 @@ __device__ void pull_build(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
 template <int SB>
 __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, const double *xcur, double *xnext,
                            unsigned int *cnt_out, unsigned long long *edges_out, unsigned long long &gath) {
-    const uint32_t V = (uint32_t)a.V, Sp = (uint32_t)a.Sp, nSC = Sp / SB;
-    const uint32_t tpc = (V + kThreads - 1) / kThreads, ntiles = __ldcg(&c->ntiles_active);
-    (void)nSC;
+    const uint32_t V = (uint32_t)a.V, Sp = (uint32_t)a.Sp;
+    const uint32_t gs = pull_gshift<SB>(a), G = 1u << gs;
+    const uint32_t tpc = pull_tiles_per_group<SB>(a), ntiles = __ldcg(&c->ntiles_active);
     uint32_t legal = 0, nz = 0;
     unsigned long long next_edges = 0;
-    double *list_res = reinterpret_cast<double *>(sm.stage);   // [kThreads][SB] sums of the listed vertices (the stage is idle during a sweep)
-    double *cta_part = sm.t_ru;                                // [kWarps][SB]
-    static_assert(kStage >= kThreads * SB && kTileMax >= kWarps * SB && kTileMax >= kThreads, "pull.cuh borrows the tile arrays");
+    double *list_res = reinterpret_cast<double *>(sm.stage);   // [kThreads / G][G][SB] sums of the listed vertices (the stage is idle during a sweep)
+    double *cta_part = sm.t_ru;                                // [kWarps][G][SB]
+    static_assert(kStage >= kThreads * SB && kTileMax >= kWarps * 8 * SB && kTileMax >= kThreads, "pull.cuh borrows the tile arrays");
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint32_t tile = __ldcg(&a.tile_list[t]);  // active tiles only, in the scrambled order pull_build listed them
-        const uint32_t ch = tile / tpc, w = (tile - ch * tpc) * kThreads + threadIdx.x, s0 = ch * SB;
+        uint32_t cg;
+        const PullUnit un = pull_unit<SB>(a, tile, tpc, cg);
+        const uint32_t w = un.w, s0 = un.s0, g = un.g;
         const bool have = w < V;
         double xc[SB], acc[SB];
 #pragma unroll
@@ -226,16 +252,17 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
             }
         }
         const int tier = len < (uint32_t)a.pull_warp_min ? 0 : len < (uint32_t)a.pull_cta_min ? 1 : len < (uint32_t)a.pull_big_min ? 2 : 3;
-        // ---- warp and CTA tiers ----
+        // ---- warp and CTA tiers (one list entry per vertex: the G lanes of a group share it) ----
         const bool listed = tier == 1 || tier == 2;
         if (__syncthreads_or(listed)) {
             uint32_t myslot = 0;
             if (threadIdx.x == 0) sm.pl_n = 0;
             __syncthreads();
-            if (listed) {
+            if (listed && g == 0) {
                 myslot = atomicAdd(&sm.pl_n, 1u);
                 sm.t_base[myslot] = base; sm.t_head[myslot] = head; sm.t_mask[myslot] = mask; sm.t_off[myslot] = len;
             }
+            myslot = __shfl_sync(kFull, myslot, lane_id() & ~(G - 1u));
             __syncthreads();
             const uint32_t ne = sm.pl_n;
             for (uint32_t e = warp_id(); e < ne; e += kWarps) {
@@ -246,13 +273,12 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
 #pragma unroll
                 for (int j = 0; j < SB; ++j) part[j] = 0.0;
 #pragma unroll 4
-                for (uint32_t k = lane_id(); k < el; k += 32)
+                for (uint32_t k = lane_id() >> gs; k < el; k += 32u >> gs)
                     pull_gather<SB>(xcur, (uint32_t)pl_ldcs(&a.pool[eb + ((eh + k) & em)]), Sp, s0, part, nz);
 #pragma unroll
                 for (int j = 0; j < SB; ++j) {
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) part[j] += __shfl_xor_sync(kFull, part[j], off);
-                    if (lane_id() == 0) list_res[e * SB + j] = part[j];
+                    for (uint32_t off = 16; off >= G; off >>= 1) part[j] += __shfl_xor_sync(kFull, part[j], off);
+                    if (lane_id() < G) list_res[((e << gs) + g) * SB + j] = part[j];
                 }
             }
             for (uint32_t e = 0; e < ne; ++e) {
@@ -263,27 +289,27 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
 #pragma unroll
                 for (int j = 0; j < SB; ++j) part[j] = 0.0;
 #pragma unroll 4
-                for (uint32_t k = threadIdx.x; k < el; k += kThreads)
+                for (uint32_t k = threadIdx.x >> gs; k < el; k += (uint32_t)kThreads >> gs)
                     pull_gather<SB>(xcur, (uint32_t)pl_ldcs(&a.pool[eb + ((eh + k) & em)]), Sp, s0, part, nz);
 #pragma unroll
                 for (int j = 0; j < SB; ++j) {
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) part[j] += __shfl_xor_sync(kFull, part[j], off);
-                    if (lane_id() == 0) cta_part[warp_id() * SB + j] = part[j];
+                    for (uint32_t off = 16; off >= G; off >>= 1) part[j] += __shfl_xor_sync(kFull, part[j], off);
+                    if (lane_id() < G) cta_part[((warp_id() << gs) + g) * SB + j] = part[j];
                 }
                 __syncthreads();
-                if (threadIdx.x < SB) {
+                if (threadIdx.x < G * SB) {  // thread = (sub-chunk, source within it)
+                    const uint32_t gg = threadIdx.x / SB, jj = threadIdx.x % SB;
                     double tsum = 0.0;
 #pragma unroll
-                    for (int ww = 0; ww < kWarps; ++ww) tsum += cta_part[ww * SB + threadIdx.x];
-                    list_res[e * SB + threadIdx.x] = tsum;
+                    for (int ww = 0; ww < kWarps; ++ww) tsum += cta_part[((ww << gs) + gg) * SB + jj];
+                    list_res[((e << gs) + gg) * SB + jj] = tsum;
                 }
                 __syncthreads();
             }
             __syncthreads();
             if (listed) {
 #pragma unroll
-                for (int j = 0; j < SB; ++j) acc[j] = list_res[myslot * SB + j];
+                for (int j = 0; j < SB; ++j) acc[j] = list_res[((myslot << gs) + g) * SB + j];
             }
             __syncthreads();  // the list is reused by the next tile
         }
@@ -295,14 +321,16 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
         }
         // ---- grid tier: finished by pull_big_finish after the next grid barrier ----
         if (tier == 3) {
-            const uint32_t nch = (len + kPullBigChunk - 1) / kPullBigChunk;
-            const unsigned long long old = atomicAdd(&c->bigpk, (1ull << 32) | nch);
-            const uint32_t hp = (uint32_t)(old >> 32);
-            if (hp < a.bigcap) {
-                __stcg(&a.big[hp].item, ((unsigned long long)ch << 32) | w);
-                __stcg(&a.big[hp].chunk0, (uint32_t)old);
-            } else {
-                atomicOr(&c->errflags, kErrHubQ);
+            if (g == 0) {  // one entry per (vertex, chunk group)
+                const uint32_t nch = (len + kPullBigChunk - 1) / kPullBigChunk;
+                const unsigned long long old = atomicAdd(&c->bigpk, (1ull << 32) | nch);
+                const uint32_t hp = (uint32_t)(old >> 32);
+                if (hp < a.bigcap) {
+                    __stcg(&a.big[hp].item, ((unsigned long long)cg << 32) | w);
+                    __stcg(&a.big[hp].chunk0, (uint32_t)old);
+                } else {
+                    atomicOr(&c->errflags, kErrHubQ);
+                }
             }
         } else if (have) {
             legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, next_edges);
@@ -318,6 +346,7 @@ __device__ void pull_big_expand(const PushArgs &a, PushSmem &sm, const double *x
                                 unsigned long long &gath) {
     const uint32_t nh = min((uint32_t)(bp >> 32), a.bigcap), nchunks = (uint32_t)bp;
     const uint32_t Sp = (uint32_t)a.Sp;
+    const uint32_t gs = pull_gshift<SB>(a), G = 1u << gs, g = threadIdx.x & (G - 1u);
     double *cta_part = sm.t_ru;
     uint32_t nz = 0;
     for (uint32_t cidx = blockIdx.x; cidx < nchunks; cidx += gridDim.x) {
@@ -328,7 +357,7 @@ __device__ void pull_big_expand(const PushArgs &a, PushSmem &sm, const double *x
         }
         const unsigned long long item = __ldcg(&a.big[lo].item);
         const uint32_t c0 = __ldcg(&a.big[lo].chunk0);
-        const uint32_t w = (uint32_t)item, s0 = (uint32_t)(item >> 32) * SB;
+        const uint32_t w = (uint32_t)item, s0 = ((((uint32_t)(item >> 32)) << gs) + g) * SB;
         const uint4 m = __ldg(&a.vmeta_out[w]);
         const uint32_t e0 = (cidx - c0) * (uint32_t)kPullBigChunk;
         const uint32_t e1 = min(m.z, e0 + (uint32_t)kPullBigChunk);
@@ -336,20 +365,20 @@ __device__ void pull_big_expand(const PushArgs &a, PushSmem &sm, const double *x
 #pragma unroll
         for (int j = 0; j < SB; ++j) part[j] = 0.0;
 #pragma unroll 4
-        for (uint32_t k = e0 + threadIdx.x; k < e1; k += kThreads)
+        for (uint32_t k = e0 + (threadIdx.x >> gs); k < e1; k += (uint32_t)kThreads >> gs)
             pull_gather<SB>(xcur, (uint32_t)pl_ldcs(&a.pool[m.x + ((m.y + k) & (m.w - 1u))]), Sp, s0, part, nz);
 #pragma unroll
         for (int j = 0; j < SB; ++j) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) part[j] += __shfl_xor_sync(kFull, part[j], off);
-            if (lane_id() == 0) cta_part[warp_id() * SB + j] = part[j];
+            for (uint32_t off = 16; off >= G; off >>= 1) part[j] += __shfl_xor_sync(kFull, part[j], off);
+            if (lane_id() < G) cta_part[((warp_id() << gs) + g) * SB + j] = part[j];
         }
         __syncthreads();
-        if (threadIdx.x < SB) {
+        if (threadIdx.x < G * SB) {
+            const uint32_t gg = threadIdx.x / SB, jj = threadIdx.x % SB;
             double t = 0.0;
 #pragma unroll
-            for (int ww = 0; ww < kWarps; ++ww) t += cta_part[ww * SB + threadIdx.x];
-            atomicAdd(&a.bigacc[(size_t)lo * 4 + threadIdx.x], t);
+            for (int ww = 0; ww < kWarps; ++ww) t += cta_part[((ww << gs) + gg) * SB + jj];
+            atomicAdd(&a.bigacc[(((size_t)lo << gs) + gg) * 4 + jj], t);
         }
         __syncthreads();
     }
@@ -360,17 +389,19 @@ template <int SB>
 __device__ void pull_big_finish(const PushArgs &a, PushSmem &sm, int phase, const double *xcur, double *xnext,
                                 unsigned long long bp, unsigned int *cnt_out, unsigned long long *edges_out) {
     const uint32_t nh = min((uint32_t)(bp >> 32), a.bigcap);
+    const uint32_t gs = pull_gshift<SB>(a), G = 1u << gs;
     uint32_t legal = 0;
     unsigned long long next_edges = 0;
-    for (uint32_t h = blockIdx.x * kThreads + threadIdx.x; h < nh; h += gridDim.x * kThreads) {
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < (nh << gs); i += gridDim.x * kThreads) {
+        const uint32_t h = i >> gs, g = i & (G - 1u);  // thread = (list entry, sub-chunk)
         const unsigned long long item = __ldcg(&a.big[h].item);
-        const uint32_t w = (uint32_t)item, s0 = (uint32_t)(item >> 32) * SB;
+        const uint32_t w = (uint32_t)item, s0 = ((((uint32_t)(item >> 32)) << gs) + g) * SB;
         double xc[SB], acc[SB];
         pull_load_x<SB>(xcur, w, (uint32_t)a.Sp, s0, xc);
 #pragma unroll
         for (int j = 0; j < SB; ++j) {
-            acc[j] = __ldcg(&a.bigacc[(size_t)h * 4 + j]);
-            __stcg(&a.bigacc[(size_t)h * 4 + j], 0.0);
+            acc[j] = __ldcg(&a.bigacc[(size_t)i * 4 + j]);
+            __stcg(&a.bigacc[(size_t)i * 4 + j], 0.0);
         }
         const uint32_t len = __ldg(&a.vmeta_out[w]).z;
         legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, next_edges);
@@ -383,10 +414,12 @@ template <int SB>
 __device__ void pull_compact(const PushArgs &a, PushSmem &sm, PushCtrl *c, const double *x, unsigned long long *qout,
                              unsigned int *cnt_out) {
     const uint32_t V = (uint32_t)a.V;
-    const uint32_t tpc = (V + kThreads - 1) / kThreads, ntiles = __ldcg(&c->ntiles_active);
+    const uint32_t tpc = pull_tiles_per_group<SB>(a), ntiles = __ldcg(&c->ntiles_active);
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint32_t tile = __ldcg(&a.tile_list[t]);
-        const uint32_t ch = tile / tpc, w = (tile - ch * tpc) * kThreads + threadIdx.x, s0 = ch * SB;
+        uint32_t cg;
+        const PullUnit un = pull_unit<SB>(a, tile, tpc, cg);
+        const uint32_t w = un.w, s0 = un.s0;
         double xc[SB];
 #pragma unroll
         for (int j = 0; j < SB; ++j) xc[j] = 0.0;

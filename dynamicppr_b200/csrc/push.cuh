@@ -125,7 +125,8 @@ struct PushArgs {
     int32_t V;
     const uint4 *vmeta_out;      // out-lists (the in-lists themselves when the graph is undirected)
     double *x[2];                // popped residuals of the running / next sweep, vertex-major [V][Sp]
-    int32_t Sp;                  // sources per vertex row of x: 1, or S rounded up to a multiple of 4
+    int32_t Sp;                  // sources per vertex row of x: 1, or S rounded up to a multiple of 4 << pull_gshift
+    int32_t pull_gshift;         // log2 of the lanes that share a vertex in a sweep (pull.cuh, PullUnit)
     unsigned long long dense_enter_edges;  // an iteration expected to traverse at least this many in-edges runs as a sweep
     unsigned long long dense_exit_edges;   // ... and below this the loop goes back to scatter iterations
     int32_t pull_warp_min, pull_cta_min, pull_big_min;  // out-degree tiers of a sweep

@@ -172,6 +172,40 @@ def test_multi_source_dense_matches_single_source_oracles(monkeypatch):
         assert sweeps > 0
 
 
+@pytest.mark.parametrize("group", ["1", "8"])
+def test_many_sources_lane_groups(group, monkeypatch):
+    """33 sources -> 9 chunks of 4: with DPPR_PULL_GROUP=8 eight adjacent lanes share a vertex (rows of 64, two chunk
+    groups, 31 padding columns); with 1 every lane has its own vertex.  Same answers either way."""
+    force_dense(monkeypatch, div="1e15", tiers=(4, 24, 120))
+    monkeypatch.setenv("DPPR_PULL_GROUP", group)
+    V, M, directed = 2_500, 30_000, True
+    edges = graphgen.rmat_directed(V, M, seed=11)
+    wl = stream.workload(M, 0.1, 0, 0.03, 3)
+    sources = [int(x) for x in graphgen.top_out_degree(V, edges, directed, 20)] + list(range(1, 14))
+    eps = 1e-8
+    oracles = []
+    for s in sources:
+        o = orc.Oracle(V, directed, edges, wl.W, wl.B, s, eps, 0)
+        o.initial_solve()
+        oracles.append(o)
+    sweeps = 0
+    with DynamicPPR(V, directed, wl.W, wl.B, sources, epsilon=eps) as eng:
+        eng.init_window_pairs(edges[: wl.W])
+        eng.solve_initial()
+        for k in range(wl.n_batches + 1):
+            if k > 0:
+                lo = wl.W + (k - 1) * wl.B
+                eng.slide_pairs(edges[lo: lo + wl.B])
+                for o in oracles:
+                    o.slide(wl.B)
+            st = eng.stats()
+            assert st.error_flags == 0
+            sweeps += st.dense_sweeps
+            for i, o in enumerate(oracles):
+                check_against(eng.estimates(i), eng.residuals(i), o.p, None, eps, f"group {group} source {sources[i]} batch {k}")
+    assert sweeps > 0
+
+
 def test_dense_off_keeps_no_out_lists(monkeypatch):
     monkeypatch.setenv("DPPR_DENSE_DIV", "0")
     V, M = 3_000, 30_000
