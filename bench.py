@@ -18,7 +18,7 @@ Printed JSON (one line, rank 0):
              push), max over ranks.  L2 is flushed between steps (outside the events).
   e2e        same metric through the C-ABI call a user makes (dppr_slide_pairs with HOST buffers:
              pinned staging + H2D inside the timed region, plus a D2H read of the step's record).
-  roofline   push kernel (push_persistent<0>): algorithmic bytes (24 B per traversed in-edge +
+  roofline   push kernel (push_persistent<0, false>): algorithmic bytes (24 B per traversed in-edge +
              56 B per frontier pop) / CUDA-event time of that kernel, vs the measured
              HBM copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline  the reference's own CPU implementation (oracle/_ref/ref_harness_omp: unmodified
@@ -309,7 +309,7 @@ def main():
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": f"push_persistent<{a.variant}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": f"push_persistent<{a.variant}, false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes / K, "launch_ms": push_s * 1e3 / K,
                     "note": "working set (p, r, window graph ~50 MB) is L2-resident on B200: the kernel is bound by dependent "
