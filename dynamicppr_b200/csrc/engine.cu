@@ -349,8 +349,11 @@ void Engine::build_initial_window() {
         rscratch.alloc(sort_scratch_elems(V_));
         perm_.alloc((size_t)V_); inv_.alloc((size_t)V_);
         DPPR_CUDA(cudaMemsetAsync(deg.ptr, 0, deg.bytes(), st_));
-        relabel_degrees<<<grid_for(W_), kThreads, 0, st_>>>(log_.ptr, W_, D_ == 1, V_, deg.ptr, werr); ++launch_counter();
-        const int dbits = bits_for((uint64_t)Ew_);
+        // key: out-degree (how often the scatter form hits r[w]); with dense iterations on a directed graph out- plus
+        // in-degree (the gather form reads x[u] once per IN-edge of u): DPPR_RELABEL_BOTH=1; no difference measured on R-MAT
+        const int both = env_int("DPPR_RELABEL_BOTH", 0);
+        relabel_degrees<<<grid_for(W_), kThreads, 0, st_>>>(log_.ptr, W_, D_ == 1, V_, deg.ptr, werr, both); ++launch_counter();
+        const int dbits = bits_for((uint64_t)2 * Ew_);
         const uint32_t degmax = (uint32_t)((1ull << dbits) - 1);
         relabel_keys<<<grid_for(V_), kThreads, 0, st_>>>(deg.ptr, degmax, rk[0].ptr, rv[0].ptr, V_); ++launch_counter();
         const int rr = sort_pairs(rk[0].ptr, rv[0].ptr, rk[1].ptr, rv[1].ptr, V_, dbits, rscratch.ptr, st_);

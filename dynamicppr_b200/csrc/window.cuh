@@ -70,12 +70,13 @@ __host__ __device__ __forceinline__ uint32_t ring_capacity_for(uint32_t need) {
 // residuals, exported CSR); everything in between is id-agnostic.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-    relabel_degrees(const int2 *__restrict__ log, int64_t W, int directed, int32_t V, uint32_t *__restrict__ deg, int *errflags) {
+    relabel_degrees(const int2 *__restrict__ log, int64_t W, int directed, int32_t V, uint32_t *__restrict__ deg, int *errflags,
+                    int both_ends) {
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < W; i += (int64_t)gridDim.x * kThreads) {
         const int2 e = log[i];
         if ((uint32_t)e.x >= (uint32_t)V || (uint32_t)e.y >= (uint32_t)V) { atomicOr(errflags, kErrBadId); continue; }
         atomicAdd(&deg[e.x], 1u);
-        if (!directed) atomicAdd(&deg[e.y], 1u);
+        if (!directed || both_ends) atomicAdd(&deg[e.y], 1u);  // both_ends: rank by out- plus in-degree
     }
 }
 __global__ void __launch_bounds__(kThreads)
