@@ -58,3 +58,51 @@ def test_baseline_config_full_size(shape, source_kind, batches):
             assert np.abs(r).max() <= eps
             assert invariant_defect(V, rp, ci, od, p, r, src) <= 1e-13
             assert abs(p.sum()) < 1e6 and np.all(np.isfinite(p))
+
+
+@pytest.mark.parametrize("directed", [False, True], ids=["orkut-shaped", "livejournal-shaped"])
+def test_multi_source_default_switching_kernel(directed):
+    """8 top-degree sources on a window large enough (>= 2e7 directed edges x sources) that the engine picks, by itself
+    and with default settings, the kernel that switches between scatter iterations and gather sweeps (csrc/pull.cuh):
+    BASELINE configs[3] / configs[2] shapes at 1/8 and 1/2 scale.  Same size-independent checks, for every source."""
+    if directed:
+        V, M = 2_423_785, 34_496_886
+        edges = graphgen.rmat_directed(V, M, graphgen.BASE_SEED + 2)
+    else:
+        V, M = 384_055, 14_648_135
+        edges = graphgen.powerlaw_undirected(V, M, graphgen.BASE_SEED + 3)
+    batches = 3
+    wl = stream.workload(M, 0.1, 0, 0.01, batches)
+    assert wl.W * (1 if directed else 2) * 8 >= 2e7
+    sources = [int(x) for x in graphgen.top_out_degree(V, edges, directed, 8)]
+    eps = 1e-9
+    sweeps = 0
+    with DynamicPPR(V, directed, wl.W, wl.B, sources, epsilon=eps) as eng:
+        eng.init_window_pairs(edges[: wl.W])
+        eng.solve_initial()
+        for k in range(batches + 1):
+            if k > 0:
+                lo = wl.W + (k - 1) * wl.B
+                eng.slide_pairs(edges[lo: lo + wl.B])
+            st = eng.stats()
+            assert st.error_flags == 0
+            sweeps += st.dense_sweeps
+            if k not in (0, batches):
+                continue
+            rp, ci, od = eng.export_window_csr()
+            erp, eci, eod = numpy_window_csr(V, directed, edges[k * wl.B: k * wl.B + wl.W])
+            np.testing.assert_array_equal(rp, erp)
+            np.testing.assert_array_equal(ci, eci)
+            np.testing.assert_array_equal(od, eod)
+            if directed:  # the out-lists the sweeps read are the transpose of the exported in-lists
+                out = eng.export_window_out_csr()
+                assert out is not None
+                order = np.lexsort((np.repeat(np.arange(V, dtype=np.int64), np.diff(rp)), ci.astype(np.int64)))
+                np.testing.assert_array_equal(out[1], np.repeat(np.arange(V, dtype=np.int32), np.diff(rp))[order])
+                np.testing.assert_array_equal(np.diff(out[0]), od)
+            for i, s in enumerate(sources):
+                p, r = eng.estimates(i), eng.residuals(i)
+                assert np.abs(r).max() <= eps, (k, i)
+                assert invariant_defect(V, rp, ci, od, p, r, s) <= 1e-13, (k, i)
+    if not directed:  # (on the directed shape the device-side cost model may legitimately keep scattering)
+        assert sweeps > 0, "the gather sweeps never ran: the default cost model or size threshold changed"
