@@ -425,6 +425,7 @@ void Engine::launch_push(bool init_mode) {
     }
     a.tile_cap = std::min(std::max(env_int("DPPR_TILE_CAP", 128), 8), kTileMax);
     a.V = V_;
+    a.avg_indeg = (float)((double)Ew_ / (double)V_);
     a.vmeta_out = outlists_ ? vmeta_out_.ptr : vmeta_.ptr;
     a.x[0] = x_[0].ptr; a.x[1] = x_[1].ptr;
     a.Sp = Sp_; a.pull_gshift = pull_gshift_;

@@ -12,10 +12,11 @@
 // iteration is the same Jacobi step, so the residual bound and the estimates are those of the push form up to the
 // order of the floating-point sums.
 //
-// The pop is deferred by one sweep: sweep k leaves x_next[w] = r'[w] where r'[w] is legal (r[w] itself still holds
-// the value, p[w] is untouched), and sweep k+1 -- or nobody, if the loop goes back to scatter mode -- performs
-// p[w] += a x[w], r[w] = 0 for it.  Leaving dense mode is therefore just a compaction of the non-zero x entries
-// into an ordinary (un-popped) frontier queue.
+// The pop is deferred by one sweep: sweep k leaves x_next[w] = r'[w] where r'[w] is legal (p[w] is untouched, and
+// r[w] is not even written: a non-zero x entry IS the residual while the episode lasts), and sweep k+1 -- or nobody,
+// if the loop goes back to scatter mode -- performs p[w] += a x[w], r[w] = 0 for it.  Leaving dense mode is therefore
+// just a compaction of the non-zero x entries into an ordinary (un-popped) frontier queue, which also writes them
+// back to r.
 //
 // Work split by out-degree: see pull_sweep.  The longest lists (big_min or more entries) are cut into chunks dealt
 // to all CTAs, their partial sums meet in `bigacc` and the vertex is finished after one more grid barrier.
@@ -102,17 +103,22 @@ __device__ __forceinline__ uint32_t pull_finish_unit(const PushArgs &a, int phas
         out[j] = 0.0;
         const uint32_t s = s0 + j;
         if (s < (uint32_t)a.S && (len != 0u || xc[j] != 0.0)) {
+            // During a dense episode a non-zero x entry IS the residual (r[w] is stale until pull_compact restores it):
+            // a vertex that stays in the frontier sweep after sweep -- the steady state -- touches r not at all.
             const size_t idx = (size_t)s * a.Vp + w;
-            double rw = pl_ldcs(&a.r[idx]);
-            if (xc[j] != 0.0) {  // w was in the frontier of this sweep: its pop (r[w] == xc[j] still)
+            double rw;
+            if (xc[j] != 0.0) {  // w is in the frontier of this sweep: its pop
                 pl_stcs(&a.p[idx], pl_ldcs(&a.p[idx]) + a.alpha * xc[j]);
                 rw = 0.0;
+            } else {
+                rw = pl_ldcs(&a.r[idx]);
             }
             rw += acc[j] * scale;
-            pl_stcs(&a.r[idx], rw);
             if (legal_push(rw, phase, a.eps)) {
                 out[j] = rw;
                 ++legal;
+            } else {
+                pl_stcs(&a.r[idx], rw);
             }
         }
     }
@@ -425,8 +431,10 @@ __device__ void pull_compact(const PushArgs &a, PushSmem &sm, PushCtrl *c, const
         for (int j = 0; j < SB; ++j) xc[j] = 0.0;
         if (w < V) pull_load_x<SB>(x, w, (uint32_t)a.Sp, s0, xc);
 #pragma unroll
-        for (int j = 0; j < SB; ++j)
+        for (int j = 0; j < SB; ++j) {
+            if (xc[j] != 0.0) __stcg(&a.r[(size_t)(s0 + j) * a.Vp + w], xc[j]);  // (see pull_finish_unit)
             stage_push(xc[j] != 0.0, ((unsigned long long)(s0 + j) << 32) | w, sm, qout, cnt_out, a.qcap, a.ctrl);
+        }
         stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
     }
 }
@@ -438,14 +446,30 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
                                            unsigned long long hpk, unsigned long long &edges_acc, unsigned long long &gath,
                                            unsigned long long &pops_acc, uint32_t &iters_done, uint32_t &sweeps_done,
                                            float rate) {
-    // hubs popped in iteration it-1 still owe their adds
+    // hubs popped in iteration it-1 still owe their adds ...
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         c->dcnt[0] = 0; c->dcnt[1] = 0; c->dcnt[2] = 0;
         c->dedges[0] = 0; c->dedges[1] = 0; c->dedges[2] = 0;
         c->bigpk = 0;
         c->ntiles_active = 0;
     }
-    expand_hubs<0>(a, sm, a.hub[(it + 1) & 1], hpk, a.q[(it + 1) & 1], &c->cnt[(it + 1) % 3], phase, 0, edges_acc);
+    // ... and are simply UN-popped instead of being scattered edge by edge: r[u] += ru, p[u] -= a ru (one thread per hub;
+    // r[u] may already hold adds of this iteration, hence the atomic).  The build pass below then finds u legal again and
+    // the first sweep pushes it in gather form.  With 125 sources on the Orkut-shaped window the seeds of a batch are
+    // mostly hubs: scattering them cost 60 ms per batch.
+    {
+        const HubItem *hin = a.hub[(it + 1) & 1];
+        const uint32_t nh = min((uint32_t)(hpk >> 32), a.hcap);
+        for (uint32_t h = blockIdx.x * kThreads + threadIdx.x; h < nh; h += gridDim.x * kThreads) {
+            const unsigned long long item = __ldcg(&hin[h].item);
+            const double ru = __ldcg(&hin[h].ru);
+            const size_t idx = (size_t)(item >> 32) * a.Vp + (uint32_t)item;
+            atomicAdd(&a.r[idx], ru);
+            atomicAdd(&a.p[idx], -a.alpha * ru);
+        }
+        (void)edges_acc;
+        if (blockIdx.x == 0 && threadIdx.x == 0) pops_acc -= nh;  // they are popped again by the first sweep
+    }
     if (!grid_barrier(c, gen, sm)) return false;
     if (blockIdx.x == 0 && threadIdx.x == 0) c->cnt[(it + 1) % 3] = 0;  // the queues are rebuilt from x on the way out
     pull_build<SB>(a, sm, c, phase, &c->dcnt[0]);

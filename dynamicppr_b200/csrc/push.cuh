@@ -123,6 +123,7 @@ struct PushArgs {
     int32_t tile_cap;            // tile size (frontier items) once a CTA's share of the frontier exceeds 512 items
     // ---- dense iterations in gather form (pull.cuh), variant 0 ----
     int32_t V;
+    float avg_indeg;             // E_w / V
     const uint4 *vmeta_out;      // out-lists (the in-lists themselves when the graph is undirected)
     double *x[2];                // popped residuals of the running / next sweep, vertex-major [V][Sp]
     int32_t Sp;                  // sources per vertex row of x: 1, or S rounded up to a multiple of 4 << pull_gshift
@@ -647,6 +648,7 @@ __global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(con
         const bool carrying = VAR == 0 && a.carry_gamma > 0.0 && a.carry_gamma < 1.0;
         double theta = carrying ? __longlong_as_double((long long)__ldcg(&c->theta0[phase])) * a.carry_scale : a.eps;
         uint32_t n_prev = 0;
+        bool fresh_phase = true;
         double t_prev = 0.0;  // in-edges the previous scatter iteration traversed, grid-wide (DENSE)
         while (alive) {
             bool want_dense = false;
@@ -664,6 +666,17 @@ __global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(con
                     alive = false;
                     break;
                 }
+                if (DENSE && !carrying && fresh_phase && rate > 0.f && sw > 0.f) {
+                    // first iteration of a phase: no history -- the seeds are batch endpoints, take
+                    // twice the average in-degree for them
+                    const double pred = 2.0 * (double)n * (double)a.avg_indeg;
+                    if (pred * (double)rate > 1.25 * (double)sw) {
+                        want_dense = true;
+                        dense_hpk = hpk;
+                        dense_rate = rate;
+                        break;
+                    }
+                }
                 if (DENSE && !carrying && n_prev != 0) {
                     // expected work of this iteration: the tiles the previous one traversed, scaled by the frontier
                     // growth, plus the hub chunks it left for this one.  Once both costs have been measured on this
@@ -680,6 +693,7 @@ __global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(con
                     }
                 }
                 n_prev = n;
+                fresh_phase = false;
                 const unsigned long long edges_before = edges_acc;
                 const unsigned long long t_iter0 = (DENSE && blockIdx.x == 0 && threadIdx.x == 0) ? global_ns() : 0ull;
                 if (blockIdx.x == 0 && threadIdx.x == 0) {  // slots nobody reads or writes during this iteration
@@ -736,6 +750,7 @@ __global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(con
                 hubs_acc += (uint32_t)(dense_hpk >> 32);
             }
             n_prev = 0;  // (no growth estimate for the first scatter iteration after the sweeps)
+            fresh_phase = false;
             t_prev = 0.0;
             DenseIO io{edges_acc, gath_acc, pops_acc, iters_done, sweeps_done, gen, dense_rate};
             alive = a.Sp == 1 ? dense_mode<1>(a, sm, c, phase, it, dense_hpk, io) : dense_mode<4>(a, sm, c, phase, it, dense_hpk, io);

@@ -14,8 +14,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=float, default=1.0); ap.add_argument("--batches", type=int, default=20)
 ap.add_argument("--kinds", default="low,top"); ap.add_argument("--check", type=int, default=1)
 ap.add_argument("--sources", type=int, default=1); ap.add_argument("--top-batches", type=int, default=3)
+ap.add_argument("--V", type=int, default=41_652_230); ap.add_argument("--M", type=int, default=1_468_365_182)
+ap.add_argument("--undirected", type=int, default=0, help="1: feed the same device-generated pairs as an UNDIRECTED stream (perf exploration of other shapes)")
 a = ap.parse_args()
-V, M = int(41_652_230 * a.scale), int(1_468_365_182 * a.scale)
+V, M = int(a.V * a.scale), int(a.M * a.scale)
 wl = stream.workload(M, 0.1, 0, 0.01, a.batches)
 nb = min(a.batches, wl.runnable_batches(M))
 need = wl.W + nb * wl.B
@@ -26,7 +28,7 @@ torch.cuda.synchronize(); tgen = time.time() - t0
 outdeg_all = torch.bincount(dev[: wl.W, 0].long(), minlength=V)  # (initial window only: the choice must not depend on --batches)
 # source buckets of the reference's workload tool (workload/Workload.cpp:47-55): ranks by out-degree
 order = torch.argsort(outdeg_all, descending=True, stable=True)
-pick = lambda lo: order[lo: lo + 8].cpu().numpy().astype(np.int32)
+pick = lambda lo: order[lo: lo + max(8, a.sources)].cpu().numpy().astype(np.int32)
 top, rank1k, rank1m = pick(0), pick(1000), pick(min(1_000_000, V // 4))
 low = np.array([1, 2, 3, 5, 8, 13, 21, 34], dtype=np.int32)
 del order
@@ -35,7 +37,7 @@ eps = 1e-9
 for kind in a.kinds.split(","):
     srcs = {"top": top, "rank1k": rank1k, "rank1m": rank1m, "low": low}[kind][: a.sources]
     t0 = time.time()
-    eng = DynamicPPR(V, True, wl.W, wl.B, srcs, epsilon=eps)
+    eng = DynamicPPR(V, not a.undirected, wl.W, wl.B, srcs, epsilon=eps)
     eng.init_window_device_pairs(dev.data_ptr(), wl.W); eng.sync(); tinit = time.time() - t0
     t0 = time.time(); eng.solve_initial(); eng.sync(); tsolve = time.time() - t0
     s0 = eng.stats(0)
