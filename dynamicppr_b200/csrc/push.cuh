@@ -25,6 +25,9 @@
 //     atomic per 256-edge step).
 //   * Residual scatter uses the native FP64 atomicAdd returning the old value (the reference emulates
 //     it with a CAS loop, gpu/GPUUtil.cuh:21-30): every variant needs `old` for its enqueue rule.
+//   * On large windows variant 0 runs the iterations whose frontier covers most of the graph as gather
+//     sweeps over the out-lists instead (pull.cuh, instantiation push_persistent<0, true>); the switch is
+//     decided on the device from measured costs.
 //
 // Variants (-o), semantics of SURVEY A.5:
 //   0 OPTIMIZED      eager + fast frontier.  ru is claimed with one atomicExch(r[u], 0) at pop time, so
