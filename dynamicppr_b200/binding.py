@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "dppr_slide_device_pairs", "dppr_sync", "dppr_get_batch_stats", "dppr_batches_done",
     "dppr_get_estimates", "dppr_get_residuals", "dppr_copy_estimates_device", "dppr_export_window_csr", "dppr_export_window_out_csr",
     "dppr_window_csr_entries", "dppr_set_state", "dppr_repair_only", "dppr_test_sort_pairs",
-    "dppr_test_exclusive_scan", "dppr_debug_iterlog", "dppr_debug_ctalog", "dppr_kernel_launches",
+    "dppr_test_exclusive_scan", "dppr_test_relabel_slot", "dppr_debug_iterlog", "dppr_debug_ctalog", "dppr_kernel_launches",
 ]
 
 
@@ -102,6 +102,8 @@ def load_library():
     L.dppr_debug_iterlog.argtypes = [vp, C.POINTER(C.c_uint32), C.c_int32, C.POINTER(C.c_int32)]
     L.dppr_test_sort_pairs.argtypes = [C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int64, C.c_int32]
     L.dppr_test_exclusive_scan.argtypes = [C.c_int32, C.POINTER(C.c_uint32), C.c_int64, C.POINTER(C.c_uint64)]
+    L.dppr_test_relabel_slot.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    L.dppr_test_relabel_slot.restype = C.c_uint32
     _LIB = L
     return L
 

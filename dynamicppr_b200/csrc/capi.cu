@@ -241,6 +241,10 @@ int dppr_test_sort_pairs(int32_t device, uint32_t *keys, uint32_t *vals, int64_t
     }
 }
 
+uint32_t dppr_test_relabel_slot(uint32_t rank, uint32_t vertex_count, uint32_t blocks) {
+    return dppr::relabel_slot(rank, vertex_count, blocks);
+}
+
 int dppr_test_exclusive_scan(int32_t device, uint32_t *data, int64_t n, uint64_t *total) {
     using namespace dppr;
     try {

@@ -187,6 +187,9 @@ int dppr_debug_ctalog(dppr_engine *e, unsigned long long *out, int32_t cap_rows,
 int dppr_test_sort_pairs(int32_t device, uint32_t *keys, uint32_t *vals, int64_t n, int32_t key_bits);
 /* exclusive prefix sum on the device, host in / host out; returns the total in *total */
 int dppr_test_exclusive_scan(int32_t device, uint32_t *data, int64_t n, uint64_t *total);
+/* host-only arithmetic (no GPU needed): the internal id of the vertex of out-degree rank k among V, ranks dealt over
+ * `blocks` blocks (csrc/window.cuh, relabel_slot) -- a bijection of [0, V) the CPU suite checks */
+uint32_t dppr_test_relabel_slot(uint32_t rank, uint32_t vertex_count, uint32_t blocks);
 
 #ifdef __cplusplus
 }

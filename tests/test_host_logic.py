@@ -247,3 +247,18 @@ def test_two_rank_gloo_source_sharding_and_gather(tmp_path):
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "GATHER_OK" in r.stdout
+
+
+def test_internal_vertex_order_is_a_bijection_with_hot_block_prefixes():
+    """csrc/window.cuh relabel_slot: rank k (0 = highest out-degree) -> internal id.  Host arithmetic, no GPU."""
+    L = binding.load_library()
+    for V, P in [(1, 1), (7, 3), (10, 1024), (1000, 1), (1000, 7), (4097, 1024), (100_003, 1024)]:
+        P = min(P, V)
+        ids = np.array([L.dppr_test_relabel_slot(k, V, P) for k in range(V)], dtype=np.int64)
+        assert sorted(ids.tolist()) == list(range(V)), (V, P)           # a permutation of [0, V)
+        q, rem = divmod(V, P)
+        starts = np.array([r * q + min(r, rem) for r in range(P)])      # first id of each block
+        np.testing.assert_array_equal(ids[:P], starts)                  # the P hottest vertices head the P blocks
+        if V >= 2 * P:                                                   # ... and consecutive ranks are a block apart
+            assert np.all(np.abs(np.diff(ids[:P])) >= q)
+            np.testing.assert_array_equal(ids[P: 2 * P], starts + 1)    # the next P sit right behind them
