@@ -1,30 +1,39 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the streaming reverse-push PPR hot path (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5] [--sources S]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A *step* is one slide of the window by one batch: B edges arrive, B expire, the window graph is
-updated on the device, residuals are repaired and both push phases run to exhaustion.
-Workload (config.workload): BASELINE.json configs[1] -- youtube-shaped synthetic undirected
-power-law stream (1,134,890 V, 2,987,624 E), window 0.1, -r 0.01 (B = 2,987 edges), eps 1e-9,
-top-out-degree source, variant -o 0.  One process per GPU; with N > 1 every rank replicates the
-window graph and owns its own source(s) (weak scaling, no collective on the data path; the final
-gather of estimates over NCCL happens after the timed region).
+A *step* is one slide of the window by one batch: B edges arrive, B expire, the window graph is updated on the
+device, and for EVERY source of the job residuals are repaired and both push phases run to exhaustion.
+
+Workloads (dynamicppr_b200/workloads.py; --config picks one, default 4):
+  4  BASELINE configs[3]: Orkut-shaped undirected power-law stream (3.07 M V, 117.2 M E, DRAM-resident window of
+     23.4 M CSR entries), the exact top-1000 out-degree sources, -r 0.01: ONE fixed multi-source job, its source list
+     split over the N GPUs (window graph replicated, no data-path collective) -> strong scaling; metric
+     source_batches_per_sec (a source-batch = one source refreshed for one batch; x B = (source, edge) updates/s).
+  5  BASELINE configs[4]: Twitter-shaped directed R-MAT (41.7 M V, 1.47 B E), top-64 sources, strong scaling.
+  2  BASELINE configs[1]: youtube-shaped (round 1's workload, L2-resident), one source per GPU, edge_updates_per_sec.
+  3  BASELINE configs[2]: LiveJournal-shaped R-MAT, mode 1 -c 100 -l 10000 (small-batch latency), --variant 0..3.
 
 Printed JSON (one line, rank 0):
-  value      whole-job edge updates/s with the stream already resident in HBM; the clock is the sum
-             of the per-step CUDA-event times on the engine's stream (window update + repair +
-             push), max over ranks.  L2 is flushed between steps (outside the events).
-  e2e        same metric through the C-ABI call a user makes (dppr_slide_pairs with HOST buffers:
-             pinned staging + H2D inside the timed region, plus a D2H read of the step's record).
-  roofline   push kernel (push_persistent<0, false>): algorithmic bytes (24 B per traversed in-edge +
-             56 B per frontier pop) / CUDA-event time of that kernel, vs the measured
-             HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline  the reference's own CPU implementation (oracle/_ref/ref_harness_omp: unmodified
-             reference sources, cilk_for backed by OpenMP) on this box's host cores, same stream,
-             same flags, bounded number of batches.
-`--impl reference` times that CPU implementation as the reference arm (rank 0 only).
+  value      whole-job throughput with the stream already resident in HBM; the clock is the sum of the per-step
+             CUDA-event times on the engine's stream (window update + repair + push), max over ranks.  The working set
+             exceeds L2 on configs 4 / 5 (said in config.l2); on configs 2 / 3 L2 is flushed between steps.
+  e2e        the same metric through the C-ABI call a user makes (dppr_slide_pairs with HOST buffers: pinned staging +
+             H2D inside the timed region) plus the read-back a query needs: the step record and the top-16 estimates
+             of every source on the rank (dppr_get_topk, D2H).
+  roofline   the persistent push kernel: algorithmic bytes of what it did (scatter iterations: 24 B per traversed
+             in-edge + 56 B per pop; gather sweeps: 4 B per out-list entry walked + 8 B per (entry, source)
+             gather + 16 B per (vertex, source) unit + 16 B per pop) / CUDA-event time of that kernel, against the
+             measured HBM copy bandwidth (MEASURED_PEAKS.json).  `traffic` = DRAM bytes per launch from the committed
+             ncu capture of the same kernel on the same config (profiles/traffic.json), else null.
+  cpu_baseline  the reference's own CPU implementation (oracle/_ref/ref_harness_omp: unmodified reference classes,
+             cilk_for backed by OpenMP) on this box's host cores, same stream (.bin prefix written by the host twin of
+             the device generator), same flags, a bounded sample (sources x batches stated).
+`--impl reference` times that CPU implementation as the reference arm (rank 0 only): K timed + W warm-up batches for
+a SAMPLE of the job's sources (--cpu-sources, quartile ranks of the source list), extrapolated to the job as
+1 / mean seconds per source-batch -- the reference runs one source per process, sequentially on all cores.
 """
 from __future__ import annotations
 
@@ -42,13 +51,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SHAPE = "youtube"
-WINDOW_RATIO, BATCH_RATIO, EPS = 0.1, 0.01, 1e-9
-METRIC, UNIT = "edge_updates_per_sec", "edge updates/s"
+TOPK = 16
 
 
 def log(*a):
-    print(*a, file=sys.stderr, flush=True)
+    print("[bench]", *a, file=sys.stderr, flush=True)
 
 
 def measured_hbm_peak():
@@ -57,28 +64,6 @@ def measured_hbm_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
-
-
-def make_workload(nsrc_total):
-    from dynamicppr_b200 import graphgen, stream
-    V, M, directed = graphgen.SHAPES[SHAPE]
-    seed = graphgen.BASE_SEED + list(graphgen.SHAPES).index(SHAPE)
-    t0 = time.time()
-    edges = graphgen.powerlaw_undirected(V, M, seed)
-    wl = stream.workload(M, WINDOW_RATIO, 0, BATCH_RATIO, 10 ** 9)
-    sources = graphgen.top_out_degree(V, edges, directed, max(nsrc_total, 1))
-    log(f"[bench] {SHAPE}-shaped stream V={V} M={M} W={wl.W} B={wl.B} generated in {time.time() - t0:.1f}s")
-    return V, M, directed, edges, wl, sources
-
-
-def bin_path(V, edges):
-    from dynamicppr_b200 import graphgen
-    d = os.path.join(tempfile.gettempdir(), "dppr_bench")
-    os.makedirs(d, exist_ok=True)
-    p = os.path.join(d, f"{SHAPE}.bin")
-    if not os.path.exists(p) or os.path.getsize(p) != 4 + 8 * len(edges):
-        graphgen.write_bin(p, V, edges)
-    return p
 
 
 class ClockSampler:
@@ -123,36 +108,85 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference_cpu(binfile, source, n_batches, threads, drop):
-    """the reference's CPU implementation of the path (oracle/_ref, built from the unmodified sources)"""
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (oracle/_ref), or the C restatement if it is not there
+# ---------------------------------------------------------------------------------------------------------------------
+def sample_sources(sources, n):
+    """n sources spread over the job's list by rank (quartile-style): rank (2i+1) S / (2n)"""
+    S = len(sources)
+    n = max(1, min(n, S))
+    return [int(sources[((2 * i + 1) * S) // (2 * n)]) for i in range(n)]
+
+
+def run_reference_cpu(cfg, sources, n_batches, threads, drop, variant):
+    """Returns per-(source, batch) times of the reference CPU classes on the same stream, or None if the binary is absent."""
+    from dynamicppr_b200 import workloads
     harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness_omp")
-    kind = "reference"
     if not os.path.exists(harness):
         return None
-    tfile = os.path.join(tempfile.gettempdir(), f"dppr_ref_times_{os.getpid()}.txt")
-    cmd = [harness, "-d", binfile, "-a", "0", "-i", "0", "-y", "1", "-n", "0", "-w", str(WINDOW_RATIO), "-r",
-           str(BATCH_RATIO), "-b", str(n_batches), "-s", str(source), "-t", str(threads), "-o", "0", "-e", repr(EPS),
-           "--quiet", "--times", tfile]
+    wl = cfg.workload()
+    d = os.path.join(tempfile.gettempdir(), "dppr_bench")
+    os.makedirs(d, exist_ok=True)
+    t0 = time.time()
+    binfile = workloads.write_prefix_bin(cfg, os.path.join(d, f"config{cfg.index}.bin"), wl.W + (n_batches + 1) * wl.B)
+    t_bin = time.time() - t0
+    tfile = os.path.join(d, f"ref_times_{os.getpid()}.txt")
+    cmd = [harness, "-d", binfile] + cfg.cli_flags(n_batches) + ["-s", str(sources[0]), "-t", str(threads), "-o", str(variant),
+           "--quiet", "--times", tfile, "--sources", ",".join(str(s) for s in sources)]
+    if not cfg.directed:
+        # the reference's incremental host adjacency is wrong on undirected streams (DESIGN.md, defect D1): rebuild the true
+        # window before each batch (untimed there, as the reference's own -DVALIDATE build does) so both arms work on the same graph
+        cmd.append("--scratch-graph")
     t0 = time.time()
     subprocess.run(cmd, check=True, capture_output=True, text=True)
     wall = time.time() - t0
     rows = [ln.split() for ln in open(tfile)]
     os.remove(tfile)
-    us = np.array([float(r[1]) for r in rows[1:]])  # row 0 = initial solve
-    us = us[drop:] if len(us) > drop else us
-    return dict(kind=kind, ms_per_step=float(us.mean() / 1e3), p50_ms=float(np.median(us) / 1e3), steps=len(us), wall_s=wall)
+    us = np.array([float(r[1]) for r in rows if int(r[0]) > drop])  # batch 0 = initial solve
+    init_us = np.array([float(r[1]) for r in rows if int(r[0]) == 0])
+    per_batch = {}
+    for r in rows:
+        if int(r[0]) > drop:
+            per_batch.setdefault(int(r[0]), []).append(float(r[1]))
+    step_ms = np.array([np.mean(v) for _, v in sorted(per_batch.items())]) / 1e3  # mean over the sampled sources, per batch
+    return dict(kind="reference", s_per_source_batch=float(us.mean() / 1e6), p50_ms=float(np.median(step_ms)), steps=len(step_ms),
+                sources=len(sources), wall_s=wall, bin_s=t_bin, init_solve_s=float(init_us.mean() / 1e6))
 
 
-def run_port_cpu(V, directed, edges, wl, source, n_batches):
+def run_port_cpu(cfg, sources, n_batches, drop, variant):
     """fallback CPU baseline: the single-threaded C restatement (oracle/dppr_oracle.c)"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle as orc
-    o = orc.Oracle(V, directed, edges, wl.W, wl.B, source, EPS, 0)
-    o.initial_solve()
+    from dynamicppr_b200 import workloads
+    wl = cfg.workload()
+    edges = workloads.host_edges(cfg, 0, wl.W + (n_batches + 1) * wl.B)
     ts = []
-    for _ in range(n_batches):
-        t0 = time.perf_counter(); o.slide(wl.B); ts.append(time.perf_counter() - t0)
-    return dict(kind="port", ms_per_step=float(np.mean(ts) * 1e3), p50_ms=float(np.median(ts) * 1e3), steps=n_batches, wall_s=sum(ts))
+    for s in sources[:1]:
+        o = orc.Oracle(cfg.V, cfg.directed, edges, wl.W, wl.B, int(s), cfg.eps, variant)
+        o.initial_solve()
+        for k in range(n_batches):
+            t0 = time.perf_counter(); o.slide(wl.B); dt = time.perf_counter() - t0
+            if k >= drop:
+                ts.append(dt)
+    return dict(kind="port", s_per_source_batch=float(np.mean(ts)), p50_ms=float(np.median(ts) * 1e3), steps=len(ts), sources=1,
+                wall_s=float(np.sum(ts)), bin_s=0.0, init_solve_s=0.0)
+
+
+def cpu_arm(cfg, job_sources, n_cpu_sources, n_batches, drop, variant, ncores):
+    picked = sample_sources(job_sources, n_cpu_sources)
+    res = run_reference_cpu(cfg, picked, n_batches + drop, ncores, drop, variant)
+    if res is None:
+        res = run_port_cpu(cfg, picked, min(n_batches, 3) + drop, drop, variant)
+    wl = cfg.workload()
+    sb_per_s = 1.0 / res["s_per_source_batch"]
+    sample = (f"{res['steps']} batches of {wl.B} edges after {drop} warm-up batch(es), {res['sources']} of the job's {len(job_sources)} "
+              f"sources (list ranks {[int(np.where(np.asarray(job_sources) == s)[0][0]) for s in picked[:res['sources']]]}), run one after "
+              f"the other with all threads each; ")
+    sample += ("unmodified reference cpu/ classes (oracle/_ref/ref_harness_omp), cilk_for backed by OpenMP" if res["kind"] == "reference"
+               else "single-threaded C restatement of the reference (oracle/dppr_oracle.c)")
+    if res["kind"] == "reference" and not cfg.directed:
+        sample += "; true window rebuilt (untimed) before each batch because the reference's incremental adjacency is wrong on undirected streams (DESIGN.md D1)"
+    return res, sb_per_s, sample, picked
 
 
 def main():
@@ -162,13 +196,16 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--sources-per-gpu", type=int, default=1)
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5])
+    ap.add_argument("--sources", type=int, default=0, help="sources of the whole job (default: the config's: 1000 / 64; configs 2, 3: per GPU)")
     ap.add_argument("--variant", type=int, default=0)
-    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps")
-    ap.add_argument("--cpu-batches", type=int, default=40, help="batches of the bounded CPU baseline sample")
+    ap.add_argument("--no-flush", action="store_true", help="configs 2 / 3: do not flush L2 between steps")
+    ap.add_argument("--cpu-sources", type=int, default=2, help="sources of the job the CPU arm samples")
+    ap.add_argument("--cpu-batches", type=int, default=3, help="timed batches of the in-line cpu_baseline (the reference arm uses --steps)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end loop (default: --steps, or 5 when a step exceeds 0.2 s)")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
@@ -176,32 +213,44 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = os.cpu_count() or 1
 
-    config = {"workload": f"BASELINE configs[1]: {SHAPE}-shaped synthetic undirected power-law stream, window {WINDOW_RATIO}, "
-                          f"-r {BATCH_RATIO} (mode 0), eps {EPS}, top-out-degree source(s), -o {a.variant}",
-              "variant": a.variant, "sources_per_gpu": a.sources_per_gpu, "parallelism": f"source-sharded x{world}, window graph replicated",
-              "l2": "flushed between steps (256 MiB write, outside the timed events)" if not a.no_flush else "not flushed (stateful stream)"}
+    from dynamicppr_b200 import workloads
+    cfg = workloads.CONFIGS[a.config]
+    wl = cfg.workload()
+    multi = cfg.multi_source
+    if multi:
+        S_total = a.sources if a.sources > 0 else cfg.n_sources
+        metric, unit, scaling = "source_batches_per_sec", "source-batches/s", "strong"
+    else:
+        spg = a.sources if a.sources > 0 else 1
+        S_total = spg * world
+        metric, unit, scaling = "edge_updates_per_sec", "edge updates/s", "weak"
+    avail = wl.runnable_batches(cfg.M)
+    resident = cfg.index in (2, 3)  # working set fits the 126 MB L2: flush between steps
+    config = {"workload": cfg.describe() + f", {'top-' + str(S_total) + ' out-degree sources' if multi else 'top out-degree source(s)'}, -o {a.variant}",
+              "variant": a.variant, "sources_total": S_total, "V": cfg.V, "M": cfg.M, "W": wl.W, "B": wl.B,
+              "parallelism": (f"{S_total} sources split over {world} GPU(s), window graph replicated, no data-path collective" if multi
+                              else f"source-sharded x{world} ({S_total // world} per GPU), window graph replicated"),
+              "l2": ("flushed between steps (256 MiB write, outside the timed events)" if resident and not a.no_flush else
+                     "not flushed: stateful stream" if resident else
+                     f"not flushed: per-GPU working set ({16 * cfg.V * max(S_total // world, 1) / 1e9:.1f} GB of p, r + the window graph) exceeds the 126 MB L2")}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if a.impl == "reference":
         if rank != 0:
             return
-        V, M, directed, edges, wl, sources = make_workload(1)
-        config.update(V=V, M=M, W=wl.W, B=wl.B)
-        binfile = bin_path(V, edges)
-        steps = min(a.steps, wl.runnable_batches(M) - a.warmup)
-        res = run_reference_cpu(binfile, int(sources[0]), steps + a.warmup, ncores, a.warmup)
-        if res is None:
-            res = run_port_cpu(V, directed, edges, wl, int(sources[0]), min(steps, 5))
-        value = wl.B / (res["ms_per_step"] * 1e-3)
+        job_sources = workloads.top_sources(cfg, S_total, on_host=not _cuda_ok())
+        steps = min(a.steps, avail - a.warmup)
+        res, sb_per_s, sample, picked = cpu_arm(cfg, job_sources, a.cpu_sources if multi else 1, steps, a.warmup, a.variant, ncores)
+        value = sb_per_s if multi else sb_per_s * wl.B
         cores = ncores if res["kind"] == "reference" else 1
-        out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": res["steps"],
-               "warmup": a.warmup, "ms_per_step": res["ms_per_step"], "p50_ms": res["p50_ms"], "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-               "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": res["kind"],
-                                "sample": f"{res['steps']} batches of {wl.B} edges after {a.warmup} warm-up batches, 1 source; "
-                                          "reference cpu/ sources, cilk_for backed by OpenMP" if res["kind"] == "reference"
-                                          else f"{res['steps']} batches, single-threaded C restatement"},
-               "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        config["reference_sampling"] = (f"value = 1 / mean seconds per source-batch over {res['sources']} sampled source(s) x {res['steps']} batches"
+                                        + (" (x B edges)" if not multi else "") + "; the reference processes a job's sources one process at a time")
+        out = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": a.gpus, "steps": res["steps"],
+               "warmup": a.warmup, "ms_per_step": res["s_per_source_batch"] * 1e3 * (S_total if multi else 1), "p50_ms": res["p50_ms"],
+               "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+               "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": res["kind"], "sample": sample,
+                                "s_per_source_batch": res["s_per_source_batch"], "init_solve_s": res["init_solve_s"]},
+               "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
         print(json.dumps(out), file=real_stdout, flush=True)
         return
@@ -216,21 +265,25 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    spg = a.sources_per_gpu
-    V, M, directed, edges, wl, sources = make_workload(world * spg)
-    config.update(V=V, M=M, W=wl.W, B=wl.B)
-    my_sources = sharding.shard_sources(sources, rank, world, spg)
-    avail = wl.runnable_batches(M)
+    t0 = time.time()
+    job_sources = workloads.top_sources(cfg, S_total, device=local_rank)
+    my_sources = sharding.shard_sources(job_sources, rank, world, None if multi else S_total // world)
     K, Wm = a.steps, a.warmup
     if Wm + 2 * K > avail:
-        K = (avail - Wm) // 2
-    eng = DynamicPPR(V, directed, wl.W, wl.B, my_sources, epsilon=EPS, variant=a.variant, device=local_rank, record_timing=True)
-    eng.init_window_pairs(edges[: wl.W])
+        K = max(1, (avail - Wm) // 2)
+    n_dev = wl.W + (Wm + K) * wl.B
+    dev_edges = workloads.device_edges(cfg, 0, n_dev, local_rank)
+    torch.cuda.synchronize()
+    log(f"config {cfg.index}: V={cfg.V} M={cfg.M} W={wl.W} B={wl.B}; {len(my_sources)} of {S_total} sources on this rank; "
+        f"stream + source ranking ready in {time.time() - t0:.1f}s")
+    t0 = time.time()
+    eng = DynamicPPR(cfg.V, cfg.directed, wl.W, wl.B, my_sources, epsilon=cfg.eps, variant=a.variant, device=local_rank, record_timing=True)
+    eng.init_window_device_pairs(dev_edges.data_ptr(), wl.W)
     eng.solve_initial()
     eng.sync()
-
-    dev_edges = torch.from_numpy(np.ascontiguousarray(edges[wl.W: wl.W + (Wm + K) * wl.B])).cuda()
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    s0 = eng.stats(0)
+    log(f"engine ready in {time.time() - t0:.1f}s (initial solve {s0.ms_push:.1f} ms, {s0.iterations} iterations)")
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if resident and not a.no_flush else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -239,12 +292,12 @@ def main():
         torch.cuda.synchronize()
 
     def flush():
-        if not a.no_flush:
+        if flush_buf is not None:
             flush_buf.zero_()
             torch.cuda.synchronize()
 
     def dev_step(k):
-        eng.slide_device_pairs(dev_edges.data_ptr() + 8 * k * wl.B, wl.B)
+        eng.slide_device_pairs(dev_edges.data_ptr() + 8 * (wl.W + k * wl.B), wl.B)
 
     for k in range(Wm):  # warm-up (untimed)
         flush(); dev_step(k)
@@ -268,79 +321,102 @@ def main():
     ppr_ms = f("ms_repair") + f("ms_push")
     dev_total_ms = float(step_ms.sum())
 
-    # ---- end to end: host buffers through the public C-ABI call, D2H of the step record inside the timed region
-    host_edges = np.ascontiguousarray(edges[wl.W + (Wm + K) * wl.B: wl.W + (Wm + 2 * K) * wl.B])
+    # ---- end to end: host buffers through the public C-ABI call; the step record and the top-k estimates of every
+    # source of this rank are read back inside the timed region
+    Ke = a.e2e_steps if a.e2e_steps > 0 else (K if dev_total_ms / K < 200.0 else min(K, 5))
+    Ke = max(1, min(Ke, avail - Wm - K))
+    host_edges = np.ascontiguousarray(workloads.host_edges(cfg, wl.W + (Wm + K) * wl.B, Ke * wl.B))
     e2e_t = []
-    for k in range(K):
+    for k in range(Ke):
         flush()
         t0 = time.perf_counter()
         eng.slide_pairs(host_edges[k * wl.B:(k + 1) * wl.B])
         st = eng.stats()  # synchronises and reads the batch record back from pinned host memory
+        ids, vals = eng.topk(TOPK)
         e2e_t.append(time.perf_counter() - t0)
         if st.error_flags:
             raise SystemExit(f"device error flags {st.error_flags}: results invalid")
-    e2e_total_s = float(np.sum(e2e_t))
+    e2e_ms_per_step = float(np.mean(e2e_t)) * 1e3
+    assert ids.shape == (len(my_sources), TOPK) and np.all(vals[:, 0] > 0)
 
-    # ---- max over ranks
-    gathered_rows = spg
+    # ---- max over ranks; the job's only data collective (after the timed region): top-k digests of every source and
+    # one full estimate vector per rank to rank 0
+    gathered_rows = len(my_sources)
     if world > 1:
-        dev_total_ms, e2e_total_s, t_wall = sharding.max_over_ranks([dev_total_ms, e2e_total_s, t_wall], device="cuda")
-        # the only data collective of the job: gather the estimate vectors (after the timed region)
-        mine = torch.empty((spg, V), dtype=torch.float64, device="cuda")
-        for i in range(spg):
-            eng.copy_estimates_device(i, mine[i].data_ptr())
-        gathered = sharding.gather_estimates(mine, dst=0)
+        dev_total_ms, e2e_ms_per_step, t_wall = sharding.max_over_ranks([dev_total_ms, e2e_ms_per_step, t_wall], device="cuda")
+        digest = torch.from_numpy(np.concatenate([ids.astype(np.float64), vals], axis=1)).cuda()
+        got = sharding.gather_estimates(digest, dst=0)
+        full = torch.empty((1, cfg.V), dtype=torch.float64, device="cuda")
+        eng.copy_estimates_device(0, full.data_ptr())
+        fulls = sharding.gather_estimates(full, dst=0)
         if rank == 0:
-            gathered_rows = sum(int(g.shape[0]) for g in gathered)
-    units = float(world * spg * K * wl.B)  # (source, edge) updates processed by the whole job
-    value = units / (dev_total_ms * 1e-3)
-    e2e_value = units / e2e_total_s
+            gathered_rows = sum(int(g.shape[0]) for g in got)
+            assert len(fulls) == world
+    n_units = float(S_total * K) if multi else float(S_total * K * wl.B)
+    value = n_units / (dev_total_ms * 1e-3)
+    e2e_value = (n_units / K) / (e2e_ms_per_step * 1e-3)
 
     if rank == 0:
         T, F = f("traversed_edges"), f("frontier_pops")
+        Ts, Fd = f("scatter_edges"), f("dense_pops")
+        L, Ls, U = f("dense_slots"), f("dense_pairs"), f("dense_units")
         push_s = float(f("ms_push").sum()) * 1e-3
-        alg_bytes = float((24.0 * T + 56.0 * F).sum())
+        alg_bytes = float((24.0 * Ts + 56.0 * (F - Fd) + 4.0 * L + 8.0 * Ls + 16.0 * U + 16.0 * Fd).sum())
         peak, peak_src = measured_hbm_peak()
         achieved = alg_bytes / push_s / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_push.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        roofline = {"bound": "hbm", "kernel": f"push_persistent<{a.variant}, false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        dense = bool(f("dense_sweeps").sum() > 0)
+        traffic, traffic_note = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ent = tj.get(f"config{cfg.index}_s{len(my_sources)}_o{a.variant}")
+            if ent:
+                traffic, traffic_note = ent.get("dram_bytes_per_launch"), ent.get("source")
+        except Exception:
+            pass
+        kname = f"push_persistent<{a.variant}, {'true' if (dense or (a.variant == 0 and cfg.index in (4, 5))) else 'false'}>"
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes / K, "launch_ms": push_s * 1e3 / K,
-                    "note": "working set (p, r, window graph ~50 MB) is L2-resident on B200: the kernel is bound by dependent "
-                            "L2 round trips and FP64 atomics, not by DRAM; see DESIGN.md"}
+                    "scatter_form_equivalent_GBps": float((24.0 * T + 56.0 * F).sum()) / push_s / 1e9,
+                    "note": ("bytes = 24 T_scatter + 56 F_scatter + 4 slots + 8 (slot, source) gathers + 16 (vertex, source) units + 16 F_dense "
+                             "(DESIGN.md 3.3); 'scatter_form_equivalent' credits every gathered non-zero pair the 24 B a scatter would move "
+                             "and is NOT the roofline figure" if dense else
+                             "scatter iterations only: 24 B per traversed in-edge + 56 B per pop; L2-resident working set: bound by dependent "
+                             "L2 round trips and FP64 atomics, not DRAM (DESIGN.md 3.3)")}
         cpu = None
         if world == 1 and not a.no_cpu:
-            binfile = bin_path(V, edges)
-            res = run_reference_cpu(binfile, int(my_sources[0]), a.cpu_batches + 2, ncores, 2)
-            if res is None:
-                res = run_port_cpu(V, directed, edges, wl, int(my_sources[0]), 3)
-            cpu = {"value": wl.B / (res["ms_per_step"] * 1e-3), "unit": UNIT, "cores": ncores if res["kind"] == "reference" else 1,
-                   "kind": res["kind"], "ms_per_step": res["ms_per_step"],
-                   "sample": f"{res['steps']} batches of {wl.B} edges of the same stream, same source, after 2 warm-up batches"
-                             + ("; unmodified reference cpu/ sources with cilk_for backed by OpenMP" if res["kind"] == "reference" else
-                                "; single-threaded C restatement of the reference")}
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-               "ms_per_step": dev_total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            res, sb_per_s, sample, _ = cpu_arm(cfg, job_sources, a.cpu_sources if multi else 1, a.cpu_batches, 1, a.variant, ncores)
+            cpu = {"value": sb_per_s if multi else sb_per_s * wl.B, "unit": unit, "cores": ncores if res["kind"] == "reference" else 1,
+                   "kind": res["kind"], "s_per_source_batch": res["s_per_source_batch"], "init_solve_s": res["init_solve_s"], "sample": sample}
+        out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": Wm,
+               "ms_per_step": dev_total_ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
-               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * wl.B, "d2h_bytes_per_step": 128,
-                       "ms_per_step": e2e_total_s * 1e3 / K},
+               "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": 8 * wl.B,
+                       "d2h_bytes_per_step": 160 + len(my_sources) * TOPK * 12, "ms_per_step": e2e_ms_per_step, "steps": Ke,
+                       "readback": f"step record + top-{TOPK} (id, estimate) of each of the rank's {len(my_sources)} sources"},
                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                "p50_ms": float(np.median(step_ms)), "p95_ms": float(np.percentile(step_ms, 95)),
-               "ppr_only": {"value": units / (float(ppr_ms.sum()) * 1e-3), "unit": UNIT, "p50_ms": float(np.median(ppr_ms)),
+               "edge_updates_per_sec": float(wl.B * K / (dev_total_ms * 1e-3)),
+               "source_edge_updates_per_sec": float(S_total * wl.B * K / (dev_total_ms * 1e-3)),
+               "ppr_only": {"ms_per_step": float(ppr_ms.mean()), "p50_ms": float(np.median(ppr_ms)),
                             "note": "the reference's own clock: repair + push, window update excluded (gpu/PPRGPU.cuh:128-163)"},
-               "per_step": {"iterations": float(f("iterations").mean()), "frontier_pops": float(F.mean()),
-                            "traversed_edges": float(T.mean()), "ms_window": float(f("ms_window").mean()),
-                            "ms_repair": float(f("ms_repair").mean()), "ms_push": float(f("ms_push").mean())},
-               "wall_ms_per_step_incl_flush": t_wall * 1e3 / K, "estimates_gathered": gathered_rows}
+               "per_step": {"iterations": float(f("iterations").mean()), "dense_sweeps": float(f("dense_sweeps").mean()),
+                            "frontier_pops": float(F.mean()), "traversed_edges": float(T.mean()), "scatter_edges": float(Ts.mean()),
+                            "ms_window": float(f("ms_window").mean()), "ms_repair": float(f("ms_repair").mean()),
+                            "ms_push": float(f("ms_push").mean()), "relocations": float(f("relocations").mean()),
+                            "pool_used": int(rows[-1].pool_used)},
+               "initial_solve_ms": float(s0.ms_push), "wall_ms_per_step": t_wall * 1e3 / K, "estimates_gathered": gathered_rows}
         print(json.dumps(out), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _cuda_ok():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
 
 
 if __name__ == "__main__":

@@ -9,17 +9,19 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 OPTIMIZED, FAST_FRONTIER, EAGER, VANILLA = 0, 1, 2, 3
-ENGINE_AUTO, ENGINE_STEPWISE, ENGINE_ASYNC, ENGINE_LEVELSYNC = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_STEPWISE, ENGINE_LEVELSYNC = 0, 1, 3
 
 # every symbol include/dppr.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = [
     "dppr_version", "dppr_last_error", "dppr_create", "dppr_destroy", "dppr_init_window",
-    "dppr_init_window_pairs", "dppr_init_window_device_pairs", "dppr_generate_rmat_device", "dppr_solve_initial", "dppr_apply_batch", "dppr_apply_batch_pairs",
+    "dppr_init_window_pairs", "dppr_init_window_device_pairs", "dppr_generate_rmat_device", "dppr_generate_stream_device",
+    "dppr_generate_stream_host", "dppr_rank_by_degree", "dppr_solve_initial", "dppr_apply_batch", "dppr_apply_batch_pairs",
     "dppr_apply_batch_device_pairs", "dppr_refresh", "dppr_slide", "dppr_slide_pairs",
     "dppr_slide_device_pairs", "dppr_sync", "dppr_get_batch_stats", "dppr_batches_done",
     "dppr_get_estimates", "dppr_get_residuals", "dppr_copy_estimates_device", "dppr_export_window_csr", "dppr_export_window_out_csr",
     "dppr_window_csr_entries", "dppr_set_state", "dppr_repair_only", "dppr_test_sort_pairs",
     "dppr_test_exclusive_scan", "dppr_test_relabel_slot", "dppr_debug_iterlog", "dppr_debug_ctalog", "dppr_kernel_launches",
+    "dppr_wait_event", "dppr_get_topk", "dppr_validate", "dppr_check_window_device",
 ]
 
 
@@ -29,6 +31,16 @@ class DpprError(RuntimeError):
         self.code = code
 
 
+class Tuning(C.Structure):
+    _fields_ = [
+        ("relabel", C.c_int32), ("relabel_blocks", C.c_int32), ("relabel_both", C.c_int32), ("ctas_per_sm", C.c_int32),
+        ("tile_cap", C.c_int32), ("max_iters", C.c_int32), ("dense", C.c_int32), ("pull_group", C.c_int32),
+        ("pull_warp_min", C.c_int32), ("pull_cta_min", C.c_int32), ("pull_big_min", C.c_int32), ("window_path", C.c_int32),
+        ("iterlog", C.c_int32), ("probe_iter", C.c_int32), ("dense_div", C.c_double), ("dense_min_edges", C.c_double),
+        ("carry_gamma", C.c_double), ("carry_scale", C.c_double), ("reserved", C.c_int32 * 8),
+    ]
+
+
 class Config(C.Structure):
     _fields_ = [
         ("vertex_count", C.c_int32), ("directed", C.c_int32), ("window_edges", C.c_int64),
@@ -36,7 +48,7 @@ class Config(C.Structure):
         ("variant", C.c_int32), ("device", C.c_int32), ("n_sources", C.c_int32),
         ("sources", C.POINTER(C.c_int32)), ("engine_mode", C.c_int32), ("record_timing", C.c_int32),
         ("pool_factor", C.c_double), ("frontier_capacity", C.c_int64), ("hub_degree", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("reserved0", C.c_int32), ("tuning", Tuning),
     ]
 
 
@@ -47,6 +59,8 @@ class BatchStats(C.Structure):
         ("traversed_edges", C.c_int64), ("hub_pops", C.c_int64), ("relocations", C.c_int64),
         ("pool_used", C.c_int64), ("ms_upload", C.c_float), ("ms_window", C.c_float),
         ("ms_repair", C.c_float), ("ms_push", C.c_float), ("error_flags", C.c_int32), ("dense_sweeps", C.c_int32),
+        ("scatter_edges", C.c_int64), ("dense_slots", C.c_int64), ("dense_pairs", C.c_int64), ("dense_units", C.c_int64), ("dense_pops", C.c_int64),
+        ("pool_leaked", C.c_int64),
     ]
 
     def as_dict(self):
@@ -78,6 +92,9 @@ def load_library():
     L.dppr_init_window_pairs.argtypes = [vp, i32p, C.c_int64]
     L.dppr_init_window_device_pairs.argtypes = [vp, vp, C.c_int64]
     L.dppr_generate_rmat_device.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_uint64, vp]
+    L.dppr_generate_stream_device.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_uint64, vp]
+    L.dppr_generate_stream_host.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_uint64, vp, C.c_int32]
+    L.dppr_rank_by_degree.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int64, C.c_int32, i32p, i32p, i32p]
     L.dppr_solve_initial.argtypes = [vp]
     for name in ("dppr_apply_batch", "dppr_slide"):
         getattr(L, name).argtypes = [vp, i32p, i32p, C.c_int64]
@@ -87,6 +104,10 @@ def load_library():
         getattr(L, name).argtypes = [vp, vp, C.c_int64]
     L.dppr_refresh.argtypes = [vp]
     L.dppr_sync.argtypes = [vp]
+    L.dppr_wait_event.argtypes = [vp, vp]
+    L.dppr_get_topk.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, i32p, f64p]
+    L.dppr_validate.argtypes = [vp, C.c_int32, f64p, f64p]
+    L.dppr_check_window_device.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64)]
     L.dppr_get_batch_stats.argtypes = [vp, C.c_int64, C.POINTER(BatchStats)]
     L.dppr_batches_done.argtypes = [vp]; L.dppr_batches_done.restype = C.c_int64
     L.dppr_get_estimates.argtypes = [vp, C.c_int32, f64p]
@@ -117,7 +138,7 @@ class DynamicPPR:
 
     def __init__(self, vertex_count, directed, window_edges, max_batch_edges, sources, epsilon=1e-9, variant=0,
                  device=0, engine_mode=ENGINE_AUTO, record_timing=True, alpha=0.15, pool_factor=0.0,
-                 frontier_capacity=0, hub_degree=0):
+                 frontier_capacity=0, hub_degree=0, tuning=None):
         self.L = load_library()
         self.V = int(vertex_count)
         self._sources = np.ascontiguousarray(np.atleast_1d(sources), dtype=np.int32)
@@ -126,6 +147,10 @@ class DynamicPPR:
                      device=int(device), n_sources=len(self._sources), sources=_i32(self._sources),
                      engine_mode=int(engine_mode), record_timing=int(bool(record_timing)), pool_factor=pool_factor,
                      frontier_capacity=int(frontier_capacity), hub_degree=int(hub_degree), reserved0=0)
+        for name, value in (tuning or {}).items():  # dppr_tuning fields by name (include/dppr.h); 0 = default
+            if name not in dict(Tuning._fields_):
+                raise ValueError(f"unknown tuning field {name!r}")
+            setattr(cfg.tuning, name, value)
         self.h = C.c_void_p()
         rc = self.L.dppr_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:
@@ -208,6 +233,28 @@ class DynamicPPR:
     def sync(self):
         self._check(self.L.dppr_sync(self.h))
 
+    def wait_event(self, cuda_event):
+        self._check(self.L.dppr_wait_event(self.h, C.c_void_p(int(cuda_event))))
+
+    def topk(self, k, first_source=0, n_sources=None):
+        """(ids[n, k], values[n, k]): the k largest estimates per source, selected on the device"""
+        n = self.n_sources - first_source if n_sources is None else int(n_sources)
+        ids = np.empty((n, k), np.int32); vals = np.empty((n, k), np.float64)
+        self._check(self.L.dppr_get_topk(self.h, first_source, n, k, _i32(ids), vals.ctypes.data_as(C.POINTER(C.c_double))))
+        return ids, vals
+
+    def validate(self, source_index=0, invariant=True):
+        """(max |r|, largest push-invariant defect) computed on the device (the reference's -DVALIDATE checks)"""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        self._check(self.L.dppr_validate(self.h, source_index, C.byref(a), C.byref(b) if invariant else None))
+        return a.value, b.value
+
+    def check_window_device(self, device_ptr, n):
+        """entries of the canonical window graph that differ from the one built from these W device-resident edges"""
+        bad = C.c_int64(-1)
+        self._check(self.L.dppr_check_window_device(self.h, C.c_void_p(int(device_ptr)), int(n), C.byref(bad)))
+        return int(bad.value)
+
     def stats(self, batch_index=-1) -> BatchStats:
         s = BatchStats()
         self._check(self.L.dppr_get_batch_stats(self.h, batch_index, C.byref(s)))
@@ -277,6 +324,49 @@ def generate_rmat_device(V, M, seed, device_ptr, device=0):
     rc = L.dppr_generate_rmat_device(device, int(V), int(M), int(seed), C.c_void_p(int(device_ptr)))
     if rc != 0:
         raise DpprError(rc, L.dppr_last_error(None).decode())
+
+
+STREAM_RMAT, STREAM_POWERLAW = 0, 1
+
+
+def generate_stream_device(kind, V, first_edge, n_edges, seed, device_ptr, device=0):
+    """fill n_edges int32 pairs of DEVICE memory with edges [first_edge, first_edge + n_edges) of a seeded stream"""
+    L = load_library()
+    rc = L.dppr_generate_stream_device(device, int(kind), int(V), int(first_edge), int(n_edges), int(seed), C.c_void_p(int(device_ptr)))
+    if rc != 0:
+        raise DpprError(rc, L.dppr_last_error(None).decode())
+
+
+def generate_stream_host(kind, V, first_edge, n_edges, seed, out=None, threads=0):
+    """the host twin of generate_stream_device (bit-identical; no GPU needed).  Returns an (n_edges, 2) int32 array;
+    `out` may be a pre-allocated C-contiguous array or memmap of that shape."""
+    L = load_library()
+    if out is None:
+        out = np.empty((int(n_edges), 2), np.int32)
+    assert out.dtype == np.int32 and out.shape == (int(n_edges), 2) and out.flags["C_CONTIGUOUS"]
+    rc = L.dppr_generate_stream_host(int(kind), int(V), int(first_edge), int(n_edges), int(seed),
+                                     C.c_void_p(out.ctypes.data), int(threads) if threads else (os.cpu_count() or 1))
+    if rc != 0:
+        raise DpprError(rc, L.dppr_last_error(None).decode())
+    return out
+
+
+def rank_by_degree(V, directed, pairs=None, n_edges=None, device_ptr=None, by_out_degree=True, device=0, want_degrees=False):
+    """exact degree ranking of a whole stream on the device (include/dppr.h, dppr_rank_by_degree)"""
+    L = load_library()
+    order = np.empty(int(V), np.int32)
+    od = np.empty(int(V), np.int32) if want_degrees else None
+    idg = np.empty(int(V), np.int32) if want_degrees else None
+    if device_ptr is not None:
+        ptr, n, on_dev = C.c_void_p(int(device_ptr)), int(n_edges), 1
+    else:
+        pairs = np.ascontiguousarray(pairs, np.int32)
+        ptr, n, on_dev = C.c_void_p(pairs.ctypes.data), len(pairs), 0
+    rc = L.dppr_rank_by_degree(device, int(V), int(bool(directed)), int(bool(by_out_degree)), ptr, n, on_dev, _i32(order),
+                               _i32(od) if od is not None else None, _i32(idg) if idg is not None else None)
+    if rc != 0:
+        raise DpprError(rc, L.dppr_last_error(None).decode())
+    return (order, od, idg) if want_degrees else order
 
 
 def kernel_launches() -> int:

@@ -5,6 +5,7 @@
 #include <vector>
 // unity build: the kernels live in headers, so the whole library is one translation unit
 #include "engine.cu"
+#include "streamgen.cuh"
 
 struct dppr_engine {
     dppr::Engine *impl = nullptr;
@@ -37,6 +38,28 @@ int guarded(dppr_engine *e, F &&f) {
         return DPPR_E_CAPACITY;
     } catch (const std::exception &x) {
         e->err = x.what();
+        return DPPR_E_CUDA;
+    }
+}
+template <typename F>
+int guarded_free(F &&f) {
+    using namespace dppr;
+    try {
+        f();
+        return DPPR_OK;
+    } catch (const InvalidArgument &x) {
+        g_create_error = x.what();
+        return DPPR_E_INVALID;
+    } catch (const CapacityError &x) {
+        g_create_error = x.what();
+        return DPPR_E_CAPACITY;
+    } catch (const std::bad_alloc &) {
+        g_create_error = "host allocation failed";
+        return DPPR_E_CAPACITY;
+    } catch (const std::exception &x) {
+        g_create_error = x.what();
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return DPPR_E_NODEVICE;
         return DPPR_E_CUDA;
     }
 }
@@ -120,6 +143,18 @@ int dppr_slide_device_pairs(dppr_engine *e, const int32_t *dpairs, int64_t B) {
 int dppr_sync(dppr_engine *e) {
     return guarded(e, [&](dppr::Engine &g) { g.sync(); });
 }
+int dppr_wait_event(dppr_engine *e, void *cuda_event) {
+    return guarded(e, [&](dppr::Engine &g) { g.wait_event(cuda_event); });
+}
+int dppr_get_topk(dppr_engine *e, int32_t first, int32_t n, int32_t k, int32_t *ids, double *values) {
+    return guarded(e, [&](dppr::Engine &g) { g.topk(first, n, k, ids, values); });
+}
+int dppr_validate(dppr_engine *e, int32_t s, double *max_abs_residual, double *max_invariant_defect) {
+    return guarded(e, [&](dppr::Engine &g) { g.validate(s, max_abs_residual, max_invariant_defect); });
+}
+int dppr_check_window_device(dppr_engine *e, const int32_t *dpairs, int64_t n, int64_t *mismatches) {
+    return guarded(e, [&](dppr::Engine &g) { g.check_window_device(dpairs, n, mismatches); });
+}
 int dppr_get_batch_stats(dppr_engine *e, int64_t k, dppr_batch_stats *out) {
     return guarded(e, [&](dppr::Engine &g) { g.get_stats(k, out); });
 }
@@ -162,57 +197,83 @@ int dppr_debug_ctalog(dppr_engine *e, unsigned long long *out, int32_t cap_rows,
 
 unsigned long long dppr_kernel_launches(void) { return dppr::launch_counter(); }
 
-// ---- synthetic stream generator on the device -------------------------------------------
-namespace {
-__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {  // splitmix64 finaliser
-    x += 0x9e3779b97f4a7c15ull;
-    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
-    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
-    return x ^ (x >> 31);
-}
-// R-MAT (a, b, c, d) with `scale` levels, counter-based: edge i is a pure function of (seed, i)
-__global__ void rmat_kernel(int2 *out, long long M, int V, int scale, unsigned long long seed, unsigned ta, unsigned tab,
-                            unsigned tabc, unsigned long long mult, unsigned long long add) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
-        unsigned long long src = 0, dst = 0;
-        unsigned long long h = 0;
-        for (int l = 0; l < scale; ++l) {
-            if ((l & 1) == 0) h = mix64(seed ^ ((unsigned long long)i * 0x100000001b3ull + (unsigned long long)(l >> 1)));
-            const unsigned r = (l & 1) ? (unsigned)(h >> 32) : (unsigned)h;  // 32 uniform bits per level
-            const unsigned sbit = r >= tab, dbit = (r >= ta && r < tab) || r >= tabc;
-            src = (src << 1) | sbit;
-            dst = (dst << 1) | dbit;
-        }
-        src %= (unsigned long long)V; dst %= (unsigned long long)V;
-        out[i] = make_int2((int)((src * mult + add) % (unsigned long long)V), (int)((dst * mult + add) % (unsigned long long)V));
-    }
-}
-}  // namespace
-
-int dppr_generate_rmat_device(int32_t device, int32_t V, int64_t M, uint64_t seed, int32_t *device_pairs) {
+// ---- synthetic streams: device generator + bit-identical host twin (csrc/streamgen.cuh) --------
+int dppr_generate_stream_device(int32_t device, int32_t kind, int32_t V, int64_t first_edge, int64_t n_edges, uint64_t seed,
+                                int32_t *device_pairs) {
     using namespace dppr;
-    try {
-        if (V <= 1 || M < 0 || !device_pairs) throw InvalidArgument("bad arguments");
+    return guarded_free([&]() {
+        if (first_edge < 0 || n_edges < 0 || (!device_pairs && n_edges)) throw InvalidArgument("bad arguments");
+        const GenParams g = make_gen_params(kind, V, seed);
         DPPR_CUDA(cudaSetDevice(device));
-        int scale = 1;
-        while ((1ll << scale) < (long long)V) ++scale;
-        unsigned long long mult = 2654435761ull % (unsigned long long)V;
-        auto gcd = [](unsigned long long a, unsigned long long b) { while (b) { unsigned long long t = a % b; a = b; b = t; } return a; };
-        while (gcd(mult, (unsigned long long)V) != 1) ++mult;
-        const double a = 0.57, b = 0.19, c = 0.19;
-        const unsigned ta = (unsigned)(a * 4294967296.0), tab = (unsigned)((a + b) * 4294967296.0),
-                       tabc = (unsigned)((a + b + c) * 4294967296.0);
-        rmat_kernel<<<148 * 8, 256>>>((int2 *)device_pairs, M, V, scale, seed, ta, tab, tabc, mult, mix64(seed) % (unsigned long long)V);
+        if (n_edges) {
+            gen_stream_kernel<<<148 * 8, kThreads>>>((int2 *)device_pairs, g, first_edge, n_edges); ++launch_counter();
+        }
         DPPR_CUDA(cudaGetLastError());
         DPPR_CUDA(cudaDeviceSynchronize());
-        return DPPR_OK;
-    } catch (const InvalidArgument &x) {
-        g_create_error = x.what();
-        return DPPR_E_INVALID;
-    } catch (const std::exception &x) {
-        g_create_error = x.what();
-        return DPPR_E_CUDA;
-    }
+    });
+}
+
+int dppr_generate_stream_host(int32_t kind, int32_t V, int64_t first_edge, int64_t n_edges, uint64_t seed, int32_t *pairs,
+                              int32_t threads) {
+    using namespace dppr;
+    return guarded_free([&]() {
+        if (first_edge < 0 || n_edges < 0 || (!pairs && n_edges)) throw InvalidArgument("bad arguments");
+        const GenParams g = make_gen_params(kind, V, seed);
+        gen_stream_host(g, first_edge, n_edges, (int2 *)pairs, threads);
+    });
+}
+
+int dppr_generate_rmat_device(int32_t device, int32_t V, int64_t M, uint64_t seed, int32_t *device_pairs) {
+    return dppr_generate_stream_device(device, DPPR_STREAM_RMAT, V, 0, M, seed, device_pairs);
+}
+
+// ---- source selection: exact degree ranking of a whole stream on the device -----------------
+int dppr_rank_by_degree(int32_t device, int32_t V, int32_t directed, int32_t by_out_degree, const int32_t *pairs, int64_t n,
+                        int32_t pairs_on_device, int32_t *order, int32_t *out_degree, int32_t *in_degree) {
+    using namespace dppr;
+    return guarded_free([&]() {
+        if (V <= 0 || n < 0 || (!pairs && n) || n > 0x7fffffffll) throw InvalidArgument("bad arguments");
+        DPPR_CUDA(cudaSetDevice(device));
+        DevBuf<unsigned> od, id;
+        DevBuf<int> err;
+        od.alloc((size_t)V); id.alloc((size_t)V); err.alloc(1);
+        DPPR_CUDA(cudaMemset(od.ptr, 0, od.bytes()));
+        DPPR_CUDA(cudaMemset(id.ptr, 0, id.bytes()));
+        DPPR_CUDA(cudaMemset(err.ptr, 0, sizeof(int)));
+        if (pairs_on_device) {
+            if (n) { degree_hist_kernel<<<148 * 8, kThreads>>>((const int2 *)pairs, n, V, directed, od.ptr, id.ptr, err.ptr); ++launch_counter(); }
+        } else {
+            const int64_t chunk = 1ll << 25;  // 256 MiB of pairs per upload
+            DevBuf<int2> buf;
+            buf.alloc((size_t)std::min<int64_t>(std::max<int64_t>(n, 1), chunk));
+            for (int64_t lo = 0; lo < n; lo += chunk) {
+                const int64_t m = std::min(chunk, n - lo);
+                DPPR_CUDA(cudaMemcpy(buf.ptr, pairs + 2 * lo, sizeof(int2) * (size_t)m, cudaMemcpyHostToDevice));
+                degree_hist_kernel<<<148 * 8, kThreads>>>(buf.ptr, m, V, directed, od.ptr, id.ptr, err.ptr); ++launch_counter();
+            }
+        }
+        DPPR_CUDA(cudaGetLastError());
+        int herr = 0;
+        DPPR_CUDA(cudaMemcpy(&herr, err.ptr, sizeof(int), cudaMemcpyDeviceToHost));
+        if (herr) throw InvalidArgument("edge endpoint outside [0, vertex_count) (workload/Graph.h:101-102 asserts the same)");
+        if (order) {
+            // descending degree, ties by ascending id (the reference's std::sort leaves tie order unspecified)
+            DevBuf<uint32_t> k[2], v[2], scratch;
+            for (int i = 0; i < 2; ++i) { k[i].alloc((size_t)V); v[i].alloc((size_t)V); }
+            scratch.alloc(sort_scratch_elems(V));
+            const int dbits = bits_for((uint64_t)std::max<int64_t>(2 * n, 1));
+            const uint32_t degmax = dbits >= 32 ? 0xffffffffu : (uint32_t)((1ull << dbits) - 1);
+            const int grid = std::max(1, std::min(div_up(V, kThreads), 148 * 16));
+            relabel_keys<<<grid, kThreads>>>(by_out_degree ? od.ptr : id.ptr, degmax, k[0].ptr, v[0].ptr, V); ++launch_counter();
+            const int res = sort_pairs(k[0].ptr, v[0].ptr, k[1].ptr, v[1].ptr, V, std::min(dbits, 32), scratch.ptr, 0);
+            DPPR_CUDA(cudaGetLastError());
+            DPPR_CUDA(cudaDeviceSynchronize());
+            DPPR_CUDA(cudaMemcpy(order, v[res].ptr, sizeof(int32_t) * (size_t)V, cudaMemcpyDeviceToHost));
+        }
+        DPPR_CUDA(cudaDeviceSynchronize());
+        if (out_degree) DPPR_CUDA(cudaMemcpy(out_degree, od.ptr, sizeof(int32_t) * (size_t)V, cudaMemcpyDeviceToHost));
+        if (in_degree) DPPR_CUDA(cudaMemcpy(in_degree, id.ptr, sizeof(int32_t) * (size_t)V, cudaMemcpyDeviceToHost));
+    });
 }
 
 // ---- primitive test hooks ------------------------------------------------------------------------

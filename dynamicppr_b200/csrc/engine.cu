@@ -11,21 +11,67 @@ namespace {
 
 __global__ void gather_record(BatchRecord *rec, const PushCtrl *ctrl, const uint32_t *counters,
                               const unsigned long long *pool_top) {
-    rec->ctrl = *ctrl;
-    rec->nseg_in = counters[0];
-    rec->nseg_out = counters[1];
-    rec->njobs = counters[2] + counters[5];
-    rec->pad = 0;
-    rec->pool_top = *pool_top;
+    BatchRecord r{};
+    r.iters = ctrl->iters; r.pops = ctrl->pops; r.edges = ctrl->edges; r.gath = ctrl->gath;
+    r.hubs = ctrl->hubs; r.carried = ctrl->carried; r.dpops = ctrl->dpops;
+    r.walk_slots = ctrl->walk_slots; r.walk_pairs = ctrl->walk_pairs; r.units = ctrl->units;
+    r.pool_top = pool_top[0]; r.pool_leaked = pool_top[1];
+    r.sweeps = ctrl->sweeps;
+    r.nseg_in = counters[0];
+    r.nseg_out = counters[1];
+    r.njobs = counters[2] + counters[5];
+    r.errflags = ctrl->errflags;
+    r.arrived = 1;
+    *rec = r;
 }
 
 __global__ void fold_window_errors(PushCtrl *ctrl, int *win_err) {
     if (*win_err) atomicOr(&ctrl->errflags, *win_err);
 }
 
+// caller ids -> internal ids for the source list (one launch instead of one blocking 4-byte copy per source)
+__global__ void translate_sources(const int32_t *__restrict__ src_in, const uint32_t *__restrict__ perm, int32_t *__restrict__ src_out, int S) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) src_out[i] = (int32_t)perm[src_in[i]];
+}
+
+// the environment is a development aid for A/B runs: consulted ONCE, in the constructor, and only for knobs the
+// caller left at 0 in dppr_config::tuning
 int env_int(const char *name, int dflt) {
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
+}
+double env_real(const char *name, double dflt) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atof(v) : dflt;
+}
+int pick_int(int32_t field, const char *env, int dflt) { return field != 0 ? (int)field : env_int(env, dflt); }
+double pick_real(double field, const char *env, double dflt) { return field != 0.0 ? field : env_real(env, dflt); }
+
+Tuning resolve_tuning(const dppr_tuning &t) {
+    Tuning r;
+    r.relabel = t.relabel != 0 ? t.relabel > 0 : env_int("DPPR_RELABEL", 1) != 0;
+    r.relabel_blocks = std::max(1, pick_int(t.relabel_blocks, "DPPR_RELABEL_BLOCKS", 1024));
+    r.relabel_both = pick_int(t.relabel_both, "DPPR_RELABEL_BOTH", 0) > 0;
+    r.ctas_per_sm = std::max(1, pick_int(t.ctas_per_sm, "DPPR_CTAS_PER_SM", 4));
+    r.tile_cap = std::min(std::max(pick_int(t.tile_cap, "DPPR_TILE_CAP", 128), 8), kTileMax);
+    r.max_iters = std::max(1, pick_int(t.max_iters, "DPPR_MAX_ITERS", 400000));
+    r.dense = pick_int(t.dense, "DPPR_DENSE", 0);
+    r.dense_div = pick_real(t.dense_div, "DPPR_DENSE_DIV", 4.0);
+    r.dense_min_edges = pick_real(t.dense_min_edges, "DPPR_DENSE_MIN_EDGES", 2.0e7);
+    if (std::getenv("DPPR_DENSE_DIV") && t.dense_div == 0.0 && std::atof(std::getenv("DPPR_DENSE_DIV")) <= 0.0) r.dense = -1;  // round-1 spelling of "off"
+    if (std::getenv("DPPR_DENSE_MIN_EDGES") && t.dense_min_edges == 0.0 && std::atof(std::getenv("DPPR_DENSE_MIN_EDGES")) <= 0.0) r.dense_min_edges = 0.0;
+    r.pull_group = std::min(std::max(pick_int(t.pull_group, "DPPR_PULL_GROUP", 8), 1), 8);
+    r.pull_warp_min = std::max(1, pick_int(t.pull_warp_min, "DPPR_PULL_WARP_MIN", 32));
+    r.pull_cta_min = std::max(r.pull_warp_min, pick_int(t.pull_cta_min, "DPPR_PULL_CTA_MIN", 1024));
+    r.pull_big_min = std::max(r.pull_cta_min, pick_int(t.pull_big_min, "DPPR_PULL_BIG_MIN", 65536));
+    r.carry_gamma = pick_real(t.carry_gamma, "DPPR_CARRY_GAMMA", 1.0);
+    r.carry_scale = pick_real(t.carry_scale, "DPPR_CARRY_SCALE", 0.01);
+    r.window_path = pick_int(t.window_path, "DPPR_WINDOW_PATH", 0);
+    if (t.window_path == 0 && !env_int("DPPR_COOP_WINDOW", 1)) r.window_path = 1;   // round-1 spellings
+    else if (t.window_path == 0 && !env_int("DPPR_FUSED_WINDOW", 1)) r.window_path = 2;
+    r.iterlog = pick_int(t.iterlog, "DPPR_ITERLOG", 0) > 0;
+    r.probe_iter = pick_int(t.probe_iter, "DPPR_PROBE_ITER", 10);
+    return r;
 }
 
 template <int VAR, bool DENSE = false>
@@ -49,18 +95,14 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     if (cfg.variant < DPPR_OPTIMIZED || cfg.variant > DPPR_VANILLA)
         throw InvalidArgument("variant must be 0..3 (Meta.h:11-17)");
     if (cfg.n_sources < 1 || cfg.sources == nullptr) throw InvalidArgument("at least one source vertex is required");
-    if (cfg.engine_mode < DPPR_ENGINE_AUTO || cfg.engine_mode > DPPR_ENGINE_LEVELSYNC)
-        throw InvalidArgument("engine_mode must be one of DPPR_ENGINE_{AUTO,STEPWISE,ASYNC,LEVELSYNC}");
-    if (cfg.engine_mode == DPPR_ENGINE_ASYNC && cfg.variant != DPPR_OPTIMIZED)
-        throw InvalidArgument("DPPR_ENGINE_ASYNC implements variant 0 (optimized) only");
-    mode_ = cfg.engine_mode;
-    if (mode_ == DPPR_ENGINE_AUTO) mode_ = DPPR_ENGINE_LEVELSYNC;  // measured fastest for every variant so far (profiles/README.md)
-    if (const char *force = std::getenv("DPPR_FORCE_ENGINE")) {  // tuning / A-B runs without touching the caller
+    if (cfg.engine_mode != DPPR_ENGINE_AUTO && cfg.engine_mode != DPPR_ENGINE_STEPWISE && cfg.engine_mode != DPPR_ENGINE_LEVELSYNC)
+        throw InvalidArgument("engine_mode must be one of DPPR_ENGINE_{AUTO,STEPWISE,LEVELSYNC}");
+    mode_ = cfg.engine_mode == DPPR_ENGINE_AUTO ? DPPR_ENGINE_LEVELSYNC : cfg.engine_mode;
+    if (const char *force = std::getenv("DPPR_FORCE_ENGINE")) {  // A/B runs without touching the caller (read once, here)
         const int f = std::atoi(force);
-        if (f >= DPPR_ENGINE_STEPWISE && f <= DPPR_ENGINE_LEVELSYNC && !(f == DPPR_ENGINE_ASYNC && cfg.variant != 0)) mode_ = f;
+        if (f == DPPR_ENGINE_STEPWISE || f == DPPR_ENGINE_LEVELSYNC) mode_ = f;
     }
-    if (mode_ == DPPR_ENGINE_ASYNC && cfg.n_sources > kMaxAsyncSources)
-        throw InvalidArgument("DPPR_ENGINE_ASYNC supports at most 4096 sources per engine");
+    tn_ = resolve_tuning(cfg.tuning);
     if (cfg_.alpha <= 0.0) cfg_.alpha = 0.15;
     if (cfg_.alpha >= 1.0) throw InvalidArgument("alpha must be in (0, 1)");
     if (cfg_.epsilon <= 0.0) cfg_.epsilon = 1e-9;
@@ -81,32 +123,24 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     if ((uint64_t)V_ >= (1ull << 31)) throw InvalidArgument("vertex ids must fit in 31 bits");
     if (Ew_ >= (int64_t)0xffffffffll) throw InvalidArgument("window too large for 32-bit CSR offsets");
     key_bits_ = bits_for((uint64_t)(V_ - 1));
-    relabel_ = env_int("DPPR_RELABEL", 1) != 0;
     {
         // dense iterations (pull.cuh): variant 0 of the level-synchronous engine; an iteration runs as a gather sweep
-        // once it is expected to traverse at least (E_w + 2 V) x sources / DPPR_DENSE_DIV in-edges.  0 disables.
-        const char *dd = std::getenv("DPPR_DENSE_DIV");
-        dense_div_ = dd ? std::atof(dd) : 4.0;
+        // once it is expected to traverse at least (E_w + 2 V) x sources / dense_div in-edges.
         // Small windows stay with the scatter-only kernel: their iterations are bound by the chain of dependent round
         // trips, which a sweep does not shorten (BASELINE configs[1]: 43 vs 18 us), and the kernel that can switch
         // carries more loop state, which costs its scatter iterations +9..+24 % when they are latency-bound (LJ/4,
         // youtube) and nothing when they are bandwidth-bound (Twitter-shaped).
-        const char *me = std::getenv("DPPR_DENSE_MIN_EDGES");
-        const double min_edges = me ? std::atof(me) : 2.0e7;
-        dense_ = dense_div_ > 0.0 && cfg.variant == DPPR_OPTIMIZED && mode_ == DPPR_ENGINE_LEVELSYNC &&
-                 (double)cfg.window_edges * (cfg.directed ? 1 : 2) * cfg.n_sources >= min_edges;
+        const bool can = cfg.variant == DPPR_OPTIMIZED && mode_ == DPPR_ENGINE_LEVELSYNC && tn_.dense_div > 0.0;
+        dense_ = can && tn_.dense >= 0 &&
+                 (tn_.dense > 0 || (double)cfg.window_edges * (cfg.directed ? 1 : 2) * cfg.n_sources >= tn_.dense_min_edges);
         outlists_ = dense_ && D_ == 1;
         // several sources: rows of x hold 4-source chunks, G = 2^gshift adjacent lanes take G chunks of a vertex (pull.cuh)
         pull_gshift_ = 0;
         if (S_ > 1) {
             const int chunks = (S_ + 3) / 4;
-            const int gmax = std::min(std::max(env_int("DPPR_PULL_GROUP", 8), 1), 8);
-            while ((2 << pull_gshift_) <= std::min(chunks, gmax)) ++pull_gshift_;
+            while ((2 << pull_gshift_) <= std::min(chunks, tn_.pull_group)) ++pull_gshift_;
         }
         Sp_ = S_ == 1 ? 1 : (S_ + (4 << pull_gshift_) - 1) / (4 << pull_gshift_) * (4 << pull_gshift_);
-        pull_warp_min_ = std::max(1, env_int("DPPR_PULL_WARP_MIN", 32));
-        pull_cta_min_ = std::max(pull_warp_min_, env_int("DPPR_PULL_CTA_MIN", 1024));
-        pull_big_min_ = std::max(pull_cta_min_, env_int("DPPR_PULL_BIG_MIN", 65536));
     }
 
     int ndev = 0;
@@ -125,20 +159,12 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     // cooperative grid per variant: every CTA must be co-resident for the software grid barrier
     void *kern[4] = {dense_ ? persistent_kernel<0, true>() : persistent_kernel<0>(), persistent_kernel<1>(),
                      persistent_kernel<2>(), persistent_kernel<3>()};
-    const int want_per_sm = env_int("DPPR_CTAS_PER_SM", 4);
     for (int v = 0; v < 4; ++v) {
         int per_sm = 0;
         DPPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern[v], kThreads, 0));
         if (per_sm < 1) throw CudaFailure("push kernel does not fit on an SM");
-        coop_grid_[v] = std::min(per_sm, std::max(want_per_sm, 1)) * sm_count_;
+        coop_grid_[v] = std::min(per_sm, tn_.ctas_per_sm) * sm_count_;
     }
-    {
-        int per_sm = 0;
-        DPPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (void *)push_async, kThreads, 0));
-        if (per_sm < 1) throw CudaFailure("async push kernel does not fit on an SM");
-        async_grid_ = std::min(per_sm, std::max(env_int("DPPR_ASYNC_CTAS_PER_SM", 4), 1)) * sm_count_;
-    }
-
     {
         int per_sm = 0;
         DPPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (void *)win_update_coop, kThreads, 0));
@@ -153,7 +179,27 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     if (pc > 4294967295.0) pc = 4294967295.0;
     pool_cap_ = (unsigned long long)pc;
     pool_.alloc((size_t)pool_cap_);
-    pool_top_.alloc(1);
+    pool_top_.alloc(2);
+    DPPR_CUDA(cudaMemsetAsync(pool_top_.ptr, 0, pool_top_.bytes(), st_));
+    {
+        // free stacks: class c (ranges of 2^c slots) gets room for min(pool >> c, max(65536, V >> (c - 2))) ranges -- the
+        // number of rings of a size class falls geometrically on a power-law graph; 8 bytes per vertex in total
+        std::vector<uint32_t> off(33, 0);
+        for (int c = 0; c < 32; ++c) {
+            unsigned long long room = 0;
+            if (c >= 2) room = std::min<unsigned long long>(pool_cap_ >> c, std::max<unsigned long long>(65536ull, (unsigned long long)V_ >> (c - 2)));
+            off[c + 1] = off[c] + (uint32_t)room;
+        }
+        fcount_.alloc(32);
+        foff_.alloc(33);
+        fstack_.alloc(std::max<size_t>(off[32], 1));
+        npend_.alloc(2);
+        for (int i = 0; i < 2; ++i) pend_[i].alloc((size_t)Nb_ * (outlists_ ? 2 : 1));
+        DPPR_CUDA(cudaMemsetAsync(fcount_.ptr, 0, fcount_.bytes(), st_));
+        DPPR_CUDA(cudaMemsetAsync(npend_.ptr, 0, npend_.bytes(), st_));
+        DPPR_CUDA(cudaMemcpyAsync(foff_.ptr, off.data(), sizeof(uint32_t) * 33, cudaMemcpyHostToDevice, st_));
+        DPPR_CUDA(cudaStreamSynchronize(st_));  // `off` is a local
+    }
     // batch scratch
     arriving_.alloc((size_t)std::max<int64_t>(Bmax_, 1));
     for (int i = 0; i < 2; ++i) {
@@ -185,7 +231,7 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
             DPPR_CUDA(cudaMemsetAsync(x_[i].ptr, 0, x_[i].bytes(), st_));  // the padding columns stay zero for good
         }
         tile_list_.alloc((size_t)div_up(V_, kThreads >> pull_gshift_) * (Sp_ == 1 ? 1 : (Sp_ / 4) >> pull_gshift_));
-        bigcap_ = (uint32_t)std::min<int64_t>((Ew_ / pull_big_min_ + 64) * (Sp_ == 1 ? 1 : Sp_ / 4), 1 << 24);
+        bigcap_ = (uint32_t)std::min<int64_t>((Ew_ / tn_.pull_big_min + 64) * (Sp_ == 1 ? 1 : Sp_ / 4), 1 << 24);
         big_.alloc(bigcap_);
         bigacc_.alloc((size_t)bigcap_ * 4 << pull_gshift_);
         DPPR_CUDA(cudaMemsetAsync(bigacc_.ptr, 0, bigacc_.bytes(), st_));
@@ -205,35 +251,21 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     qc = std::max<int64_t>(qc, 1024);
     if (qc > 0xfffffff0ll) qc = 0xfffffff0ll;
     qcap_ = (uint32_t)qc;
-    hcap_ = (uint32_t)std::min<int64_t>(qc, std::max<int64_t>(1024, (Ew_ / cfg_.hub_degree + 1) * S_));
-    if (use_async()) {
-        // ticket rings (one per phase): at most one outstanding entry per (source, vertex) plus hub chunks
-        // ... plus the tickets idle warps hold ahead of `tail`: two live tickets must never share a slot
-        const unsigned long long worst = 2ull * (unsigned long long)V_ * S_ + (unsigned long long)Ew_ / kHubChunk * S_ +
-                                         64ull * (unsigned long long)async_grid_ * kWarps;
-        unsigned long long want = cfg_.frontier_capacity > 0 ? (unsigned long long)cfg_.frontier_capacity
-                                                             : std::min<unsigned long long>(worst, 1ull << 30);
-        ring_cap_ = 1ull << 16;
-        while (ring_cap_ < want) ring_cap_ <<= 1;
-        guard_slots_ = ring_cap_ < worst ? 1 : 0;
-        for (int i = 0; i < 2; ++i) {
-            q_[i].alloc(ring_cap_);
-            qr_[i].alloc(ring_cap_);
-            DPPR_CUDA(cudaMemsetAsync(q_[i].ptr, 0xff, q_[i].bytes(), st_));  // every slot EMPTY
-        }
-        async_ctr_.alloc(10 * 16);
-        DPPR_CUDA(cudaMemsetAsync(async_ctr_.ptr, 0, async_ctr_.bytes(), st_));
-    } else {
-        for (int i = 0; i < 2; ++i) {
-            q_[i].alloc(qcap_);
-            if (cfg_.variant != DPPR_OPTIMIZED) qr_[i].alloc(qcap_);
-            hub_[i].alloc(hcap_);
-        }
+    // hub list: one entry per popped (source, vertex) of in-degree >= hub_degree.  With the switching kernel the large
+    // frontiers run as sweeps (hubs still pending at the switch are un-popped), so a quarter of the worst case is plenty;
+    // overflow is detected (DPPR_DEVERR_HUBQ), never silent
+    int64_t hc = std::max<int64_t>(1024, (Ew_ / cfg_.hub_degree + 1) * S_);
+    if (dense_ && S_ > 8) hc = std::max<int64_t>(1 << 20, hc / 4);
+    hcap_ = (uint32_t)std::min<int64_t>(qc, hc);
+    for (int i = 0; i < 2; ++i) {
+        q_[i].alloc(qcap_);
+        if (cfg_.variant != DPPR_OPTIMIZED) qr_[i].alloc(qcap_);
+        hub_[i].alloc(hcap_);
     }
     ctrl_.alloc(1);
     DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, sizeof(PushCtrl), st_));
     dev_record_.alloc(1);
-    if (env_int("DPPR_ITERLOG", 0)) {
+    if (tn_.iterlog) {
         iterlog_.alloc(kIterLogCap);
         ctalog_.alloc((size_t)8 * 148 * 16);
         DPPR_CUDA(cudaMemsetAsync(ctalog_.ptr, 0, ctalog_.bytes(), st_));
@@ -248,19 +280,62 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
 Engine::~Engine() {
     cudaSetDevice(dev_);
     if (st_) cudaStreamSynchronize(st_);
-    for (auto &m : meta_)
-        for (auto &ev : m.ev)
+    for (auto &es : events_)
+        for (auto &ev : es.ev)
             if (ev) cudaEventDestroy(ev);
     for (auto &ev : hstage_free_)
         if (ev) cudaEventDestroy(ev);
     if (st_) cudaStreamDestroy(st_);
 }
 
+PoolFree Engine::pool_free_view(int parity) {
+    return PoolFree{fcount_.ptr, foff_.ptr, fstack_.ptr, pend_[parity].ptr, npend_.ptr + parity, pool_top_.ptr + 1};
+}
+
+// ---- per-batch bookkeeping ------------------------------------------------------------------------------------
+// Phase timings use a fixed ring of event sets (no event is created in the streaming loop after the first
+// kEventSlots batches); the set of batch k - kEventSlots is resolved into plain floats before batch k reuses it.
+void Engine::resolve_events(EventSet &es) {
+    if (es.batch < 0 || es.batch >= (int64_t)meta_.size()) return;
+    BatchMeta &m = meta_[(size_t)es.batch];
+    if (m.resolved) return;
+    for (int i = 4; i >= 0; --i)
+        if (es.used[i]) { DPPR_CUDA(cudaEventSynchronize(es.ev[i])); break; }
+    auto ms = [&](int a, int b) -> float {
+        if (!es.used[a] || !es.used[b]) return 0.f;
+        float t = 0.f;
+        return cudaEventElapsedTime(&t, es.ev[a], es.ev[b]) == cudaSuccess ? t : 0.f;
+    };
+    m.ms[0] = m.has_upload ? ms(0, 1) : 0.f;
+    m.ms[1] = m.has_window ? ms(1, 2) : 0.f;
+    m.ms[2] = m.has_window ? ms(2, 3) : 0.f;
+    m.ms[3] = ms(3, 4);
+    m.resolved = true;
+}
+
+void Engine::begin_batch(int64_t edges, int64_t entries) {
+    check_health();
+    meta_.emplace_back();
+    BatchMeta &m = meta_.back();
+    m.edges = edges;
+    m.entries = entries;
+    const int64_t k = (int64_t)meta_.size() - 1;
+    BatchRecord *rec = record_slot((size_t)k);
+    std::memset(rec, 0, sizeof(BatchRecord));
+    if (cfg_.record_timing) {
+        EventSet &es = events_[k % kEventSlots];
+        resolve_events(es);
+        es.batch = k;
+        for (bool &u : es.used) u = false;
+    }
+}
+
 void Engine::record(int which) {
     if (!cfg_.record_timing) return;
-    BatchMeta &m = cur();
-    if (!m.ev[which]) DPPR_CUDA(cudaEventCreate(&m.ev[which]));
-    DPPR_CUDA(cudaEventRecord(m.ev[which], st_));
+    EventSet &es = events_[((int64_t)meta_.size() - 1) % kEventSlots];
+    if (!es.ev[which]) DPPR_CUDA(cudaEventCreate(&es.ev[which]));
+    DPPR_CUDA(cudaEventRecord(es.ev[which], st_));
+    es.used[which] = true;
 }
 
 BatchRecord *Engine::record_slot(size_t k) {
@@ -280,9 +355,54 @@ void Engine::finish_record() {
                               cudaMemcpyDeviceToHost, st_));
 }
 
+// Device-side failures (pool / queue exhaustion, watchdog, FIFO underflow, bad ids) travel to the host in the batch
+// record.  Every record that has landed is inspected here -- at the start of each batch, and by the synchronising calls --
+// and the first flagged one fails the engine for good: the window graph is no longer the reference's (round-1 verdict:
+// inserts were dropped while the call still returned DPPR_OK).
+void Engine::check_health() {
+    if (failed_code_ == 0) {
+        const size_t n = batch_pending_ ? meta_.size() - 1 : meta_.size();
+        while (health_checked_ < n) {
+            const BatchRecord *rec = record_slot(health_checked_);
+            if (!*(volatile const int *)&rec->arrived) break;  // (copy not landed yet: look again at the next call)
+            const int f = rec->errflags;
+            if (f) {
+                std::string what;
+                if (f & kErrPool) what += " adjacency pool exhausted (raise dppr_config.pool_factor);";
+                if (f & kErrQueue) what += " frontier queue overflow (raise dppr_config.frontier_capacity);";
+                if (f & kErrHubQ) what += " hub list overflow (raise dppr_config.frontier_capacity / hub_degree);";
+                if (f & kErrWatchdog) what += " push watchdog fired (max_iters / grid barrier);";
+                if (f & kErrUnderflow) what += " expiry of an edge the window does not hold;";
+                if (f & kErrBadId) what += " edge endpoint outside [0, vertex_count);";
+                failed_msg_ = "batch " + std::to_string(health_checked_) + " left device error flags " + std::to_string(f) + ":" + what +
+                              " the engine state is no longer valid";
+                failed_code_ = (f & (kErrPool | kErrQueue | kErrHubQ)) ? DPPR_E_CAPACITY : (f & kErrBadId) ? DPPR_E_INVALID : DPPR_E_STATE;
+                break;
+            }
+            ++health_checked_;
+        }
+    }
+    if (failed_code_ == DPPR_E_CAPACITY) throw CapacityError(failed_msg_);
+    if (failed_code_ == DPPR_E_INVALID) throw InvalidArgument(failed_msg_);
+    if (failed_code_) throw StateError(failed_msg_);
+}
+
 // ---------------------------------------------------------------------------------------------
 // initial window
 // ---------------------------------------------------------------------------------------------
+// host input is checked before it is staged: a bad id fails the call, nothing reaches the device
+// (the reference asserts the same while reading the file, GraphVec.h:55-56)
+void Engine::validate_host_ids(const int32_t *pairs, const int32_t *e1, const int32_t *e2, int64_t n) const {
+    const uint32_t V = (uint32_t)V_;
+    uint32_t worst = 0;
+    if (pairs) {
+        for (int64_t i = 0; i < 2 * n; ++i) worst = std::max(worst, (uint32_t)pairs[i]);
+    } else {
+        for (int64_t i = 0; i < n; ++i) worst = std::max(worst, std::max((uint32_t)e1[i], (uint32_t)e2[i]));
+    }
+    if (worst >= V) throw InvalidArgument("edge endpoint outside [0, vertex_count) (GraphVec.h:55-56 asserts the same)");
+}
+
 int2 *Engine::stage_pairs(const int32_t *pairs, const int32_t *e1, const int32_t *e2, int64_t n) {
     const int slot = hstage_next_;
     hstage_next_ = (hstage_next_ + 1) % kStageSlots;
@@ -312,6 +432,7 @@ void Engine::init_window_soa(const int32_t *e1, const int32_t *e2, int64_t n) {
 void Engine::init_window_pairs(const int32_t *pairs, int64_t n) {
     if (!pairs) throw InvalidArgument("null edge array");
     if (n != W_) throw InvalidArgument("init_window needs exactly window_edges edges (InitWindowStream asserts the same)");
+    validate_host_ids(pairs, nullptr, nullptr, n);
     DPPR_CUDA(cudaSetDevice(dev_));
     DPPR_CUDA(cudaMemcpyAsync(log_.ptr, pairs, sizeof(int2) * (size_t)W_, cudaMemcpyHostToDevice, st_));
     build_initial_window();
@@ -339,9 +460,12 @@ void Engine::build_initial_window() {
     DPPR_CUDA(cudaMemsetAsync(indeg.ptr, 0, indeg.bytes(), st_));
     DPPR_CUDA(cudaMemsetAsync(outdeg_.ptr, 0, outdeg_.bytes(), st_));
     DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, counters_.bytes(), st_));
+    DPPR_CUDA(cudaMemsetAsync(fcount_.ptr, 0, fcount_.bytes(), st_));
+    DPPR_CUDA(cudaMemsetAsync(npend_.ptr, 0, npend_.bytes(), st_));
+    DPPR_CUDA(cudaMemsetAsync(pool_top_.ptr, 0, pool_top_.bytes(), st_));
     int *werr = (int *)(counters_.ptr + 3);
 
-    if (relabel_) {
+    if (tn_.relabel) {
         // internal order = descending out-degree of the initial window (window.cuh, "internal vertex order")
         DevBuf<uint32_t> deg, rk[2], rv[2], rscratch;
         deg.alloc((size_t)V_);
@@ -351,21 +475,21 @@ void Engine::build_initial_window() {
         DPPR_CUDA(cudaMemsetAsync(deg.ptr, 0, deg.bytes(), st_));
         // key: out-degree (how often the scatter form hits r[w]); with dense iterations on a directed graph out- plus
         // in-degree (the gather form reads x[u] once per IN-edge of u): DPPR_RELABEL_BOTH=1; no difference measured on R-MAT
-        const int both = env_int("DPPR_RELABEL_BOTH", 0);
+        const int both = tn_.relabel_both ? 1 : 0;
         relabel_degrees<<<grid_for(W_), kThreads, 0, st_>>>(log_.ptr, W_, D_ == 1, V_, deg.ptr, werr, both); ++launch_counter();
         const int dbits = bits_for((uint64_t)2 * Ew_);
         const uint32_t degmax = (uint32_t)((1ull << dbits) - 1);
         relabel_keys<<<grid_for(V_), kThreads, 0, st_>>>(deg.ptr, degmax, rk[0].ptr, rv[0].ptr, V_); ++launch_counter();
         const int rr = sort_pairs(rk[0].ptr, rv[0].ptr, rk[1].ptr, rv[1].ptr, V_, dbits, rscratch.ptr, st_);
-        const uint32_t P = (uint32_t)std::max(1, std::min(env_int("DPPR_RELABEL_BLOCKS", 1024), V_));
+        const uint32_t P = (uint32_t)std::max(1, std::min(tn_.relabel_blocks, V_));
         relabel_assign<<<grid_for(V_), kThreads, 0, st_>>>(rv[rr].ptr, perm_.ptr, inv_.ptr, V_, P); ++launch_counter();
         relabel_log<<<grid_for(W_), kThreads, 0, st_>>>(log_.ptr, W_, perm_.ptr, V_); ++launch_counter();
         // the sources, in internal ids
-        std::vector<uint32_t> hp((size_t)S_);
-        DPPR_CUDA(cudaStreamSynchronize(st_));
-        for (int s = 0; s < S_; ++s)
-            DPPR_CUDA(cudaMemcpy(&hp[s], perm_.ptr + sources_[s], sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        DPPR_CUDA(cudaMemcpy(src_.ptr, hp.data(), sizeof(uint32_t) * (size_t)S_, cudaMemcpyHostToDevice));
+        DevBuf<int32_t> src_in;
+        src_in.alloc((size_t)S_);
+        DPPR_CUDA(cudaMemcpyAsync(src_in.ptr, sources_.data(), sizeof(int32_t) * (size_t)S_, cudaMemcpyHostToDevice, st_));
+        translate_sources<<<std::max(1, std::min(div_up(S_, 256), 64)), 256, 0, st_>>>(src_in.ptr, perm_.ptr, src_.ptr, S_); ++launch_counter();
+        DPPR_CUDA(cudaStreamSynchronize(st_));  // (src_in and the sort buffers above are locals)
     }
 
     // in-lists, then (directed graphs with dense iterations enabled) out-lists behind them in the same pool
@@ -394,6 +518,7 @@ void Engine::build_initial_window() {
     }
     DPPR_CUDA(cudaMemcpyAsync(pool_top_.ptr, &top, sizeof(top), cudaMemcpyHostToDevice, st_));
     DPPR_CUDA(cudaStreamSynchronize(st_));
+    win_batches_ = 0;
     window_ready_ = true;
     solved_ = false;
     batch_pending_ = false;
@@ -415,15 +540,12 @@ void Engine::launch_push(bool init_mode) {
     a.eps = cfg_.epsilon; a.alpha = cfg_.alpha;
     a.hub_degree = cfg_.hub_degree;
     a.init_mode = init_mode ? 1 : 0;
-    a.max_iters = env_int("DPPR_MAX_ITERS", 400000);
-    {
-        const char *g = std::getenv("DPPR_CARRY_GAMMA"), *sc = std::getenv("DPPR_CARRY_SCALE");
-        // off by default: on the L2-resident BASELINE configs the extra (latency-bound) iterations cost more than
-        // the saved traversals (profiles/README.md); DPPR_CARRY_GAMMA=0.7 enables the threshold schedule
-        a.carry_gamma = g ? std::atof(g) : 1.0;
-        a.carry_scale = sc ? std::atof(sc) : 0.01;
-    }
-    a.tile_cap = std::min(std::max(env_int("DPPR_TILE_CAP", 128), 8), kTileMax);
+    a.max_iters = tn_.max_iters;
+    // threshold schedule: off by default (gamma 1.0) -- on the L2-resident BASELINE configs the extra, latency-bound
+    // iterations cost more than the saved traversals (profiles/README.md); tuning.carry_gamma = 0.7 enables it
+    a.carry_gamma = tn_.carry_gamma;
+    a.carry_scale = tn_.carry_scale;
+    a.tile_cap = tn_.tile_cap;
     a.V = V_;
     a.avg_indeg = (float)((double)Ew_ / (double)V_);
     a.vmeta_out = outlists_ ? vmeta_out_.ptr : vmeta_.ptr;
@@ -433,9 +555,9 @@ void Engine::launch_push(bool init_mode) {
     // iteration pays one random atomic per traversed in-edge.  Measured ratio ~ DPPR_DENSE_DIV (3): Twitter-shaped
     // 3.3 ms per sweep vs 17 edges/ns scattered; Orkut/4 97 us vs 40 edges/ns.
     a.dense_enter_edges = ~0ull;
-    if (dense_) a.dense_enter_edges = (unsigned long long)std::max(1.0, ((double)Ew_ + 2.0 * (double)V_) * (double)S_ / dense_div_);
+    if (dense_) a.dense_enter_edges = (unsigned long long)std::max(1.0, ((double)Ew_ + 2.0 * (double)V_) * (double)S_ / tn_.dense_div);
     a.dense_exit_edges = a.dense_enter_edges / 2;
-    a.pull_warp_min = pull_warp_min_; a.pull_cta_min = pull_cta_min_; a.pull_big_min = pull_big_min_;
+    a.pull_warp_min = tn_.pull_warp_min; a.pull_cta_min = tn_.pull_cta_min; a.pull_big_min = tn_.pull_big_min;
     a.big = big_.ptr; a.bigcap = bigcap_; a.bigacc = bigacc_.ptr; a.tile_list = tile_list_.ptr;
     {
         const uint64_t ntiles = (uint64_t)div_up(V_, kThreads >> pull_gshift_) * (Sp_ == 1 ? 1 : (Sp_ / 4) >> pull_gshift_);
@@ -448,13 +570,9 @@ void Engine::launch_push(bool init_mode) {
     a.iterlog = iterlog_.ptr;
     a.iterlog_cap = iterlog_.ptr ? kIterLogCap : 0;
     a.ctalog = ctalog_.ptr;
-    a.probe_iter = env_int("DPPR_PROBE_ITER", 10);
+    a.probe_iter = tn_.probe_iter;
     if (mode_ == DPPR_ENGINE_STEPWISE) {
         launch_push_stepwise(a);
-        return;
-    }
-    if (mode_ == DPPR_ENGINE_ASYNC) {
-        launch_push_async(a);
         return;
     }
     void *params[] = {(void *)&a};
@@ -466,37 +584,6 @@ void Engine::launch_push(bool init_mode) {
         default: kern = persistent_kernel<3>(); break;
     }
     DPPR_CUDA(cudaLaunchCooperativeKernel(kern, dim3(coop_grid_[cfg_.variant]), dim3(kThreads), params, 0, st_));
-    ++launch_counter();
-}
-
-void Engine::launch_push_async(PushArgs &b) {
-    AsyncArgs a{};
-    a.base = b;
-    for (int i = 0; i < 2; ++i) {
-        a.q[i].slots = q_[i].ptr;
-        a.q[i].slot_ru = qr_[i].ptr;
-        a.q[i].mask = ring_cap_ - 1;
-        a.q[i].tail = async_ctr_.ptr + (3 * i + 0) * 16;
-        a.q[i].head = async_ctr_.ptr + (3 * i + 1) * 16;
-        a.q[i].done = async_ctr_.ptr + (3 * i + 2) * 16;
-        a.q[i].fence = async_ctr_.ptr + (6 + 2 * i) * 16;
-        a.q[i].theta0 = async_ctr_.ptr + (7 + 2 * i) * 16;
-    }
-    a.guard_slots = 0;
-    a.dbg = iterlog_.ptr ? (unsigned long long *)ctalog_.ptr : nullptr;
-    if (a.dbg) {
-        DPPR_CUDA(cudaMemsetAsync(a.dbg, 0, 128, st_));
-        DPPR_CUDA(cudaMemsetAsync(a.dbg + 10, 0xff, 8, st_));
-        DPPR_CUDA(cudaMemsetAsync(a.dbg + 12, 0xff, 8, st_));
-    }
-    {
-        const char *g = std::getenv("DPPR_CARRY_GAMMA"), *sc = std::getenv("DPPR_CARRY_SCALE");
-        a.carry_gamma = g ? std::atof(g) : 0.7;
-        a.carry_scale = sc ? std::atof(sc) : 0.01;
-    }
-    DPPR_CUDA(cudaMemsetAsync(async_ctr_.ptr, 0, async_ctr_.bytes(), st_));
-    void *params[] = {(void *)&a};
-    DPPR_CUDA(cudaLaunchCooperativeKernel((void *)push_async, dim3(async_grid_), dim3(kThreads), params, 0, st_));
     ++launch_counter();
 }
 
@@ -556,11 +643,12 @@ void Engine::launch_push_stepwise(PushArgs &a) {
 void Engine::solve_initial() {
     if (!window_ready_) throw StateError("dppr_solve_initial before dppr_init_window");
     DPPR_CUDA(cudaSetDevice(dev_));
-    for (auto &m : meta_)
-        for (auto &ev : m.ev)
-            if (ev) cudaEventDestroy(ev);
+    DPPR_CUDA(cudaStreamSynchronize(st_));
     meta_.clear();
-    meta_.emplace_back();
+    for (auto &es : events_) es.batch = -1;
+    health_checked_ = 0;
+    batch_pending_ = false;
+    begin_batch(0, 0);
     record(0);
     state_init<<<grid_for(Vp_ * S_), kThreads, 0, st_>>>(p_.ptr, r_.ptr, status_.ptr, Vp_, S_, src_.ptr); ++launch_counter();
     DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, sizeof(PushCtrl), st_));
@@ -582,8 +670,9 @@ void Engine::apply_batch_host_pairs(const int32_t *pairs, int64_t B) {
     if (B <= 0 || B > Bmax_) throw InvalidArgument("batch size must be in [1, max_batch_edges]");
     if (!solved_) throw StateError("dppr_apply_batch before dppr_solve_initial");
     if (batch_pending_) throw StateError("dppr_apply_batch twice without dppr_refresh");
+    validate_host_ids(pairs, nullptr, nullptr, B);
     DPPR_CUDA(cudaSetDevice(dev_));
-    meta_.emplace_back();
+    begin_batch(B, 2 * D_ * B);
     record(0);
     int2 *d = stage_pairs(pairs, nullptr, nullptr, B);
     cur().has_upload = true;
@@ -596,8 +685,9 @@ void Engine::apply_batch_host_soa(const int32_t *e1, const int32_t *e2, int64_t 
     if (B <= 0 || B > Bmax_) throw InvalidArgument("batch size must be in [1, max_batch_edges]");
     if (!solved_) throw StateError("dppr_apply_batch before dppr_solve_initial");
     if (batch_pending_) throw StateError("dppr_apply_batch twice without dppr_refresh");
+    validate_host_ids(nullptr, e1, e2, B);
     DPPR_CUDA(cudaSetDevice(dev_));
-    meta_.emplace_back();
+    begin_batch(B, 2 * D_ * B);
     record(0);
     int2 *d = stage_pairs(nullptr, e1, e2, B);
     cur().has_upload = true;
@@ -611,7 +701,7 @@ void Engine::apply_batch_device_pairs(const int32_t *dpairs, int64_t B) {
     if (!solved_) throw StateError("dppr_apply_batch before dppr_solve_initial");
     if (batch_pending_) throw StateError("dppr_apply_batch twice without dppr_refresh");
     DPPR_CUDA(cudaSetDevice(dev_));
-    meta_.emplace_back();
+    begin_batch(B, 2 * D_ * B);
     record(0);
     record(1);
     apply_batch_common((const int2 *)dpairs, B);
@@ -620,14 +710,20 @@ void Engine::apply_batch_device_pairs(const int32_t *dpairs, int64_t B) {
 void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
     BatchMeta &m = cur();
     const int64_t nA = 2 * D_ * B;  // entries in a group (directed: 2B per group, undirected: 4B in the one group)
-    m.edges = B;
-    m.entries = nA;
     m.has_window = true;
     int *werr = (int *)(counters_.ptr + 3);
     DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, sizeof(uint32_t) * 3, st_));
-    WindowView wv{V_, vmeta_.ptr, pool_.ptr, outdeg_.ptr, pool_top_.ptr, pool_cap_, werr};
-    WindowView wvo{V_, vmeta_out_.ptr, pool_.ptr, outdeg_.ptr, pool_top_.ptr, pool_cap_, werr};  // vmeta null = no out-lists
-    if (nA <= kFusedMaxEntries && env_int("DPPR_FUSED_WINDOW", 1)) {
+    // ranges released by this batch are collected in pend_[parity]; the first stage of this update hands the previous
+    // batch's list (other parity) to the free stacks (window.cuh, PoolFree)
+    const int parity = (int)(win_batches_ & 1);
+    ++win_batches_;
+    DPPR_CUDA(cudaMemsetAsync(npend_.ptr + parity, 0, sizeof(uint32_t), st_));
+    const PoolFree fr = pool_free_view(parity);
+    const uint2 *pend_prev = pend_[parity ^ 1].ptr;
+    const uint32_t *npend_prev = npend_.ptr + (parity ^ 1);
+    WindowView wv{V_, vmeta_.ptr, pool_.ptr, outdeg_.ptr, pool_top_.ptr, pool_cap_, werr, fr};
+    WindowView wvo{V_, vmeta_out_.ptr, pool_.ptr, outdeg_.ptr, pool_top_.ptr, pool_cap_, werr, fr};  // vmeta null = no out-lists
+    if (nA <= kFusedMaxEntries && tn_.window_path == 0) {
         // small batch: the whole update in one single-CTA launch (window_fused.cuh)
         FusedArgs f{};
         f.log = log_.ptr; f.W = W_; f.log_start = log_start_; f.arriving = arriving; f.B = B;
@@ -636,6 +732,7 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
         f.segA = segA_; f.segB = segB_; f.w = wv;
         f.ins_pos = ins_pos_.ptr; f.jobs = jobs_.ptr; f.njobs = counters_.ptr + 2; f.seg_d0 = seg_d0_.ptr; f.perm = perm_.ptr;
         f.wo = wvo; f.ins_posB = ins_posB_.ptr; f.jobsB = jobsB_.ptr; f.njobsB = counters_.ptr + 5;
+        f.pend_prev = pend_prev; f.npend_prev = npend_prev;
         win_fused_small<<<1, kFusedThreads, 0, st_>>>(f); ++launch_counter();
         const int res = ((key_bits_ + 7) / 8) & 1;  // same parity rule as sort_pairs
         sa_key_ = akey_[res].ptr; sa_val_ = aval_[res].ptr;
@@ -647,7 +744,7 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
         batch_pending_ = true;
         return;
     }
-    if (nA <= kCoopMaxEntries && coop_win_grid_ > 0 && env_int("DPPR_COOP_WINDOW", 1)) {
+    if (nA <= kCoopMaxEntries && coop_win_grid_ > 0 && tn_.window_path != 1) {
         // mid-size batch: the same stages inside one cooperative launch (window_coop.cuh)
         CoopArgs c{};
         c.log = log_.ptr; c.W = W_; c.log_start = log_start_; c.arriving = arriving; c.B = B;
@@ -658,6 +755,7 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
         c.ins_pos = ins_pos_.ptr; c.jobs = jobs_.ptr; c.njobs = counters_.ptr + 2; c.seg_d0 = seg_d0_.ptr; c.perm = perm_.ptr;
         c.wo = wvo; c.ins_posB = ins_posB_.ptr; c.jobsB = jobsB_.ptr; c.njobsB = counters_.ptr + 5;
         c.bar = counters_.ptr + 4;
+        c.pend_prev = pend_prev; c.npend_prev = npend_prev;
         DPPR_CUDA(cudaMemsetAsync(counters_.ptr + 4, 0, sizeof(uint32_t), st_));
         const int tiles = div_up(nA, kSortTile);
         const int grid = std::max(1, std::min(coop_win_grid_, std::max(tiles, div_up(nA, kThreads))));
@@ -674,7 +772,8 @@ void Engine::apply_batch_common(const int2 *arriving, int64_t B) {
         return;
     }
     win_batch_entries<<<grid_for(B), kThreads, 0, st_>>>(log_.ptr, W_, log_start_, arriving, B, D_ == 1, V_,
-                                                        akey_[0].ptr, aval_[0].ptr, bkey_[0].ptr, bval_[0].ptr, werr, perm_.ptr); ++launch_counter();
+                                                        akey_[0].ptr, aval_[0].ptr, bkey_[0].ptr, bval_[0].ptr, werr, perm_.ptr,
+                                                        pend_prev, npend_prev, fr); ++launch_counter();
     log_start_ = (log_start_ + B) % W_;
     uint32_t *scan_scratch = sort_scratch_.ptr + sort_scratch_elems(Nb_);
 
@@ -733,40 +832,53 @@ void Engine::refresh(bool repair_only) {
 void Engine::sync() {
     DPPR_CUDA(cudaSetDevice(dev_));
     DPPR_CUDA(cudaStreamSynchronize(st_));
+    check_health();
 }
 
+void Engine::wait_event(void *cuda_event) {
+    if (!cuda_event) throw InvalidArgument("null event");
+    DPPR_CUDA(cudaSetDevice(dev_));
+    DPPR_CUDA(cudaStreamWaitEvent(st_, (cudaEvent_t)cuda_event, 0));
+}
+
+// (does not fail on a flagged engine: the caller reads the flags here)
 void Engine::get_stats(int64_t batch_index, dppr_batch_stats *out) {
     if (!out) throw InvalidArgument("null stats pointer");
     if (meta_.empty()) throw StateError("no batch has been processed yet");
     if (batch_index < 0) batch_index = (int64_t)meta_.size() - 1;
     if (batch_index >= (int64_t)meta_.size()) throw InvalidArgument("batch index out of range");
     if (batch_index == (int64_t)meta_.size() - 1 && batch_pending_) throw StateError("batch applied but not refreshed yet");
-    sync();
-    const BatchMeta &m = meta_[(size_t)batch_index];
+    DPPR_CUDA(cudaSetDevice(dev_));
+    DPPR_CUDA(cudaStreamSynchronize(st_));
+    BatchMeta &m = meta_[(size_t)batch_index];
     const BatchRecord *rec = record_slot((size_t)batch_index);
+    if (cfg_.record_timing && !m.resolved) {
+        EventSet &es = events_[batch_index % kEventSlots];
+        if (es.batch == batch_index) resolve_events(es);
+    }
     std::memset(out, 0, sizeof(*out));
     out->batch_index = batch_index;
     out->edges = m.edges;
     out->batch_entries = m.entries;  // N_b = 2*D*B
     out->touched_vertices = (D_ == 1) ? rec->nseg_out : rec->nseg_in;
-    out->iterations = (int64_t)rec->ctrl.iters;
-    out->frontier_pops = (int64_t)rec->ctrl.pops - (int64_t)rec->ctrl.carried;  // carried items are not pushed
-    out->traversed_edges = (int64_t)rec->ctrl.edges;
-    out->hub_pops = (int64_t)rec->ctrl.hubs;
+    out->iterations = (int64_t)rec->iters;
+    out->frontier_pops = (int64_t)rec->pops - (int64_t)rec->carried;  // carried items are not pushed
+    out->traversed_edges = (int64_t)(rec->edges + rec->gath);
+    out->scatter_edges = (int64_t)rec->edges;
+    out->dense_slots = (int64_t)rec->walk_slots;
+    out->dense_pairs = (int64_t)rec->walk_pairs;
+    out->dense_units = (int64_t)rec->units;
+    out->dense_pops = (int64_t)rec->dpops;
+    out->hub_pops = (int64_t)rec->hubs;
     out->relocations = rec->njobs;
     out->pool_used = (int64_t)rec->pool_top;
-    out->error_flags = rec->ctrl.errflags;
-    out->dense_sweeps = (int32_t)rec->ctrl.sweeps;
-    auto ms = [&](int a, int b) -> float {
-        if (!cfg_.record_timing || !m.ev[a] || !m.ev[b]) return 0.f;
-        float t = 0.f;
-        if (cudaEventElapsedTime(&t, m.ev[a], m.ev[b]) != cudaSuccess) return 0.f;
-        return t;
-    };
-    out->ms_upload = m.has_upload ? ms(0, 1) : 0.f;
-    out->ms_window = m.has_window ? ms(1, 2) : 0.f;
-    out->ms_repair = m.has_window ? ms(2, 3) : 0.f;
-    out->ms_push = ms(3, 4);
+    out->pool_leaked = (int64_t)rec->pool_leaked;
+    out->error_flags = rec->errflags;
+    out->dense_sweeps = (int32_t)rec->sweeps;
+    out->ms_upload = m.ms[0];
+    out->ms_window = m.ms[1];
+    out->ms_repair = m.ms[2];
+    out->ms_push = m.ms[3];
 }
 
 void Engine::get_vector(int which, int32_t s, double *out) {
@@ -815,7 +927,7 @@ int Engine::get_iterlog(uint32_t *out, int cap) {
     if (!iterlog_.ptr || meta_.empty()) return 0;
     sync();
     const BatchRecord *rec = record_slot(meta_.size() - 1);
-    int n = (int)std::min<unsigned long long>(rec->ctrl.iters, (unsigned long long)std::min(cap, kIterLogCap));
+    int n = (int)std::min<unsigned long long>(rec->iters, (unsigned long long)std::min(cap, kIterLogCap));
     if (n > 0) DPPR_CUDA(cudaMemcpy(out, iterlog_.ptr, sizeof(uint4) * (size_t)n, cudaMemcpyDeviceToHost));
     return n;
 }
@@ -824,41 +936,45 @@ int Engine::get_ctalog(unsigned long long *out, int cap_rows) {
     if (!ctalog_.ptr) return 0;
     sync();
     int rows = std::min(cap_rows, coop_grid_[cfg_.variant]);
-    if (use_async()) rows = 2;
     DPPR_CUDA(cudaMemcpy(out, ctalog_.ptr, sizeof(unsigned long long) * 8 * (size_t)rows, cudaMemcpyDeviceToHost));
     return rows;
 }
 
-// canonical CSR: rows ascending, duplicates kept.  Device sort, test/validation path.
-void Engine::export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_deg, bool out_lists) {
+// canonical CSR: rows ascending, duplicates kept.  Device sort, test / validation path.
+void Engine::export_sorted_device(SortedCsr &o, bool out_lists) {
     if (!window_ready_) throw StateError("dppr_export_window_csr before dppr_init_window");
     if (out_lists && !outlists_ && D_ == 1) throw StateError("this engine does not maintain out-lists (dense iterations are off)");
     const uint4 *vm = (out_lists && outlists_) ? vmeta_out_.ptr : vmeta_.ptr;
     sync();
-    DevBuf<uint32_t> len, rowptr, key[2], val[2], scratch, total;
-    len.alloc((size_t)V_); rowptr.alloc((size_t)V_ + 1);
-    for (int i = 0; i < 2; ++i) { key[i].alloc((size_t)Ew_); val[i].alloc((size_t)Ew_); }
-    scratch.alloc(std::max(sort_scratch_elems(Ew_), scan_scratch_elems(V_)));
-    total.alloc(1);
-    win_export_len<<<grid_for(V_), kThreads, 0, st_>>>(vm, len.ptr, V_, perm_.ptr); ++launch_counter();
-    exclusive_scan<uint32_t>(len.ptr, rowptr.ptr, V_, scratch.ptr, total.ptr, st_);
-    DPPR_CUDA(cudaMemcpyAsync(rowptr.ptr + V_, total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st_));
+    o.len.alloc((size_t)V_); o.rowptr.alloc((size_t)V_ + 1);
+    for (int i = 0; i < 2; ++i) { o.key[i].alloc((size_t)Ew_); o.val[i].alloc((size_t)Ew_); }
+    o.scratch.alloc(std::max(sort_scratch_elems(Ew_), scan_scratch_elems(V_)));
+    o.total.alloc(1);
+    win_export_len<<<grid_for(V_), kThreads, 0, st_>>>(vm, o.len.ptr, V_, perm_.ptr); ++launch_counter();
+    exclusive_scan<uint32_t>(o.len.ptr, o.rowptr.ptr, V_, o.scratch.ptr, o.total.ptr, st_);
+    DPPR_CUDA(cudaMemcpyAsync(o.rowptr.ptr + V_, o.total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st_));
     uint32_t htotal = 0;
-    DPPR_CUDA(cudaMemcpyAsync(&htotal, total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
+    DPPR_CUDA(cudaMemcpyAsync(&htotal, o.total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
     DPPR_CUDA(cudaStreamSynchronize(st_));
     if ((int64_t)htotal != Ew_)
         throw StateError("window graph holds " + std::to_string(htotal) + " entries, expected " + std::to_string(Ew_));
-    win_export_entries<<<grid_for((int64_t)V_ * 32), kThreads, 0, st_>>>(vm, pool_.ptr, rowptr.ptr, key[0].ptr,
-                                                                      val[0].ptr, V_, perm_.ptr, inv_.ptr); ++launch_counter();
+    win_export_entries<<<grid_for((int64_t)V_ * 32), kThreads, 0, st_>>>(vm, pool_.ptr, o.rowptr.ptr, o.key[0].ptr,
+                                                                      o.val[0].ptr, V_, perm_.ptr, inv_.ptr); ++launch_counter();
     // sort by (dst, src): LSD over the pair = stable sort by src, then stable sort by dst
-    int res = sort_pairs(val[0].ptr, key[0].ptr, val[1].ptr, key[1].ptr, Ew_, key_bits_, scratch.ptr, st_);
-    uint32_t *k0 = key[res].ptr, *v0 = val[res].ptr, *k1 = key[1 - res].ptr, *v1 = val[1 - res].ptr;
-    res = sort_pairs(k0, v0, k1, v1, Ew_, key_bits_, scratch.ptr, st_);
-    const uint32_t *cols = res ? v1 : v0;
+    int res = sort_pairs(o.val[0].ptr, o.key[0].ptr, o.val[1].ptr, o.key[1].ptr, Ew_, key_bits_, o.scratch.ptr, st_);
+    uint32_t *k0 = o.key[res].ptr, *v0 = o.val[res].ptr, *k1 = o.key[1 - res].ptr, *v1 = o.val[1 - res].ptr;
+    res = sort_pairs(k0, v0, k1, v1, Ew_, key_bits_, o.scratch.ptr, st_);
+    o.rows = res ? k1 : k0;
+    o.cols = res ? v1 : v0;
     DPPR_CUDA(cudaGetLastError());
     DPPR_CUDA(cudaStreamSynchronize(st_));
-    if (in_row_ptr) DPPR_CUDA(cudaMemcpy(in_row_ptr, rowptr.ptr, sizeof(int32_t) * ((size_t)V_ + 1), cudaMemcpyDeviceToHost));
-    if (in_col_ind && Ew_ > 0) DPPR_CUDA(cudaMemcpy(in_col_ind, cols, sizeof(int32_t) * (size_t)Ew_, cudaMemcpyDeviceToHost));
+}
+
+void Engine::export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_deg, bool out_lists) {
+    SortedCsr o;
+    export_sorted_device(o, out_lists);
+    if (in_row_ptr) DPPR_CUDA(cudaMemcpy(in_row_ptr, o.rowptr.ptr, sizeof(int32_t) * ((size_t)V_ + 1), cudaMemcpyDeviceToHost));
+    if (in_col_ind && Ew_ > 0) DPPR_CUDA(cudaMemcpy(in_col_ind, o.cols, sizeof(int32_t) * (size_t)Ew_, cudaMemcpyDeviceToHost));
     if (out_deg) {
         DevBuf<int32_t> od;
         od.alloc((size_t)V_);
@@ -866,6 +982,96 @@ void Engine::export_csr(int32_t *in_row_ptr, int32_t *in_col_ind, int32_t *out_d
         DPPR_CUDA(cudaStreamSynchronize(st_));
         DPPR_CUDA(cudaMemcpy(out_deg, od.ptr, sizeof(int32_t) * (size_t)V_, cudaMemcpyDeviceToHost));
     }
+}
+
+// the reference's ValidateGraph (gpu/PPRRevPushGPU.cuh:45-90) without the host: expected entries from the window's own
+// edges, same stable sorts, compared on the device
+void Engine::check_window_device(const int32_t *dpairs, int64_t n, int64_t *mismatches) {
+    if (!dpairs || !mismatches) throw InvalidArgument("null argument");
+    if (n != W_) throw InvalidArgument("dppr_check_window_device needs exactly window_edges pairs");
+    SortedCsr mine;
+    export_sorted_device(mine, false);
+    DevBuf<uint32_t> key[2], val[2], od_exp, scratch;
+    DevBuf<int32_t> od_mine;
+    DevBuf<unsigned long long> bad;
+    for (int i = 0; i < 2; ++i) { key[i].alloc((size_t)Ew_); val[i].alloc((size_t)Ew_); }
+    od_exp.alloc((size_t)V_); od_mine.alloc((size_t)V_);
+    scratch.alloc(sort_scratch_elems(Ew_));
+    bad.alloc(1);
+    DPPR_CUDA(cudaMemsetAsync(od_exp.ptr, 0, od_exp.bytes(), st_));
+    DPPR_CUDA(cudaMemsetAsync(bad.ptr, 0, sizeof(unsigned long long), st_));
+    val_window_entries<<<grid_for(W_), kThreads, 0, st_>>>((const int2 *)dpairs, W_, D_ == 1, V_, key[0].ptr, val[0].ptr, od_exp.ptr, bad.ptr); ++launch_counter();
+    int res = sort_pairs(val[0].ptr, key[0].ptr, val[1].ptr, key[1].ptr, Ew_, key_bits_, scratch.ptr, st_);
+    uint32_t *k0 = key[res].ptr, *v0 = val[res].ptr, *k1 = key[1 - res].ptr, *v1 = val[1 - res].ptr;
+    res = sort_pairs(k0, v0, k1, v1, Ew_, key_bits_, scratch.ptr, st_);
+    const uint32_t *rows = res ? k1 : k0, *cols = res ? v1 : v0;
+    val_count_diff<<<grid_for(Ew_), kThreads, 0, st_>>>(rows, mine.rows, cols, mine.cols, Ew_, bad.ptr); ++launch_counter();
+    gather_by_perm<int32_t><<<grid_for(V_), kThreads, 0, st_>>>(outdeg_.ptr, 1, perm_.ptr, od_mine.ptr, V_); ++launch_counter();
+    val_count_diff<<<grid_for(V_), kThreads, 0, st_>>>(od_exp.ptr, (const uint32_t *)od_mine.ptr, nullptr, nullptr, V_, bad.ptr); ++launch_counter();
+    DPPR_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    DPPR_CUDA(cudaMemcpyAsync(&h, bad.ptr, sizeof(h), cudaMemcpyDeviceToHost, st_));
+    DPPR_CUDA(cudaStreamSynchronize(st_));
+    *mismatches = (int64_t)h;
+}
+
+void Engine::validate(int32_t s, double *max_abs_residual, double *max_invariant_defect) {
+    if (s < 0 || s >= S_) throw InvalidArgument("source index out of range");
+    if (!solved_) throw StateError("no estimates before dppr_solve_initial");
+    sync();
+    DevBuf<unsigned long long> out;
+    out.alloc(2);
+    DPPR_CUDA(cudaMemsetAsync(out.ptr, 0, out.bytes(), st_));
+    const double *p = p_.ptr + (size_t)s * Vp_, *r = r_.ptr + (size_t)s * Vp_;
+    val_residual_max<<<grid_for(V_), kThreads, 0, st_>>>(r, V_, out.ptr); ++launch_counter();
+    DevBuf<double> acc;
+    if (max_invariant_defect) {
+        acc.alloc((size_t)V_);
+        DPPR_CUDA(cudaMemsetAsync(acc.ptr, 0, acc.bytes(), st_));
+        val_out_sums<<<grid_for((int64_t)V_ * 32), kThreads, 0, st_>>>(vmeta_.ptr, pool_.ptr, p, V_, acc.ptr); ++launch_counter();
+        int32_t hsrc = 0;
+        DPPR_CUDA(cudaMemcpyAsync(&hsrc, src_.ptr + s, sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
+        DPPR_CUDA(cudaStreamSynchronize(st_));
+        val_invariant<<<grid_for(V_), kThreads, 0, st_>>>(p, r, outdeg_.ptr, acc.ptr, V_, hsrc, cfg_.alpha, out.ptr + 1); ++launch_counter();
+    }
+    DPPR_CUDA(cudaGetLastError());
+    unsigned long long h[2] = {0, 0};
+    DPPR_CUDA(cudaMemcpyAsync(h, out.ptr, sizeof(h), cudaMemcpyDeviceToHost, st_));
+    DPPR_CUDA(cudaStreamSynchronize(st_));
+    double d[2];
+    std::memcpy(d, h, sizeof(d));
+    if (max_abs_residual) *max_abs_residual = d[0];
+    if (max_invariant_defect) *max_invariant_defect = d[1];
+}
+
+// the k largest estimates of sources [first, first + n): csrc/topk.cuh
+void Engine::topk(int32_t first, int32_t n, int32_t k, int32_t *ids, double *values) {
+    if (!ids || !values) throw InvalidArgument("null output pointer");
+    if (first < 0 || n < 1 || first + n > S_) throw InvalidArgument("source range out of bounds");
+    if (k < 1 || k > kTopKMax) throw InvalidArgument("k must be in [1, 128]");
+    if (!solved_) throw StateError("no estimates before dppr_solve_initial");
+    DPPR_CUDA(cudaSetDevice(dev_));
+    const int slices = div_up(V_, kTopSlice);
+    const size_t need = (size_t)n * slices * k, outn = (size_t)n * k;
+    if (topk_key_.count < need) { topk_key_.alloc(need); topk_id_.alloc(need); }
+    if (topk_out_ids_.count < outn) {
+        topk_out_ids_.alloc(outn); topk_out_vals_.alloc(outn);
+        topk_host_ids_.alloc(outn); topk_host_vals_.alloc(outn);
+    }
+    for (int32_t lo = 0; lo < n; lo += 32768) {  // (grid.y limit)
+        const int32_t m = std::min<int32_t>(32768, n - lo);
+        topk_partial<<<dim3((unsigned)slices, (unsigned)m), kThreads, 0, st_>>>(p_.ptr, Vp_, V_, first + lo, inv_.ptr, k,
+                                                                              topk_key_.ptr + (size_t)lo * slices * k,
+                                                                              topk_id_.ptr + (size_t)lo * slices * k); ++launch_counter();
+    }
+    topk_merge<<<(unsigned)n, kThreads, 0, st_>>>(topk_key_.ptr, topk_id_.ptr, slices, k, topk_out_ids_.ptr, topk_out_vals_.ptr); ++launch_counter();
+    DPPR_CUDA(cudaGetLastError());
+    DPPR_CUDA(cudaMemcpyAsync(topk_host_ids_.ptr, topk_out_ids_.ptr, sizeof(int32_t) * outn, cudaMemcpyDeviceToHost, st_));
+    DPPR_CUDA(cudaMemcpyAsync(topk_host_vals_.ptr, topk_out_vals_.ptr, sizeof(double) * outn, cudaMemcpyDeviceToHost, st_));
+    DPPR_CUDA(cudaStreamSynchronize(st_));
+    check_health();
+    std::memcpy(ids, topk_host_ids_.ptr, sizeof(int32_t) * outn);
+    std::memcpy(values, topk_host_vals_.ptr, sizeof(double) * outn);
 }
 
 }  // namespace dppr

@@ -185,15 +185,18 @@ __device__ void pull_build(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
     const uint32_t V = (uint32_t)a.V, nCG = ((uint32_t)a.Sp / SB) >> pull_gshift<SB>(a);
     const uint32_t tpc = pull_tiles_per_group<SB>(a), ntiles = tpc * nCG;
     uint32_t legal = 0;
+    unsigned long long ep_slots = 0, ep_pairs = 0, ep_units = 0;  // what ONE sweep over the active tiles moves
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint32_t tile = (uint32_t)(((unsigned long long)t * a.pull_tile_mul) % ntiles);
         uint32_t cg;
         const PullUnit un = pull_unit<SB>(a, tile, tpc, cg);
         const uint32_t w = un.w, s0 = un.s0;
         bool active = false;
+        uint32_t wlen = 0;
         if (w < V) {
             double out[SB];
-            active = __ldg(&a.outdeg[w]) != 0;
+            wlen = (uint32_t)__ldg(&a.outdeg[w]);
+            active = wlen != 0;
 #pragma unroll
             for (int j = 0; j < SB; ++j) {
                 out[j] = 0.0;
@@ -215,7 +218,26 @@ __device__ void pull_build(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
                 }
             }
         }
-        if (__syncthreads_or(active) && threadIdx.x == 0) a.tile_list[atomicAdd(&c->ntiles_active, 1u)] = tile;
+        if (__syncthreads_or(active)) {
+            if (threadIdx.x == 0) a.tile_list[atomicAdd(&c->ntiles_active, 1u)] = tile;
+            if (w < V && s0 < (uint32_t)a.S) {
+                const uint32_t nreal = min((uint32_t)SB, (uint32_t)a.S - s0);
+                ep_units += nreal;
+                ep_pairs += (unsigned long long)wlen * nreal;
+                if (un.g == 0) ep_slots += wlen;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        ep_slots += __shfl_xor_sync(kFull, ep_slots, off);
+        ep_pairs += __shfl_xor_sync(kFull, ep_pairs, off);
+        ep_units += __shfl_xor_sync(kFull, ep_units, off);
+    }
+    if (lane_id() == 0 && ep_units) {
+        atomicAdd(&c->ep_slots, ep_slots);
+        atomicAdd(&c->ep_pairs, ep_pairs);
+        atomicAdd(&c->ep_units, ep_units);
     }
     pull_count_flush(sm, legal, cnt_out);
 }
@@ -452,6 +474,7 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
         c->dedges[0] = 0; c->dedges[1] = 0; c->dedges[2] = 0;
         c->bigpk = 0;
         c->ntiles_active = 0;
+        c->ep_slots = 0; c->ep_pairs = 0; c->ep_units = 0;
     }
     // ... and are simply UN-popped instead of being scattered edge by edge: r[u] += ru, p[u] -= a ru (one thread per hub;
     // r[u] may already hold adds of this iteration, hence the atomic).  The build pass below then finds u legal again and
@@ -497,6 +520,7 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
             c->dcnt[(k + 2) % 3] = 0;
             c->dedges[(k + 2) % 3] = 0;
             pops_acc += n;
+            c->dpops += n;
             if (a.iterlog && (int)iters_done < a.iterlog_cap) {
                 const unsigned long long t = global_ns();
                 a.iterlog[iters_done] = make_uint4(n, 0xffffffffu, (uint32_t)t, (uint32_t)(t >> 32));
@@ -517,7 +541,12 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
         ++iters_done;
         ++sweeps_done;
     }
-    if (k > 0 && blockIdx.x == 0 && threadIdx.x == 0) c->sweep_ns = (float)((double)(global_ns() - t_ep0) / (double)k);
+    if (k > 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        c->sweep_ns = (float)((double)(global_ns() - t_ep0) / (double)k);
+        c->walk_slots += (unsigned long long)k * __ldcg(&c->ep_slots);  // (written before the barrier that followed pull_build)
+        c->walk_pairs += (unsigned long long)k * __ldcg(&c->ep_pairs);
+        c->units += (unsigned long long)k * __ldcg(&c->ep_units);
+    }
     if (__ldcg(&c->dcnt[k % 3]) != 0)
         pull_compact<SB>(a, sm, c, a.x[cur], a.q[(it + 1) & 1], &c->cnt[(it + 1) % 3]);
     return grid_barrier(c, gen, sm);

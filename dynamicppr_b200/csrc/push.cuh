@@ -78,6 +78,12 @@ struct PushCtrl {
     unsigned int ntiles_active;    // dense mode: length of tile_list
     unsigned int pad0;
     unsigned long long bigpk;      // dense mode: grid-tier list of the running sweep, (entries << 32) | chunks
+    unsigned long long gath;       // dense sweeps: gathered x entries that were non-zero = the (edge, source) pairs a scatter
+                                   // iteration would have traversed
+    unsigned long long walk_slots, walk_pairs, units;  // dense sweeps, what they actually moved: out-list entries walked (per
+                                   // chunk group), (entry, source) gathers, (vertex, source) units finished
+    unsigned long long ep_slots, ep_pairs, ep_units;   // the same for ONE sweep of the running dense episode (pull_build)
+    unsigned long long dpops;      // frontier pops performed by sweeps (included in `pops`)
     // ---- persistent across launches ----
     int errflags;
     int level;              // last status stamp handed out (variants 2, 3)
@@ -673,7 +679,7 @@ __global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(con
                     // first iteration of a phase: no history -- the seeds are batch endpoints, take
                     // twice the average in-degree for them
                     const double pred = 2.0 * (double)n * (double)a.avg_indeg;
-                    if (pred * (double)rate > 1.25 * (double)sw) {
+                    if (pred * (double)rate > 1.25 * (double)sw || pred >= 0.5 * (double)a.qcap) {
                         want_dense = true;
                         dense_hpk = hpk;
                         dense_rate = rate;
@@ -686,8 +692,11 @@ __global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(con
                     // engine (a sweep costs the same whatever the frontier; a scatter iteration pays per edge) the
                     // measured figures decide, before that the static estimate of the host.
                     const double pred = t_prev * ((double)n / (double)n_prev) + 0.75 * (double)kHubChunk * (double)(uint32_t)hpk;
-                    const bool enter = (rate > 0.f && sw > 0.f) ? pred * (double)rate > 1.25 * (double)sw
-                                                                 : pred >= (double)a.dense_enter_edges;
+                    // (a traversed edge yields at most one new frontier item: never let the predicted next frontier come
+                    // near the queue capacity -- with many sources V x S exceeds it, the sweeps need no queue)
+                    const bool enter = ((rate > 0.f && sw > 0.f) ? pred * (double)rate > 1.25 * (double)sw
+                                                                  : pred >= (double)a.dense_enter_edges) ||
+                                       pred >= 0.5 * (double)a.qcap;
                     if (enter) {  // handled by the outer loop
                         want_dense = true;
                         dense_hpk = hpk;
@@ -769,7 +778,7 @@ __global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(con
         gath_acc += __shfl_xor_sync(kFull, gath_acc, off);
     }
     if (lane_id() == 0 && carried_acc) atomicAdd(&c->carried, carried_acc);
-    if (lane_id() == 0 && gath_acc) atomicAdd(&c->edges, gath_acc);
+    if (lane_id() == 0 && gath_acc) atomicAdd(&c->gath, gath_acc);
     if (threadIdx.x == 0) {
         if (edges_acc) atomicAdd(&c->edges, edges_acc);
         if (blockIdx.x == 0) {

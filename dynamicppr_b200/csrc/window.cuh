@@ -10,7 +10,11 @@
 //               stream order, so per vertex the expiring in-edges are always the oldest ones:
 //               expire = advance `head`, insert = append at `head+len`.  VMeta{base,head,len,cap}
 //               is one 16-byte load per frontier pop; cap is a power of two (ring index = mask).
-//               A ring that fills up moves to a fresh, larger slot range (amortised doubling).
+//               A ring that fills up moves to a larger slot range (amortised doubling); one that has shrunk to a
+//               quarter of its capacity moves to a smaller one; the range it leaves goes onto a per-size-class free
+//               stack (one batch later: the relocation copy still reads it) and is handed out again before the pool's
+//               bump pointer advances.  Pool use therefore tracks the LIVE degree sum, not the sum of every vertex's
+//               peak degree over the life of the stream (round-1 advisor finding).
 //   * out-degree: plain int32 per vertex (the reference only ever uses row_ptr differences,
 //               gpu/ExpandRev.cuh:71, gpu/StreamUpdate.cuh:13).
 //   * out-adjacency (directed graphs, when dense iterations are enabled -- pull.cuh): a second set of per-vertex
@@ -39,6 +43,16 @@ struct RelocJob {
     uint32_t old_base, old_head, old_cap, len, new_base, pad;
 };
 
+// free ranges of the adjacency pool, one stack per power-of-two size class (class c holds ranges of 2^c slots)
+struct PoolFree {
+    int *count;              // [32] entries on each stack (transiently negative while several pops race for the last entry)
+    const uint32_t *off;     // [33] stack c lives in stack[off[c], off[c+1])
+    uint32_t *stack;
+    uint2 *pend;             // ranges released by THIS batch: {base, capacity}; pushed onto the stacks by the next batch
+    uint32_t *npend;
+    unsigned long long *leaked;  // slots dropped because a stack was full
+};
+
 struct WindowView {
     int32_t V;
     uint4 *vmeta;
@@ -47,7 +61,38 @@ struct WindowView {
     unsigned long long *pool_top;
     unsigned long long pool_cap;
     int *errflags;
+    PoolFree fr;
 };
+
+constexpr uint32_t kNoRange = 0xffffffffu;
+
+// A range of `cap` (power of two) slots: the free stack of its class first, the bump pointer otherwise.  Called from the
+// plan stage only, where nothing pushes: concurrent pops are safe with a plain fetch-and-subtract.
+__device__ __forceinline__ uint32_t pool_alloc(const WindowView &w, uint32_t cap) {
+    const int cls = 31 - __clz((int)cap);
+    if (__ldcg(&w.fr.count[cls]) > 0) {
+        const int i = atomicSub(&w.fr.count[cls], 1) - 1;
+        if (i >= 0) return __ldcg(&w.fr.stack[w.fr.off[cls] + (uint32_t)i]);
+        atomicAdd(&w.fr.count[cls], 1);  // lost the race for the last entry
+    }
+    const unsigned long long nb = atomicAdd(w.pool_top, (unsigned long long)cap);
+    return nb + cap > w.pool_cap ? kNoRange : (uint32_t)nb;
+}
+
+// Hands the ranges the PREVIOUS batch released to the free stacks.  Runs in the first stage of a window update (entries),
+// which is separated from the plan stage by a kernel boundary / grid barrier: pushes never race with pops.
+__device__ __forceinline__ void pool_reclaim_one(uint32_t j, const uint2 *pend_prev, const PoolFree &fr) {
+    const uint2 r = __ldcg(&pend_prev[j]);
+    const int cls = 31 - __clz((int)r.y);
+    const uint32_t room = fr.off[cls + 1] - fr.off[cls];
+    const int i = atomicAdd(&fr.count[cls], 1);
+    if (i >= 0 && (uint32_t)i < room) {
+        fr.stack[fr.off[cls] + (uint32_t)i] = r.x;
+    } else {
+        atomicSub(&fr.count[cls], 1);
+        atomicAdd(fr.leaked, (unsigned long long)r.y);
+    }
+}
 
 __host__ __device__ __forceinline__ uint32_t next_pow2_u32(uint32_t x) {
     if (x <= 1) return 1;
@@ -217,9 +262,12 @@ __device__ __forceinline__ void batch_entries_one(int64_t i, int2 *log, int64_t 
 __global__ void __launch_bounds__(kThreads)
     win_batch_entries(int2 *__restrict__ log, int64_t W, int64_t log_start, const int2 *__restrict__ arriving, int64_t B,
                       int directed, int32_t V, uint32_t *__restrict__ akey, uint32_t *__restrict__ aval,
-                      uint32_t *__restrict__ bkey, uint32_t *__restrict__ bval, int *errflags, const uint32_t *perm) {
+                      uint32_t *__restrict__ bkey, uint32_t *__restrict__ bval, int *errflags, const uint32_t *perm,
+                      const uint2 *__restrict__ pend_prev, const uint32_t *__restrict__ npend_prev, PoolFree fr) {
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < B; i += (int64_t)gridDim.x * kThreads)
         batch_entries_one(i, log, W, log_start, arriving, B, directed, V, akey, aval, bkey, bval, errflags, perm);
+    const uint32_t np = *npend_prev;
+    for (uint32_t j = blockIdx.x * kThreads + threadIdx.x; j < np; j += gridDim.x * kThreads) pool_reclaim_one(j, pend_prev, fr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -270,7 +318,7 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
-// one thread per touched vertex: expire (advance head), reserve room for the inserts, grow the ring
+// one thread per touched vertex: expire (advance head), reserve room for the inserts, grow or shrink the ring
 __device__ __forceinline__ void plan_one(uint32_t s, const Segments &sg, const WindowView &w, uint32_t *ins_pos,
                                          RelocJob *jobs, uint32_t *njobs) {
     const uint32_t v = sg.vertex[s];
@@ -288,26 +336,29 @@ __device__ __forceinline__ void plan_one(uint32_t s, const Segments &sg, const W
         m.len -= ndel;
     }
     uint32_t pos = m.len;
-    if (nins) {
-        const uint32_t need = m.len + nins;
-        if (need > m.cap) {
-            const uint32_t ncap = ring_capacity_for(need);
-            const unsigned long long nb = atomicAdd(w.pool_top, (unsigned long long)ncap);
-            if (nb + ncap > w.pool_cap) {
+    const uint32_t need = m.len + nins;
+    const bool grow = need > m.cap;
+    const bool shrink = !grow && m.cap > 4u && need <= (m.cap >> 2);  // hysteresis: it grows again only beyond 2x
+    if (grow || shrink) {
+        const uint32_t ncap = need ? ring_capacity_for(need) : 0u;  // an emptied ring gives its range back entirely
+        const uint32_t nb = ncap ? pool_alloc(w, ncap) : 0u;
+        if (nb == kNoRange) {
+            if (grow) {
                 atomicOr(w.errflags, kErrPool);
-                pos = 0xffffffffu;  // inserts of this run are dropped; engine is flagged unhealthy
-            } else {
-                if (m.len) {
-                    const uint32_t j = atomicAdd(njobs, 1u);
-                    jobs[j] = RelocJob{m.base, m.head, m.cap, m.len, (uint32_t)nb, 0u};
-                }
-                m.base = (uint32_t)nb;
-                m.head = 0u;
-                m.cap = ncap;
+                pos = 0xffffffffu;  // inserts of this run are dropped; the engine is flagged and refuses further batches
+            }                       // (a shrink that finds no range simply keeps the ring)
+        } else {
+            if (m.cap) w.fr.pend[atomicAdd(w.fr.npend, 1u)] = make_uint2(m.base, m.cap);
+            if (m.len) {
+                const uint32_t j = atomicAdd(njobs, 1u);
+                jobs[j] = RelocJob{m.base, m.head, m.cap, m.len, nb, 0u};
             }
+            m.base = nb;
+            m.head = 0u;
+            m.cap = ncap;
         }
-        if (pos != 0xffffffffu) m.len += nins;
     }
+    if (nins && pos != 0xffffffffu) m.len += nins;
     ins_pos[s] = pos;
     w.vmeta[v] = make_uint4(m.base, m.head, m.len, m.cap);
 }

@@ -38,6 +38,8 @@ struct CoopArgs {
     uint32_t *ins_posB;
     RelocJob *jobsB;
     uint32_t *njobsB;
+    const uint2 *pend_prev;        // ranges released by the previous batch (window.cuh, PoolFree)
+    const uint32_t *npend_prev;
 };
 
 struct CoopSmem {
@@ -161,6 +163,10 @@ __global__ void __launch_bounds__(kThreads) win_update_coop(const CoopArgs a) {
     for (uint32_t i = gtid; i < B; i += gsize)
         batch_entries_one(i, a.log, a.W, a.log_start, a.arriving, a.B, a.directed, a.w.V, a.akey[0], a.aval[0], a.bkey[0],
                           a.bval[0], a.w.errflags, a.perm);
+    {
+        const uint32_t np = *a.npend_prev;
+        for (uint32_t j = gtid; j < np; j += gsize) pool_reclaim_one(j, a.pend_prev, a.w.fr);
+    }
     if (!coop_barrier(a.bar, gen, sm.abort_flag, a.w.errflags)) return;
     const int ra = coop_sort_and_rle(a, a.akey, a.aval, n, a.segA, sm, gen, alive);
     if (!alive) return;

@@ -139,6 +139,8 @@ struct FusedArgs {
     uint32_t *ins_posB;
     RelocJob *jobsB;
     uint32_t *njobsB;
+    const uint2 *pend_prev;        // ranges released by the previous batch (window.cuh, PoolFree)
+    const uint32_t *npend_prev;
 };
 
 __global__ void __launch_bounds__(kFusedThreads, 1) win_fused_small(const FusedArgs a) {
@@ -148,6 +150,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) win_fused_small(const FusedA
     for (uint32_t i = threadIdx.x; i < B; i += kFusedThreads)
         batch_entries_one(i, a.log, a.W, a.log_start, a.arriving, a.B, a.directed, a.w.V, a.akey[0], a.aval[0], a.bkey[0],
                           a.bval[0], a.w.errflags, a.perm);
+    {
+        const uint32_t np = *a.npend_prev;
+        for (uint32_t j = threadIdx.x; j < np; j += kFusedThreads) pool_reclaim_one(j, a.pend_prev, a.w.fr);
+    }
     __syncthreads();
     // group A: keyed by destination -> in-lists
     const int ra = fused_sort_pairs(a.akey[0], a.aval[0], a.akey[1], a.aval[1], n, a.key_bits, sm);

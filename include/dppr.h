@@ -27,14 +27,16 @@
 extern "C" {
 #endif
 
-#define DPPR_VERSION 100
+#define DPPR_VERSION 200
 
 enum {
     DPPR_OK = 0,
     DPPR_E_INVALID = 1,   /* bad argument / configuration (reference: ArgumentsChecker, Arguments.h:42-64) */
     DPPR_E_CUDA = 2,      /* CUDA runtime failure (reference: CUDA_ERROR prints + exit(-1), gpu/GPUUtil.cuh:7-19) */
     DPPR_E_STATE = 3,     /* call out of order (e.g. slide before init_window) */
-    DPPR_E_CAPACITY = 4,  /* adjacency pool / frontier queue exhausted -- enlarge via dppr_config */
+    DPPR_E_CAPACITY = 4,  /* adjacency pool / frontier queue exhausted -- enlarge via dppr_config.  Detected on the device:
+                             reported by the first call after the failing batch has finished (dppr_slide* / dppr_apply_batch* /
+                             dppr_sync / dppr_get_*), and by every call after that -- the engine stays failed */
     DPPR_E_NODEVICE = 5   /* no usable CUDA device: there is NO CPU fallback */
 };
 
@@ -43,14 +45,37 @@ enum { DPPR_OPTIMIZED = 0, DPPR_FAST_FRONTIER = 1, DPPR_EAGER = 2, DPPR_VANILLA 
 
 /* how the push loop is driven */
 enum {
-    DPPR_ENGINE_AUTO = 0,      /* fastest measured: currently LEVELSYNC for every variant */
+    DPPR_ENGINE_AUTO = 0,      /* = LEVELSYNC */
     DPPR_ENGINE_STEPWISE = 1,  /* one launch per push sub-pass, host reads the frontier count every iteration
                                   (the reference's structure, gpu/PPRRevPushGPU.cuh:97-131); debugging / profiling */
-    DPPR_ENGINE_ASYNC = 2,     /* variant 0 only: one cooperative launch per refresh, device-wide ticket queue,
-                                  no barrier between pushes (csrc/push_async.cuh) */
+    /* 2 was an experimental ticket-queue engine in round 1; removed (it lost on every probe), the value is rejected */
     DPPR_ENGINE_LEVELSYNC = 3  /* one cooperative launch per refresh, level-synchronous iterations separated by a
                                   software grid barrier (csrc/push.cuh) */
 };
+
+/* Tuning knobs.  Every field: 0 = default.  Read once by dppr_create; a DPPR_<NAME> environment variable of the same
+ * meaning (development aid for A/B runs, also read once, in dppr_create) is consulted only where the field is 0. */
+typedef struct dppr_tuning {
+    int32_t relabel;            /* internal vertex order by out-degree rank: 0/1 on (default), -1 off             [DPPR_RELABEL=0] */
+    int32_t relabel_blocks;     /* ranks are dealt round-robin over this many blocks; default 1024               [DPPR_RELABEL_BLOCKS] */
+    int32_t relabel_both;       /* 1: rank by out- plus in-degree                                                 [DPPR_RELABEL_BOTH] */
+    int32_t ctas_per_sm;        /* co-resident CTAs per SM of the persistent push kernel; default 4               [DPPR_CTAS_PER_SM] */
+    int32_t tile_cap;           /* frontier items per tile once a CTA's share exceeds 512; default 128            [DPPR_TILE_CAP] */
+    int32_t max_iters;          /* push iterations per refresh before the watchdog fires; default 400000         [DPPR_MAX_ITERS] */
+    int32_t dense;              /* gather sweeps (variant 0): 0 auto by window size, 1 always, -1 never           [DPPR_DENSE] */
+    int32_t pull_group;         /* lanes sharing a vertex in a multi-source sweep (1..8); default 8               [DPPR_PULL_GROUP] */
+    int32_t pull_warp_min;      /* out-degree tiers of a sweep; defaults 32 / 1024 / 65536                        [DPPR_PULL_WARP_MIN ...] */
+    int32_t pull_cta_min;
+    int32_t pull_big_min;
+    int32_t window_path;        /* 0 auto, 1 multi-kernel window update only, 2 no single-CTA kernel              [DPPR_WINDOW_PATH] */
+    int32_t iterlog;            /* 1: keep a per-iteration log of the last refresh (dppr_debug_iterlog)           [DPPR_ITERLOG] */
+    int32_t probe_iter;         /* iteration whose per-CTA timeline dppr_debug_ctalog returns; default 10         [DPPR_PROBE_ITER] */
+    double dense_div;           /* static scatter/gather switch estimate: (E_w + 2V) S / dense_div; default 4     [DPPR_DENSE_DIV] */
+    double dense_min_edges;     /* auto: window entries x sources from which the switching kernel is used; 2e7   [DPPR_DENSE_MIN_EDGES] */
+    double carry_gamma;         /* variant 0 threshold schedule; default off (1.0)                               [DPPR_CARRY_GAMMA] */
+    double carry_scale;         /* default 0.01                                                                   [DPPR_CARRY_SCALE] */
+    int32_t reserved[8];
+} dppr_tuning;
 
 typedef struct dppr_engine dppr_engine;
 
@@ -71,6 +96,7 @@ typedef struct dppr_config {
     int64_t frontier_capacity;  /* (source, vertex) items per frontier queue; <=0 -> default */
     int32_t hub_degree;         /* in-degree at/above which a vertex is expanded grid-wide; <=0 -> 64 */
     int32_t reserved0;
+    dppr_tuning tuning;
 } dppr_config;
 
 typedef struct dppr_batch_stats {
@@ -90,6 +116,15 @@ typedef struct dppr_batch_stats {
     float ms_push;              /* both push phases  } (gpu/PPRGPU.cuh:128-163)                    */
     int32_t error_flags;        /* device-side DPPR_DEVERR_* bits, 0 when healthy */
     int32_t dense_sweeps;       /* iterations that ran as gather sweeps over the out-lists (counted in `iterations` too) */
+    /* traversed_edges = scatter_edges + the (edge, source) pairs the sweeps gathered with a non-zero residual, i.e. the
+     * work in the reference's push form.  What the sweeps actually moved (they read every out-list entry of the active
+     * tiles, whatever the frontier) is counted separately, for the roofline of the gather form: */
+    int64_t scatter_edges;      /* in-edges traversed by scatter iterations = FP64 atomics issued */
+    int64_t dense_slots;        /* out-list entries walked by sweeps (once per chunk group of sources) */
+    int64_t dense_pairs;        /* (out-list entry, source) gathers of x by sweeps */
+    int64_t dense_units;        /* (vertex, source) units finished by sweeps */
+    int64_t dense_pops;         /* frontier pops performed by sweeps (included in frontier_pops) */
+    int64_t pool_leaked;        /* pool slots dropped because a free stack was full (0 in every run so far) */
 } dppr_batch_stats;
 
 enum {
@@ -97,7 +132,9 @@ enum {
     DPPR_DEVERR_QUEUE = 2,      /* frontier queue overflow */
     DPPR_DEVERR_HUBQ = 4,       /* hub list overflow */
     DPPR_DEVERR_WATCHDOG = 8,   /* grid barrier / iteration watchdog fired */
-    DPPR_DEVERR_UNDERFLOW = 16  /* expiry of an edge the window does not hold (caller broke FIFO order) */
+    DPPR_DEVERR_UNDERFLOW = 16, /* expiry of an edge the window does not hold (caller broke FIFO order) */
+    DPPR_DEVERR_BADID = 32      /* an edge endpoint outside [0, vertex_count) reached the device (device-pointer input; host
+                                   input is checked before it is staged and fails the call with DPPR_E_INVALID) */
 };
 
 int dppr_version(void);
@@ -129,8 +166,14 @@ int dppr_solve_initial(dppr_engine *e);
  * expiring edges are read from the device's own arrival-order ring.  O(B) work, no re-sort of the window. */
 int dppr_apply_batch(dppr_engine *e, const int32_t *new_edge1, const int32_t *new_edge2, int64_t B);
 int dppr_apply_batch_pairs(dppr_engine *e, const int32_t *pairs, int64_t B);
-/* same, input already resident in device memory (B x int32 pairs) */
+/* same, input already resident in device memory (B x int32 pairs).  Stream contract of every *_device_pairs entry point:
+ * the engine reads the buffer asynchronously on its OWN non-blocking stream, which does not order against the stream
+ * that produced the buffer (not even the legacy default stream).  The caller must either have synchronised the producer
+ * before the call, or pass an event recorded after the producer to dppr_wait_event() first; and it must keep the buffer
+ * alive and unmodified until dppr_sync() (or any synchronising call) returns. */
 int dppr_apply_batch_device_pairs(dppr_engine *e, const int32_t *device_pairs, int64_t B);
+/* makes the engine's stream wait for `cuda_event` (a cudaEvent_t) before any work enqueued after this call */
+int dppr_wait_event(dppr_engine *e, void *cuda_event);
 
 /* Replaces: IncrementalBatchUpdate + ExecuteMainLoop(0) + ExecuteMainLoop(1), the region the reference
  * times as ppr_time (gpu/PPRGPU.cuh:128-163; kernels gpu/StreamUpdate.cuh, Inspect.cuh, ExpandRev.cuh). */
@@ -156,6 +199,20 @@ int dppr_get_residuals(dppr_engine *e, int32_t source_index, double *out);
 /* device-to-device copy of one estimate vector into caller-owned device memory (for the final
  * NCCL gather done by the caller; there is no collective on the hot path). */
 int dppr_copy_estimates_device(dppr_engine *e, int32_t source_index, void *device_out);
+/* What a query reads back: the k (<= 128) largest estimates of sources [first_source, first_source + n_sources), selected
+ * on the device (csrc/topk.cuh).  ids / values: n_sources x k, host memory; value descending, ties by ascending vertex id;
+ * rows shorter than k (V < k) are padded with id -1.  Synchronises. */
+int dppr_get_topk(dppr_engine *e, int32_t first_source, int32_t n_sources, int32_t k, int32_t *ids, double *values);
+
+/* ---- validation on the device (reference: -DVALIDATE, gpu/PPRRevPushGPU.cuh:45-90,133-165; csrc/validate.cuh) ---------
+ * dppr_validate: max |r[u]| (the reference asserts < eps) and the largest defect of the push invariant
+ *   p[u] + a r[u] = a [u==s] + (1-a)/(outdeg(u)+1) sum_{w in out(u)} p[w]   over all u, from the device-resident window
+ * graph; defect ~1e-15 and max |r| <= eps together imply |p - pi| <= eps.  Either output may be NULL.  Synchronises.
+ * dppr_check_window_device: the reference's ValidateGraph, without the host: `device_pairs` = the n = W edges the window
+ * must hold right now (device memory, stream order, caller ids); *mismatches = entries of the canonical (dst, src)-sorted
+ * edge list + out-degrees that differ from the engine's window graph (0 = bit-exact). */
+int dppr_validate(dppr_engine *e, int32_t source_index, double *max_abs_residual, double *max_invariant_defect);
+int dppr_check_window_device(dppr_engine *e, const int32_t *device_pairs, int64_t n, int64_t *mismatches);
 
 /* Canonical window graph, the object the reference validator compares
  * (gpu/PPRRevPushGPU.cuh:45-90): in_row_ptr[V+1], in_col_ind[E_w] with rows ascending and duplicates
@@ -168,17 +225,40 @@ int64_t dppr_window_csr_entries(const dppr_engine *e); /* E_w = D*W */
  * (undirected graph: the in-lists serve; or dense iterations disabled). */
 int dppr_export_window_out_csr(dppr_engine *e, int32_t *out_row_ptr, int32_t *out_col_ind);
 
-/* Synthetic directed R-MAT stream (a,b,c,d = 0.57,0.19,0.19,0.05; ids folded and relabelled into [0,V)) written as
- * M int32 pairs into caller-owned DEVICE memory.  Counter-based: edge i depends on (seed, i) only.  Stands in for
- * the reference's offline encoder (encoder/GraphEncoder.h:20-98) for shapes too large to ship. */
+/* ---- synthetic streams ------------------------------------------------------------------
+ * Stand-in for the reference's offline encoder (encoder/GraphEncoder.h:20-98) for shapes too large to ship: the
+ * payload of a .bin file (int32 pairs in stream order, encoder/GraphEncoder.h:86-95) generated from a seed.
+ * Counter-based and integer-only: edge i depends on (kind, vertex_count, seed, i) alone, so any slice
+ * [first_edge, first_edge + n_edges) can be produced on its own, and the DEVICE generator and its HOST twin write
+ * identical bytes -- the GPU holds the whole stream in HBM while the host writes only the prefix the reference CPU
+ * implementation reads.  DPPR_STREAM_RMAT: directed R-MAT (0.57, 0.19, 0.19, 0.05), ids folded and scrambled into
+ * [0, V), duplicates and self-loops kept.  DPPR_STREAM_POWERLAW: undirected Chung-Lu power law, P(rank k) ~
+ * (k+1)^-0.75 per endpoint, no self-loops, duplicate pairs kept (the reference keeps multi-edges). */
+enum { DPPR_STREAM_RMAT = 0, DPPR_STREAM_POWERLAW = 1 };
+int dppr_generate_stream_device(int32_t device, int32_t kind, int32_t vertex_count, int64_t first_edge, int64_t n_edges,
+                                uint64_t seed, int32_t *device_pairs);
+/* host twin: no GPU needed; `threads` host threads */
+int dppr_generate_stream_host(int32_t kind, int32_t vertex_count, int64_t first_edge, int64_t n_edges, uint64_t seed,
+                              int32_t *pairs, int32_t threads);
+/* = dppr_generate_stream_device(device, DPPR_STREAM_RMAT, vertex_count, 0, n_edges, seed, device_pairs) */
 int dppr_generate_rmat_device(int32_t device, int32_t vertex_count, int64_t n_edges, uint64_t seed, int32_t *device_pairs);
+
+/* ---- source selection ---------------------------------------------------------------------
+ * Replaces: workload/Graph.h:85-131 (degree histograms over the whole file; an undirected edge counts at both ends)
+ * + the sort of ChooseVertexDegreeRange (workload/Graph.h:178-190).  `pairs` = n int32 pairs in host memory
+ * (uploaded in chunks) or, with pairs_on_device != 0, in device memory.  order[V] (host): vertex ids by descending
+ * out-degree (by_out_degree != 0) or in-degree, ties by ascending id -- exact, also at Twitter scale.  out_degree[V] /
+ * in_degree[V] (host, optional): the histograms.  The bucket rules on top of the ranking (top10 = ranks 0..9, top1000 =
+ * 10 random ranks of [10, 1000), ...; workload/Workload.cpp:47-55) live in the `pagerank --pick` host tool. */
+int dppr_rank_by_degree(int32_t device, int32_t vertex_count, int32_t directed, int32_t by_out_degree, const int32_t *pairs,
+                        int64_t n_edges, int32_t pairs_on_device, int32_t *order, int32_t *out_degree, int32_t *in_degree);
 
 /* ---- test hooks (used by tests/ only) ---------------------------------------------------- */
 /* overwrite (p, r) of one source (V doubles each; either may be NULL) */
 int dppr_set_state(dppr_engine *e, int32_t source_index, const double *p, const double *r);
 /* residual repair only (no push): the closed form checked against the sequential oracle */
 int dppr_repair_only(dppr_engine *e);
-/* debug: with DPPR_ITERLOG=1 in the environment at dppr_create, (frontier size, hub chunks, globaltimer lo, hi)
+/* debug: with tuning.iterlog (or DPPR_ITERLOG=1 in the environment at dppr_create), (frontier size, hub chunks, globaltimer lo, hi)
  * of every push iteration of the most recent refresh; out holds 4*cap uint32 */
 int dppr_debug_iterlog(dppr_engine *e, uint32_t *out, int32_t cap, int32_t *n_out);
 /* debug: 8 globaltimer stamps per CTA for push iteration DPPR_PROBE_ITER of the most recent refresh */

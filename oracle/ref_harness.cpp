@@ -23,8 +23,13 @@
 //                     (the line the reference keeps commented at
 //                     cpu/PPRCPUMTCilk.h:126) so PPR always runs on the true window
 //   --quiet           silence the reference's std::cout chatter
-//   --times <file>    one line per batch: "<batch> <ppr_us> <iteration_id>" (cheap; used by bench.py's
-//                     reference arm to drop warm-up batches -- the reference itself only prints a mean)
+//   --times <file>    one line per (batch, source): "<batch> <ppr_us> <iteration_id> <source_index>" (cheap; used by
+//                     bench.py's reference arm to drop warm-up batches -- the reference itself only prints a mean)
+//   --sources a,b,c   several sources over ONE stream: one reference PPR object per source (the constructor reads
+//                     gSourceVertexId, cpu/PPRCPUMTCilk.h:34), all on the same SlidingGraphVec; per batch the graph
+//                     is advanced once and IncExecuteImpl runs for each source in turn, each with every thread.
+//                     The reference itself runs one process per source (scripts/cpu.sh); this only shares the
+//                     untimed graph maintenance.  --dump / --pow use the first source.
 //
 // Dump format (native little-endian):
 //   char[8] "DPPRDMP1"; int32 V; int32 directed; int64 W; int64 B; int32 has_pow; int32 nsnap
@@ -110,12 +115,13 @@ int CountIncRowsDiffer(SlidingGraphVec *dg, const std::vector<int32_t> &row_ptr,
 }  // namespace
 
 int main(int argc, char *argv[]) {
-    std::string dump_path, times_path;
+    std::string dump_path, times_path, sources_arg;
     bool want_pow = false, scratch_graph = false, quiet = false;
     for (int i = 1; i < argc; ++i) {
         std::string a(argv[i]);
         if (a == "--dump" && i + 1 < argc) dump_path = argv[i + 1];
         if (a == "--times" && i + 1 < argc) times_path = argv[i + 1];
+        if (a == "--sources" && i + 1 < argc) sources_arg = argv[i + 1];
         if (a == "--pow") want_pow = true;
         if (a == "--scratch-graph") scratch_graph = true;
         if (a == "--quiet") quiet = true;
@@ -129,12 +135,26 @@ int main(int argc, char *argv[]) {
     SlidingGraphVec *dg = new SlidingGraphVec(gDataFileName, gIsDirected);
     Profiler::InitProfiler(1, PROFILE_PHASE_NUM, PROFILE_COUNT_TYPE_NUM);
 
-    PPRCPUMTCilkRev *ppr = NULL;
-    if (gVariant == OPTIMIZED) ppr = new PPRCPUMTCilkRev(dg);
-    else if (gVariant == FAST_FRONTIER) ppr = new PPRCPUMTCilkRevFF(dg);
-    else if (gVariant == EAGER) ppr = new PPRCPUMTCilkRevEager(dg);
-    else if (gVariant == VANILLA) ppr = new PPRCPUMTCilkRevVanilla(dg);
-    assert(ppr != NULL);
+    std::vector<int> source_ids;
+    for (size_t pos = 0; pos < sources_arg.size();) {
+        size_t comma = sources_arg.find(',', pos);
+        if (comma == std::string::npos) comma = sources_arg.size();
+        if (comma > pos) source_ids.push_back(atoi(sources_arg.substr(pos, comma - pos).c_str()));
+        pos = comma + 1;
+    }
+    if (source_ids.empty()) source_ids.push_back(gSourceVertexId);
+    std::vector<PPRCPUMTCilkRev *> pprs;
+    for (size_t si = 0; si < source_ids.size(); ++si) {
+        gSourceVertexId = source_ids[si];
+        PPRCPUMTCilkRev *one = NULL;
+        if (gVariant == OPTIMIZED) one = new PPRCPUMTCilkRev(dg);
+        else if (gVariant == FAST_FRONTIER) one = new PPRCPUMTCilkRevFF(dg);
+        else if (gVariant == EAGER) one = new PPRCPUMTCilkRevEager(dg);
+        else if (gVariant == VANILLA) one = new PPRCPUMTCilkRevVanilla(dg);
+        assert(one != NULL);
+        pprs.push_back(one);
+    }
+    PPRCPUMTCilkRev *ppr = pprs[0];
 
     const int V = dg->vertex_count;
     FILE *out = NULL;
@@ -184,10 +204,12 @@ int main(int argc, char *argv[]) {
     FILE *times = times_path.empty() ? NULL : fopen(times_path.c_str(), "w");
     // initial solve on the first window (cpu/PPRCPUMTCilk.h:74-91)
     TimeMeasurer t0;
-    t0.StartTimer();
-    ppr->ExecuteImpl();
-    t0.EndTimer();
-    if (times) fprintf(times, "0 %lld %d\n", (long long)t0.GetElapsedMicroSeconds(), (int)ppr->iteration_id);
+    for (size_t si = pprs.size(); si-- > 0;) {  // (source 0 last: t0 below stays its time)
+        t0.StartTimer();
+        pprs[si]->ExecuteImpl();
+        t0.EndTimer();
+        if (times) fprintf(times, "0 %lld %d %d\n", (long long)t0.GetElapsedMicroSeconds(), (int)pprs[si]->iteration_id, (int)si);
+    }
     if (out) {
         ScratchWindowCSR(dg, row_ptr, col, outdeg);
         snapshot(0, (double)t0.GetElapsedMicroSeconds(), CountIncRowsDiffer(dg, row_ptr, col, outdeg));
@@ -209,11 +231,13 @@ int main(int argc, char *argv[]) {
         total_inc_rows_differ += differ;
         if (scratch_graph) dg->ConstructGraph();
         TimeMeasurer timer;
-        timer.StartTimer();
-        ppr->IncExecuteImpl();
-        timer.EndTimer();
-        ppr_time += timer.GetElapsedMicroSeconds();
-        if (times) fprintf(times, "%d %lld %d\n", (int)stream_batch_count, (long long)timer.GetElapsedMicroSeconds(), (int)ppr->iteration_id);
+        for (size_t si = pprs.size(); si-- > 0;) {
+            timer.StartTimer();
+            pprs[si]->IncExecuteImpl();
+            timer.EndTimer();
+            ppr_time += timer.GetElapsedMicroSeconds();
+            if (times) fprintf(times, "%d %lld %d %d\n", (int)stream_batch_count, (long long)timer.GetElapsedMicroSeconds(), (int)pprs[si]->iteration_id, (int)si);
+        }
         snapshot((int)stream_batch_count, (double)timer.GetElapsedMicroSeconds(), differ);
     }
     if (times) fclose(times);
@@ -226,6 +250,7 @@ int main(int argc, char *argv[]) {
     size_t done = stream_batch_count - 1;
     double ms = ppr_time / 1000.0;
     std::cout << "harness_batches " << done << std::endl;
+    std::cout << "harness_sources " << pprs.size() << std::endl;
     std::cout << "harness_inc_rows_differ " << total_inc_rows_differ << std::endl;
     std::cout << "ppr_time " << ms << " ms" << std::endl;
     std::cout << "edge_count " << (long long)gStreamUpdateCountPerBatch * (long long)done << std::endl;

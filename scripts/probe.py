@@ -46,13 +46,7 @@ T = f('traversed_edges').sum(); F = f('frontier_pops').sum()
 print(f"push algorithmic GB/s: {(24*T+56*F)/ (f('ms_push').sum()*1e-3)/1e9:.1f}; edges/us {T/(f('ms_push').sum()*1e3):.1f}; us/iter {f('ms_push').sum()*1e3/max(f('iterations').sum(),1):.2f}")
 for r in rows[:a.show]:
     print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.as_dict().items()})
-if os.environ.get("DPPR_ITERLOG") and a.mode == 2 and a.variant == 0:
-    dd = eng.ctalog(2).reshape(-1)
-    d = dd.astype(np.float64)
-    t0 = int(dd[8])
-    print("gen 20 timeline (us after publish): done_seen %.2f | first notice %.2f last notice %.2f | first pass end %.2f last pass end %.2f | passes %d items %d" % tuple([(int(dd[i]) - t0) / 1e3 for i in (9, 10, 11, 12, 13)] + [int(dd[15]), int(dd[14])]))
-    print(f"async dbg (last batch): passes {d[0]:.0f} items {d[1]:.0f} ({d[1]/max(d[0],1):.1f}/pass) avg pass {d[2]/max(d[0],1)/1965:.2f} us idle polls {d[3]:.0f} slot spins {d[4]:.0f} rounds {d[5]:.0f}")
-elif os.environ.get("DPPR_ITERLOG"):
+if os.environ.get("DPPR_ITERLOG"):
     lg = eng.iterlog()
     if len(lg):
         t = lg[:, 2].astype(np.int64); dt = np.diff(t) / 1e3

@@ -3,11 +3,14 @@
   * residual bound |r| <= eps,
   * the push invariant  p[u] + a r[u] = a [u==s] + (1-a)/(outdeg(u)+1) * sum_{w in out(u)} p[w]  for EVERY vertex
      -- together with the residual bound it implies |p - pi| <= eps, i.e. the 2-eps parity criterion.
-Config 1 (dblp-shaped) and config 2 (youtube-shaped) run here; configs 3-5 are driven by scripts/run_config.py."""
+Config 1 (dblp-shaped) and config 2 (youtube-shaped) are checked against numpy on the host; configs 3 (all four
+variants), 4 (8 of the top-1000 sources) and 5 (one source, a few batches) run at FULL size with every check on the
+device: window graph bit-exact against the canonical entry list built from the window's own edges
+(dppr_check_window_device), residual bound and push invariant by dppr_validate -- SURVEY Appendix E T3-T6, T10."""
 import numpy as np
 import pytest
 
-from dynamicppr_b200 import DynamicPPR, graphgen, stream
+from dynamicppr_b200 import DynamicPPR, graphgen, stream, workloads
 
 pytestmark = pytest.mark.gpu
 ALPHA = 0.15
@@ -106,3 +109,64 @@ def test_multi_source_default_switching_kernel(directed):
                 assert invariant_defect(V, rp, ci, od, p, r, s) <= 1e-13, (k, i)
     if not directed:  # (on the directed shape the device-side cost model may legitimately keep scattering)
         assert sweeps > 0, "the gather sweeps never ran: the default cost model or size threshold changed"
+
+
+def _fullsize_run(cfg, sources, batches, variant=0, check_at=None, **kw):
+    """stream generated on the device, engine fed device pointers, every check on the device"""
+    import torch
+    wl = cfg.workload()
+    batches = min(batches, wl.runnable_batches(cfg.M))
+    check_at = set(check_at if check_at is not None else (0, batches))
+    dev = workloads.device_edges(cfg, 0, wl.W + batches * wl.B)
+    stats = []
+    with DynamicPPR(cfg.V, cfg.directed, wl.W, wl.B, sources, epsilon=cfg.eps, variant=variant, **kw) as eng:
+        eng.init_window_device_pairs(dev.data_ptr(), wl.W)
+        eng.solve_initial()
+        for k in range(batches + 1):
+            if k > 0:
+                eng.slide_device_pairs(dev.data_ptr() + 8 * (wl.W + (k - 1) * wl.B), wl.B)
+            if k not in check_at:
+                continue
+            st = eng.stats()
+            assert st.error_flags == 0 and st.pool_leaked == 0, (k, st.error_flags)
+            stats.append(st)
+            assert eng.check_window_device(dev.data_ptr() + 8 * k * wl.B, wl.W) == 0, f"window graph differs after batch {k}"
+            for i in range(len(sources)):
+                max_r, defect = eng.validate(i)
+                assert max_r <= cfg.eps, (k, i, max_r)
+                assert defect <= 1e-13, (k, i, defect)
+        ids, vals = eng.topk(4)
+        for i, s in enumerate(sources):
+            assert int(s) in ids[i], "a source is among the top estimates of its own PPR vector"
+    del dev
+    torch.cuda.empty_cache()
+    return stats
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_config3_livejournal_shaped_mode1_all_variants_full_size(variant):
+    """BASELINE configs[2]: 4.8 M vertices, 69 M-edge R-MAT stream, -n 1 -c 100 -l 10000 (100 batches of 100 edges)"""
+    cfg = workloads.CONFIGS[3]
+    src = workloads.top_sources(cfg, 1)
+    stats = _fullsize_run(cfg, src, 100, variant=variant, check_at=(0, 1, 50, 100))
+    assert stats[-1].batch_index == 100 and stats[-1].edges == 100
+
+
+def test_config4_orkut_shaped_multi_source_full_size():
+    """BASELINE configs[3]: 3.07 M vertices, 117 M-edge undirected stream; 8 of the job's top-1000 sources (list ranks
+    0, 142, ..., 999) in one engine -- the switching kernel with gather sweeps"""
+    cfg = workloads.CONFIGS[4]
+    job = workloads.top_sources(cfg, 1000)
+    srcs = job[np.linspace(0, 999, 8).astype(int)]
+    stats = _fullsize_run(cfg, srcs, 4, check_at=(0, 2, 4))
+    assert sum(st.dense_sweeps for st in stats) > 0, "the gather sweeps never ran"
+    assert stats[-1].dense_pairs > 0 and stats[-1].scatter_edges > 0
+
+
+def test_config5_twitter_shaped_one_source_full_size():
+    """BASELINE configs[4] shape on one GPU: 41.7 M vertices, 146.8 M-edge window, 1.47 M-edge batches; the top source;
+    window graph compared bit-exactly on the device (round 1 used a checksum)"""
+    cfg = workloads.CONFIGS[5]
+    src = workloads.top_sources(cfg, 1)
+    stats = _fullsize_run(cfg, src, 3, check_at=(0, 3))
+    assert stats[-1].edges == 1_468_365 and stats[-1].traversed_edges > 1e9

@@ -12,8 +12,8 @@ from helpers import GOLDEN, GOLDEN_IDS, golden_workload, d2_possible, check_agai
 
 pytestmark = pytest.mark.gpu
 
-MODES = [binding.ENGINE_LEVELSYNC, binding.ENGINE_STEPWISE, binding.ENGINE_ASYNC]
-MODE_IDS = ["levelsync", "stepwise", "async"]
+MODES = [binding.ENGINE_LEVELSYNC, binding.ENGINE_STEPWISE]
+MODE_IDS = ["levelsync", "stepwise"]
 
 
 def _run_golden(path, variant, mode, hub_degree=0):
@@ -45,8 +45,6 @@ def _run_golden(path, variant, mode, hub_degree=0):
 @pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("path", GOLDEN, ids=GOLDEN_IDS)
 def test_golden_window_bit_exact_and_estimates_within_2eps(path, variant, mode):
-    if mode == binding.ENGINE_ASYNC and variant != 0:
-        pytest.skip("the asynchronous engine implements variant 0 only")
     _run_golden(path, variant, mode)
 
 
@@ -56,8 +54,6 @@ def test_golden_with_tiny_hub_threshold(variant):
     for path in GOLDEN:
         if any(t in path for t in ("dense_multi_directed", "hub_expiry", "pl_undirected")):
             _run_golden(path, variant, binding.ENGINE_LEVELSYNC, hub_degree=2)
-            if variant == 0:
-                _run_golden(path, variant, binding.ENGINE_ASYNC, hub_degree=2)
 
 
 def _oracle_vs_engine(V, directed, edges, wl, source, eps, variant, mode, n_batches, check_every=1, **kw):
@@ -104,8 +100,7 @@ def test_top_degree_source_heavy_push(mode):
     wl = stream.workload(M, 0.1, 0, 0.01, 100)
     st = _oracle_vs_engine(V, directed, edges, wl, src, 1e-9, 0, mode, 10, check_every=5)
     assert st.traversed_edges > 1000 and st.frontier_pops > 100
-    if mode != binding.ENGINE_ASYNC:
-        assert st.iterations > 5  # the asynchronous engine has no iterations
+    assert st.iterations > 5
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3])
@@ -118,15 +113,14 @@ def test_rmat_directed_small_batches_mode1(variant):
     _oracle_vs_engine(V, directed, edges, wl, src, 1e-9, variant, binding.ENGINE_AUTO, wl.n_batches, check_every=10)
 
 
-@pytest.mark.parametrize("mode", [binding.ENGINE_LEVELSYNC, binding.ENGINE_STEPWISE, binding.ENGINE_ASYNC], ids=["levelsync", "stepwise", "async"])
-def test_threshold_carry_schedule_keeps_the_contract(mode, monkeypatch):
-    """DPPR_CARRY_GAMMA < 1: items below a decaying threshold are carried, not pushed; same 2-eps / eps contract."""
-    monkeypatch.setenv("DPPR_CARRY_GAMMA", "0.7")
+@pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
+def test_threshold_carry_schedule_keeps_the_contract(mode):
+    """tuning.carry_gamma < 1: items below a decaying threshold are carried, not pushed; same 2-eps / eps contract."""
     V, M, directed = 39_635, 131_233, False
     edges = graphgen.powerlaw_undirected(V, M, seed=graphgen.BASE_SEED)
     src = int(graphgen.top_out_degree(V, edges, directed, 1)[0])
     wl = stream.workload(M, 0.1, 0, 0.01, 100)
-    _oracle_vs_engine(V, directed, edges, wl, src, 1e-9, 0, mode, 6, check_every=3)
+    _oracle_vs_engine(V, directed, edges, wl, src, 1e-9, 0, mode, 6, check_every=3, tuning={"carry_gamma": 0.7})
 
 
 def test_loose_epsilon():
@@ -156,7 +150,6 @@ def test_spill_path_many_crossings_per_tile():
     allE = np.concatenate([edges, tail])
     W = len(edges)
     wl = stream.Workload(W, 100, 5, 500)
-    _oracle_vs_engine(V, True, allE, wl, s, 1e-9, 0, binding.ENGINE_ASYNC, 5)
     _oracle_vs_engine(V, True, allE, wl, s, 1e-9, 0, binding.ENGINE_LEVELSYNC, 5)
     _oracle_vs_engine(V, True, allE, wl, s, 1e-9, 3, binding.ENGINE_AUTO, 5)
 

@@ -33,7 +33,7 @@ def test_library_exports_every_symbol_the_header_declares():
     lib = binding.load_library()
     for name in sorted(declared):
         assert getattr(lib, name) is not None
-    assert lib.dppr_version() == 100
+    assert lib.dppr_version() == 200
 
 
 def test_create_fails_loudly_without_a_gpu_or_with_bad_config():
