@@ -46,7 +46,7 @@ def test_topk_matches_numpy(relabel):
 
 def test_topk_with_fewer_vertices_than_k_and_ties():
     V = 40
-    edges = np.array([[i, (i * 7 + 1) % V] for i in range(200)], dtype=np.int32)
+    edges = np.array([[i % V, (i * 7 + 1) % V] for i in range(200)], dtype=np.int32)
     with DynamicPPR(V, True, 100, 10, [3]) as eng:
         eng.init_window_pairs(edges[:100])
         eng.solve_initial()
