@@ -35,7 +35,7 @@ class Tuning(C.Structure):
     _fields_ = [
         ("relabel", C.c_int32), ("relabel_blocks", C.c_int32), ("relabel_both", C.c_int32), ("ctas_per_sm", C.c_int32),
         ("tile_cap", C.c_int32), ("max_iters", C.c_int32), ("dense", C.c_int32), ("pull_group", C.c_int32),
-        ("pull_warp_min", C.c_int32), ("pull_cta_min", C.c_int32), ("pull_big_min", C.c_int32), ("window_path", C.c_int32),
+        ("pull_warp_min", C.c_int32), ("pull_big_min", C.c_int32), ("pull_big_chunk", C.c_int32), ("window_path", C.c_int32),
         ("iterlog", C.c_int32), ("probe_iter", C.c_int32), ("dense_div", C.c_double), ("dense_min_edges", C.c_double),
         ("carry_gamma", C.c_double), ("carry_scale", C.c_double), ("reserved", C.c_int32 * 8),
     ]

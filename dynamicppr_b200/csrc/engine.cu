@@ -60,10 +60,10 @@ Tuning resolve_tuning(const dppr_tuning &t) {
     r.dense_min_edges = pick_real(t.dense_min_edges, "DPPR_DENSE_MIN_EDGES", 2.0e7);
     if (std::getenv("DPPR_DENSE_DIV") && t.dense_div == 0.0 && std::atof(std::getenv("DPPR_DENSE_DIV")) <= 0.0) r.dense = -1;  // round-1 spelling of "off"
     if (std::getenv("DPPR_DENSE_MIN_EDGES") && t.dense_min_edges == 0.0 && std::atof(std::getenv("DPPR_DENSE_MIN_EDGES")) <= 0.0) r.dense_min_edges = 0.0;
-    r.pull_group = std::min(std::max(pick_int(t.pull_group, "DPPR_PULL_GROUP", 8), 1), 8);
+    r.pull_group = std::min(std::max(pick_int(t.pull_group, "DPPR_PULL_GROUP", 32), 1), 32);
     r.pull_warp_min = std::max(1, pick_int(t.pull_warp_min, "DPPR_PULL_WARP_MIN", 32));
-    r.pull_cta_min = std::max(r.pull_warp_min, pick_int(t.pull_cta_min, "DPPR_PULL_CTA_MIN", 1024));
-    r.pull_big_min = std::max(r.pull_cta_min, pick_int(t.pull_big_min, "DPPR_PULL_BIG_MIN", 65536));
+    r.pull_big_min = pick_int(t.pull_big_min, "DPPR_PULL_BIG_MIN", 0);
+    r.pull_big_chunk = pick_int(t.pull_big_chunk, "DPPR_PULL_BIG_CHUNK", 0);
     r.carry_gamma = pick_real(t.carry_gamma, "DPPR_CARRY_GAMMA", 1.0);
     r.carry_scale = pick_real(t.carry_scale, "DPPR_CARRY_SCALE", 0.01);
     r.window_path = pick_int(t.window_path, "DPPR_WINDOW_PATH", 0);
@@ -115,7 +115,7 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     Bmax_ = cfg.max_batch_edges;
     Nb_ = std::max<int64_t>(2 * D_ * Bmax_, 1);
     S_ = cfg.n_sources;
-    Vp_ = ((int64_t)V_ + 31) / 32 * 32;
+    Sr_ = S_ == 1 ? 1 : ((int64_t)S_ + 7) / 8 * 8;
     sources_.assign(cfg.sources, cfg.sources + S_);
     cfg_.sources = sources_.data();
     for (int32_t s : sources_)
@@ -134,13 +134,17 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
         dense_ = can && tn_.dense >= 0 &&
                  (tn_.dense > 0 || (double)cfg.window_edges * (cfg.directed ? 1 : 2) * cfg.n_sources >= tn_.dense_min_edges);
         outlists_ = dense_ && D_ == 1;
-        // several sources: rows of x hold 4-source chunks, G = 2^gshift adjacent lanes take G chunks of a vertex (pull.cuh)
+        // several sources: a lane takes 8 sources (16 bytes of an x row), G = 2^gshift adjacent lanes share a vertex (pull.cuh)
         pull_gshift_ = 0;
         if (S_ > 1) {
-            const int chunks = (S_ + 3) / 4;
-            while ((2 << pull_gshift_) <= std::min(chunks, tn_.pull_group)) ++pull_gshift_;
+            const int chunks = (int)(Sr_ / 8);
+            while ((1 << pull_gshift_) < std::min(chunks, tn_.pull_group) && pull_gshift_ < 5) ++pull_gshift_;
         }
-        Sp_ = S_ == 1 ? 1 : (S_ + (4 << pull_gshift_) - 1) / (4 << pull_gshift_) * (4 << pull_gshift_);
+        // out-lists of big_min or more entries are cut into chunks any warp of the grid takes: a warp streams a list at
+        // kPullUnroll rows per memory round trip, so the wider the rows (the fewer vertices a warp holds) the shorter the chunks
+        pull_big_min_ = tn_.pull_big_min > 0 ? tn_.pull_big_min : (S_ == 1 ? 4096 : 1024);
+        pull_big_min_ = std::max(pull_big_min_, tn_.pull_warp_min);
+        pull_big_chunk_ = tn_.pull_big_chunk > 0 ? tn_.pull_big_chunk : std::max(32, pull_big_min_ / 4);
     }
 
     int ndev = 0;
@@ -227,23 +231,25 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     if (outlists_) { ins_posB_.alloc((size_t)Nb_); jobsB_.alloc((size_t)Nb_); }
     if (dense_) {
         for (int i = 0; i < 2; ++i) {
-            x_[i].alloc((size_t)V_ * Sp_);
-            DPPR_CUDA(cudaMemsetAsync(x_[i].ptr, 0, x_[i].bytes(), st_));  // the padding columns stay zero for good
+            x_[i].alloc((size_t)V_ * Sr_ + 8);
+            DPPR_CUDA(cudaMemsetAsync(x_[i].ptr, 0, x_[i].bytes(), st_));
         }
-        tile_list_.alloc((size_t)div_up(V_, kThreads >> pull_gshift_) * (Sp_ == 1 ? 1 : (Sp_ / 4) >> pull_gshift_));
-        bigcap_ = (uint32_t)std::min<int64_t>((Ew_ / tn_.pull_big_min + 64) * (Sp_ == 1 ? 1 : Sp_ / 4), 1 << 24);
+        const int lanes_sources = S_ == 1 ? 1 : 8 << pull_gshift_;                 // sources one pass over a vertex covers
+        const int n_cg = (int)((Sr_ + lanes_sources - 1) / lanes_sources);          // chunk groups
+        tile_list_.alloc((size_t)div_up(V_, kThreads >> pull_gshift_) * n_cg);
+        bigcap_ = (uint32_t)std::min<int64_t>((Ew_ / pull_big_min_ + 64) * n_cg, 1 << 24);
         big_.alloc(bigcap_);
-        bigacc_.alloc((size_t)bigcap_ * 4 << pull_gshift_);
+        bigacc_.alloc((size_t)bigcap_ * lanes_sources);
         DPPR_CUDA(cudaMemsetAsync(bigacc_.ptr, 0, bigacc_.bytes(), st_));
     }
     seg_d0_.alloc((size_t)Nb_);
-    delta_.alloc((size_t)Nb_ * S_);
+    delta_.alloc((size_t)Nb_ * Sr_);
     DPPR_CUDA(cudaMemsetAsync(delta_.ptr, 0, delta_.bytes(), st_));
     DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, counters_.bytes(), st_));
     // state
-    p_.alloc((size_t)Vp_ * S_);
-    r_.alloc((size_t)Vp_ * S_);
-    if (cfg_.variant >= DPPR_EAGER) status_.alloc((size_t)Vp_ * S_);
+    p_.alloc((size_t)V_ * Sr_);
+    r_.alloc((size_t)V_ * Sr_);
+    if (cfg_.variant >= DPPR_EAGER) status_.alloc((size_t)V_ * Sr_);
     src_.alloc((size_t)S_);
     DPPR_CUDA(cudaMemcpyAsync(src_.ptr, sources_.data(), sizeof(int32_t) * S_, cudaMemcpyHostToDevice, st_));
     // push queues: a frontier holds each (source, vertex) at most once
@@ -532,7 +538,7 @@ void Engine::launch_push(bool init_mode) {
     PushArgs a{};
     a.vmeta = vmeta_.ptr; a.pool = pool_.ptr; a.outdeg = outdeg_.ptr;
     a.p = p_.ptr; a.r = r_.ptr; a.status = status_.ptr;
-    a.Vp = Vp_; a.S = S_; a.src = src_.ptr;
+    a.Sr = Sr_; a.S = S_; a.src = src_.ptr;
     for (int i = 0; i < 2; ++i) { a.q[i] = q_[i].ptr; a.qr[i] = qr_[i].ptr; a.hub[i] = hub_[i].ptr; }
     a.qcap = qcap_; a.hcap = hcap_;
     a.cand = segB_.vertex; a.ncand = segB_.count;
@@ -550,17 +556,18 @@ void Engine::launch_push(bool init_mode) {
     a.avg_indeg = (float)((double)Ew_ / (double)V_);
     a.vmeta_out = outlists_ ? vmeta_out_.ptr : vmeta_.ptr;
     a.x[0] = x_[0].ptr; a.x[1] = x_[1].ptr;
-    a.Sp = Sp_; a.pull_gshift = pull_gshift_;
+    a.pull_gshift = pull_gshift_;
     // cost model: a sweep reads every out-list entry and every vertex row once, whatever the frontier; a scatter
     // iteration pays one random atomic per traversed in-edge.  Measured ratio ~ DPPR_DENSE_DIV (3): Twitter-shaped
     // 3.3 ms per sweep vs 17 edges/ns scattered; Orkut/4 97 us vs 40 edges/ns.
     a.dense_enter_edges = ~0ull;
     if (dense_) a.dense_enter_edges = (unsigned long long)std::max(1.0, ((double)Ew_ + 2.0 * (double)V_) * (double)S_ / tn_.dense_div);
     a.dense_exit_edges = a.dense_enter_edges / 2;
-    a.pull_warp_min = tn_.pull_warp_min; a.pull_cta_min = tn_.pull_cta_min; a.pull_big_min = tn_.pull_big_min;
+    a.pull_warp_min = tn_.pull_warp_min; a.pull_big_min = pull_big_min_; a.pull_big_chunk = pull_big_chunk_;
     a.big = big_.ptr; a.bigcap = bigcap_; a.bigacc = bigacc_.ptr; a.tile_list = tile_list_.ptr;
     {
-        const uint64_t ntiles = (uint64_t)div_up(V_, kThreads >> pull_gshift_) * (Sp_ == 1 ? 1 : (Sp_ / 4) >> pull_gshift_);
+        const int lanes_sources = S_ == 1 ? 1 : 8 << pull_gshift_;
+        const uint64_t ntiles = (uint64_t)div_up(V_, kThreads >> pull_gshift_) * (uint64_t)((Sr_ + lanes_sources - 1) / lanes_sources);
         auto gcd = [](uint64_t x, uint64_t y) { while (y) { const uint64_t t = x % y; x = y; y = t; } return x; };
         uint64_t k = std::max<uint64_t>(1, (uint64_t)(0.6180339887 * (double)ntiles)) | 1ull;
         while (gcd(k, ntiles) != 1) k += 2;
@@ -650,7 +657,7 @@ void Engine::solve_initial() {
     batch_pending_ = false;
     begin_batch(0, 0);
     record(0);
-    state_init<<<grid_for(Vp_ * S_), kThreads, 0, st_>>>(p_.ptr, r_.ptr, status_.ptr, Vp_, S_, src_.ptr); ++launch_counter();
+    state_init<<<grid_for((int64_t)V_ * Sr_), kThreads, 0, st_>>>(p_.ptr, r_.ptr, status_.ptr, V_, Sr_, S_, src_.ptr); ++launch_counter();
     DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, sizeof(PushCtrl), st_));
     DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, counters_.bytes(), st_));
     step_level_ = 0;
@@ -816,10 +823,14 @@ void Engine::refresh(bool repair_only) {
     if (!batch_pending_) throw StateError("dppr_refresh without a preceding dppr_apply_batch");
     DPPR_CUDA(cudaSetDevice(dev_));
     const int64_t n = cur().entries;
-    dim3 g((unsigned)std::min(grid_for(n), 8 * sm_count_), (unsigned)S_);
-    repair_accumulate<<<g, kThreads, 0, st_>>>(sb_val_, n, segB_.segof, p_.ptr, Vp_, delta_.ptr, Nb_); ++launch_counter();
-    repair_finalize<<<grid_for(n * S_), kThreads, 0, st_>>>(segB_, seg_d0_.ptr, src_.ptr, S_, p_.ptr, r_.ptr, Vp_,
-                                                          delta_.ptr, Nb_, cfg_.alpha); ++launch_counter();
+    if (S_ == 1) {
+        repair_accumulate<<<std::min(grid_for(n), 8 * sm_count_), kThreads, 0, st_>>>(sb_val_, n, segB_.segof, p_.ptr, delta_.ptr); ++launch_counter();
+    } else {
+        dim3 g((unsigned)std::max(1, std::min(div_up(n, 32 * kWarps), 8 * sm_count_)), (unsigned)div_up(S_, 32 * kRepairCols));
+        repair_accumulate_rows<<<g, kThreads, 0, st_>>>(sb_val_, n, segB_.segof, p_.ptr, Sr_, S_, delta_.ptr); ++launch_counter();
+    }
+    repair_finalize<<<grid_for(n * S_), kThreads, 0, st_>>>(segB_, seg_d0_.ptr, src_.ptr, S_, Sr_, p_.ptr, r_.ptr, delta_.ptr,
+                                                          cfg_.alpha); ++launch_counter();
     DPPR_CUDA(cudaGetLastError());
     record(3);
     if (!repair_only) launch_push(false);
@@ -886,14 +897,14 @@ void Engine::get_vector(int which, int32_t s, double *out) {
     if (s < 0 || s >= S_) throw InvalidArgument("source index out of range");
     if (!solved_) throw StateError("no estimates before dppr_solve_initial");
     sync();
-    const double *src = (which == 0 ? p_.ptr : r_.ptr) + (size_t)s * Vp_;
-    if (!perm_.ptr) {
+    const double *src = (which == 0 ? p_.ptr : r_.ptr) + s;  // vertex-major: element v of source s at v * Sr_ + s
+    if (!perm_.ptr && Sr_ == 1) {
         DPPR_CUDA(cudaMemcpy(out, src, sizeof(double) * (size_t)V_, cudaMemcpyDeviceToHost));
         return;
     }
     DevBuf<double> tmp;
     tmp.alloc((size_t)V_);
-    gather_by_perm<double><<<grid_for(V_), kThreads, 0, st_>>>(src, 1, perm_.ptr, tmp.ptr, V_); ++launch_counter();
+    gather_by_perm<double><<<grid_for(V_), kThreads, 0, st_>>>(src, Sr_, perm_.ptr, tmp.ptr, V_); ++launch_counter();
     DPPR_CUDA(cudaStreamSynchronize(st_));
     DPPR_CUDA(cudaMemcpy(out, tmp.ptr, sizeof(double) * (size_t)V_, cudaMemcpyDeviceToHost));
 }
@@ -902,7 +913,7 @@ void Engine::copy_estimates_device(int32_t s, void *dptr) {
     if (!dptr) throw InvalidArgument("null device pointer");
     if (s < 0 || s >= S_) throw InvalidArgument("source index out of range");
     DPPR_CUDA(cudaSetDevice(dev_));
-    gather_by_perm<double><<<grid_for(V_), kThreads, 0, st_>>>(p_.ptr + (size_t)s * Vp_, 1, perm_.ptr, (double *)dptr, V_); ++launch_counter();
+    gather_by_perm<double><<<grid_for(V_), kThreads, 0, st_>>>(p_.ptr + s, Sr_, perm_.ptr, (double *)dptr, V_); ++launch_counter();
     DPPR_CUDA(cudaStreamSynchronize(st_));
 }
 
@@ -914,9 +925,9 @@ void Engine::set_state(int32_t s, const double *p, const double *r) {
     for (int which = 0; which < 2; ++which) {
         const double *h = which == 0 ? p : r;
         if (!h) continue;
-        double *dst = (which == 0 ? p_.ptr : r_.ptr) + (size_t)s * Vp_;
+        double *dst = (which == 0 ? p_.ptr : r_.ptr) + s;
         DPPR_CUDA(cudaMemcpy(tmp.ptr, h, sizeof(double) * (size_t)V_, cudaMemcpyHostToDevice));
-        scatter_by_perm<double><<<grid_for(V_), kThreads, 0, st_>>>(tmp.ptr, perm_.ptr, dst, V_); ++launch_counter();
+        scatter_by_perm<double><<<grid_for(V_), kThreads, 0, st_>>>(tmp.ptr, perm_.ptr, dst, Sr_, V_); ++launch_counter();
         DPPR_CUDA(cudaStreamSynchronize(st_));
     }
     solved_ = true;
@@ -1022,17 +1033,17 @@ void Engine::validate(int32_t s, double *max_abs_residual, double *max_invariant
     DevBuf<unsigned long long> out;
     out.alloc(2);
     DPPR_CUDA(cudaMemsetAsync(out.ptr, 0, out.bytes(), st_));
-    const double *p = p_.ptr + (size_t)s * Vp_, *r = r_.ptr + (size_t)s * Vp_;
-    val_residual_max<<<grid_for(V_), kThreads, 0, st_>>>(r, V_, out.ptr); ++launch_counter();
+    const double *p = p_.ptr + s, *r = r_.ptr + s;
+    val_residual_max<<<grid_for(V_), kThreads, 0, st_>>>(r, Sr_, V_, out.ptr); ++launch_counter();
     DevBuf<double> acc;
     if (max_invariant_defect) {
         acc.alloc((size_t)V_);
         DPPR_CUDA(cudaMemsetAsync(acc.ptr, 0, acc.bytes(), st_));
-        val_out_sums<<<grid_for((int64_t)V_ * 32), kThreads, 0, st_>>>(vmeta_.ptr, pool_.ptr, p, V_, acc.ptr); ++launch_counter();
+        val_out_sums<<<grid_for((int64_t)V_ * 32), kThreads, 0, st_>>>(vmeta_.ptr, pool_.ptr, p, Sr_, V_, acc.ptr); ++launch_counter();
         int32_t hsrc = 0;
         DPPR_CUDA(cudaMemcpyAsync(&hsrc, src_.ptr + s, sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
         DPPR_CUDA(cudaStreamSynchronize(st_));
-        val_invariant<<<grid_for(V_), kThreads, 0, st_>>>(p, r, outdeg_.ptr, acc.ptr, V_, hsrc, cfg_.alpha, out.ptr + 1); ++launch_counter();
+        val_invariant<<<grid_for(V_), kThreads, 0, st_>>>(p, r, Sr_, outdeg_.ptr, acc.ptr, V_, hsrc, cfg_.alpha, out.ptr + 1); ++launch_counter();
     }
     DPPR_CUDA(cudaGetLastError());
     unsigned long long h[2] = {0, 0};
@@ -1060,7 +1071,7 @@ void Engine::topk(int32_t first, int32_t n, int32_t k, int32_t *ids, double *val
     }
     for (int32_t lo = 0; lo < n; lo += 32768) {  // (grid.y limit)
         const int32_t m = std::min<int32_t>(32768, n - lo);
-        topk_partial<<<dim3((unsigned)slices, (unsigned)m), kThreads, 0, st_>>>(p_.ptr, Vp_, V_, first + lo, inv_.ptr, k,
+        topk_partial<<<dim3((unsigned)slices, (unsigned)m), kThreads, 0, st_>>>(p_.ptr, Sr_, V_, first + lo, inv_.ptr, k,
                                                                               topk_key_.ptr + (size_t)lo * slices * k,
                                                                               topk_id_.ptr + (size_t)lo * slices * k); ++launch_counter();
     }

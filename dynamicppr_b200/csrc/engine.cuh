@@ -39,7 +39,7 @@ struct Tuning {
     int ctas_per_sm = 4, tile_cap = 128, max_iters = 400000;
     int dense = 0;  // 0 auto, 1 always the switching kernel, -1 scatter only
     double dense_div = 4.0, dense_min_edges = 2.0e7;
-    int pull_group = 8, pull_warp_min = 32, pull_cta_min = 1024, pull_big_min = 65536;
+    int pull_group = 32, pull_warp_min = 32, pull_big_min = 0, pull_big_chunk = 0;  // (0: by the number of sources)
     double carry_gamma = 1.0, carry_scale = 0.01;
     int window_path = 0;  // 0 auto, 1 multi-kernel only, 2 cooperative or multi-kernel (no single-CTA kernel)
     bool iterlog = false;
@@ -117,7 +117,7 @@ private:
     int dev_ = 0, sm_count_ = 0, coop_grid_[4] = {0, 0, 0, 0}, mode_ = 0;
     cudaStream_t st_ = nullptr;
     int32_t V_ = 0;
-    int64_t Vp_ = 0, W_ = 0, Ew_ = 0, Bmax_ = 0, Nb_ = 0;
+    int64_t Sr_ = 1, W_ = 0, Ew_ = 0, Bmax_ = 0, Nb_ = 0;  // Sr_: row stride of the vertex-major state (1, or S rounded up to 8)
     int D_ = 1, S_ = 1, key_bits_ = 1;
     bool window_ready_ = false, solved_ = false, batch_pending_ = false;
     int64_t log_start_ = 0;
@@ -141,11 +141,12 @@ private:
     DevBuf<uint4> vmeta_out_;       // out-lists of a directed graph (undirected: the in-lists serve)
     DevBuf<uint32_t> ins_posB_;
     DevBuf<RelocJob> jobsB_;
-    DevBuf<double> x_[2], bigacc_;
+    DevBuf<uint16_t> x_[2];
+    DevBuf<double> bigacc_;
     DevBuf<HubItem> big_;
     DevBuf<uint32_t> tile_list_;
     uint32_t bigcap_ = 0;
-    int Sp_ = 1, pull_gshift_ = 0;
+    int pull_gshift_ = 0, pull_big_min_ = 0, pull_big_chunk_ = 0;
     bool dense_ = false, outlists_ = false;
     unsigned long long pool_cap_ = 0;
     // batch scratch

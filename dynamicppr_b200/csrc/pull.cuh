@@ -1,134 +1,200 @@
 // pull.cuh -- DENSE iterations of the level-synchronous push, executed in gather ("pull") form.
 //
-// One level-synchronous iteration of variant 0 (push.cuh) pops every frontier vertex u -- ru = r[u], r[u] = 0,
-// p[u] += a ru -- and adds (1-a) ru / (outdeg(w)+1) to r[w] of every in-neighbour w: one random FP64 atomic per
-// traversed edge.  When the frontier covers a large part of the graph the same iteration is cheaper the other
-// way round: publish the popped residuals as a dense vector x (x[u] = ru for frontier vertices, 0 elsewhere) and
-// let every vertex w GATHER
-//     r'[w] = (popped ? 0 : r[w]) + (1-a) / (outdeg(w)+1) * sum_{u in out(w)} x[u]
-// from its OUT-list.  No atomics, no frontier queue, no owner search; each (w, source) is written by exactly one
-// thread; per edge one 8-byte read of x (a 32-byte sector for 4 sources at once when several sources share the
-// launch: x is vertex-major).  The reference has no counterpart (it always scatters, gpu/ExpandRev.cuh); the
-// iteration is the same Jacobi step, so the residual bound and the estimates are those of the push form up to the
-// order of the floating-point sums.
+// One level-synchronous iteration of variant 0 (push.cuh) pops every frontier vertex u -- p[u] += a x, r[u] -= x for the
+// popped amount x -- and adds (1-a) x / (outdeg(w)+1) to r[w] of every in-neighbour w: one random FP64 atomic per
+// traversed edge.  When the frontier covers a large part of the graph the same iteration is cheaper the other way
+// round: publish the popped amounts as a dense vector x (0 for vertices outside the frontier) and let every vertex w
+// GATHER
+//     r'[w] = r[w] + (1-a) / (outdeg(w)+1) * sum_{u in out(w)} x[u]
+// from its OUT-list.  No atomics, no frontier queue, no owner search; each (w, source) is written by exactly one lane.
+// The reference has no counterpart (it always scatters, gpu/ExpandRev.cuh).
 //
-// The pop is deferred by one sweep: sweep k leaves x_next[w] = r'[w] where r'[w] is legal (p[w] is untouched, and
-// r[w] is not even written: a non-zero x entry IS the residual while the episode lasts), and sweep k+1 -- or nobody,
-// if the loop goes back to scatter mode -- performs p[w] += a x[w], r[w] = 0 for it.  Leaving dense mode is therefore
-// just a compaction of the non-zero x entries into an ordinary (un-popped) frontier queue, which also writes them
-// back to r.
+// Round 2 rewrite (ncu on BASELINE configs[3], 125 sources: 29 % of DRAM peak, 5.2 G spill loads, barrier and
+// long-scoreboard stalls; scripts/micro/gather.cu: random rows >= 256 B stream at 5-7 TB/s, anything narrower is bound
+// by ~25 rows/ns):
 //
-// Work split by out-degree: see pull_sweep.  The longest lists (big_min or more entries) are cut into chunks dealt
-// to all CTAs, their partial sums meet in `bigacc` and the vertex is finished after one more grid barrier.
+//   * x holds bf16 values.  A push may move ANY part of a residual and keeps the invariant
+//     (p + a r = a e_s + (1-a)/(d+1) sum p), so a sweep pops the residual TRUNCATED TOWARDS ZERO to bf16 and
+//     leaves the remainder (< 2^-7 of it, same sign) in r, where it is popped by a later sweep if it is still above eps.
+//     Every gathered value is exactly what was added to p / a, the sums are formed in FP64: the invariant stays exact to
+//     rounding, the contraction per sweep goes from 0.85 to ~0.854, and the gather traffic -- the dominant term -- drops
+//     4x (2 instead of 8 bytes per (edge, source)).  With one source the whole x vector of the Twitter-shaped window is
+//     83 MB and stays L2-resident (126 MB) instead of being a 333 MB random-sector DRAM stream.
+//   * p, r and x are VERTEX-major ([V][Sr]): the lanes that share a vertex read one contiguous row piece per out-list
+//     entry (16 B = 8 sources per lane, up to 32 lanes = 512 B per request), and the per-vertex work (r row, p row, x
+//     row) is coalesced too.
+//   * no CTA-wide barrier in a sweep: a WARP owns 32 / G consecutive vertices (G = lanes per vertex).  Short lists are
+//     walked by the owning lane group with kPullUnroll independent gathers in flight; lists of warp_min or more entries
+//     are walked by the whole warp and reduced by shuffles; lists of big_min or more entries are cut into chunks that any
+//     warp of the grid takes, partial sums meet in `bigacc` by FP64 atomics and the warp that completes the last chunk
+//     finishes the vertex.  One grid barrier per sweep.
+//   * the pop is still deferred by one sweep: sweep k decides x_next[w]; sweep k+1 adds a x to p[w].  Leaving dense mode
+//     gives the undelivered x back to r and compacts those entries into an ordinary (un-popped) frontier queue.
 //
 // Included by push.cuh (needs PushArgs / PushSmem / the grid barrier).
 #pragma once
 
 namespace dppr {
 
-constexpr int kPullBigChunk = 16 * kThreads;     // out-edges per grid-tier chunk
+#ifndef DPPR_PULL_UNROLL
+#define DPPR_PULL_UNROLL 8
+#endif
+constexpr int kPullUnroll = DPPR_PULL_UNROLL;   // independent row gathers in flight per lane
+
+// ---- bf16 pop amounts ----------------------------------------------------------------------------------------------
+// truncation towards zero: |x| <= |r| and the remainder keeps the sign of r (a phase never creates residual of the
+// other sign); values below the smallest normal float are not popped (they stay in r)
+__device__ __forceinline__ uint32_t bf16_trunc(double r) {
+    const uint32_t f = __float_as_uint(__double2float_rz(r)) >> 16;
+    return (f & 0x7f80u) ? f : 0u;
+}
+__device__ __forceinline__ double bf16_value(uint32_t h) { return (double)__uint_as_float(h << 16); }
 
 // x is gathered at random and re-read every sweep: keep it in L2 (evict_last), and let everything that merely streams
-// through -- out-list slots, ring metadata, r / p rows -- leave first (ld.cs / st.cs).  ncu on the Twitter-shaped graph:
-// 50 % L2 hit rate with default policies, DRAM at its random-sector ceiling (~1.3 TB/s).
+// through -- out-list slots, ring metadata -- leave first (ld.cs)
 __device__ __forceinline__ unsigned long long l2_keep_policy() {
     unsigned long long pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-template <class T> __device__ __forceinline__ T pl_ldcs(const T *p);
 #ifndef DPPR_PULL_HINTS
-#define DPPR_PULL_HINTS 3   // bit 0: streaming (evict-first) loads / stores, bit 1: evict_last gathers of x
+#define DPPR_PULL_HINTS 3   // bit 0: streaming (evict-first) loads of slots / metadata, bit 1: evict_last gathers of x
 #endif
-__device__ __forceinline__ double ld_keep(const double *p) {
-    if (!(DPPR_PULL_HINTS & 2)) return *p;
-    double v;
-    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(l2_keep_policy()));
-    return v;
-}
-__device__ __forceinline__ double2 ld_keep2(const double2 *p) {
-    if (!(DPPR_PULL_HINTS & 2)) return *p;
-    double2 v;
-    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(l2_keep_policy()));
-    return v;
-}
-
 template <class T> __device__ __forceinline__ T pl_ldcs(const T *p) { return (DPPR_PULL_HINTS & 1) ? __ldcs(p) : __ldcg(p); }
-template <class T> __device__ __forceinline__ void pl_stcs(T *p, T v) { if (DPPR_PULL_HINTS & 1) __stcs(p, v); else __stcg(p, v); }
 
-template <int SB>
-__device__ __forceinline__ void pull_gather(const double *x, uint32_t u, uint32_t Sp, uint32_t s0, double (&acc)[SB],
-                                            uint32_t &nz) {
-    if (SB == 1) {
-        const double v = ld_keep(&x[u]);
-        acc[0] += v;
-        nz += (v != 0.0) ? 1u : 0u;
-    } else {
-        const double2 *px = reinterpret_cast<const double2 *>(x + (size_t)u * Sp + s0);
-#pragma unroll
-        for (int j = 0; j < SB / 2; ++j) {
-            const double2 v = ld_keep2(&px[j]);
-            acc[2 * j] += v.x;
-            acc[2 * j + 1] += v.y;
-            nz += ((v.x != 0.0) ? 1u : 0u) + ((v.y != 0.0) ? 1u : 0u);
-        }
+// a lane's piece of an x row: SB = 1 -> one bf16 (single source), SB = 8 -> 16 bytes
+template <int SB> struct XPiece;
+template <> struct XPiece<1> {
+    uint32_t h;
+    __device__ __forceinline__ bool any() const { return h != 0u; }
+    __device__ __forceinline__ uint32_t get(int) const { return h; }
+};
+template <> struct XPiece<8> {
+    uint4 v;
+    __device__ __forceinline__ bool any() const { return (v.x | v.y | v.z | v.w) != 0u; }
+    __device__ __forceinline__ uint32_t get(int j) const {
+        const uint32_t w = j < 2 ? v.x : j < 4 ? v.y : j < 6 ? v.z : v.w;
+        return (j & 1) ? (w >> 16) : (w & 0xffffu);
     }
+};
+template <int SB> __device__ __forceinline__ XPiece<SB> x_zero();
+template <> __device__ __forceinline__ XPiece<1> x_zero<1>() { return XPiece<1>{0u}; }
+template <> __device__ __forceinline__ XPiece<8> x_zero<8>() { return XPiece<8>{make_uint4(0u, 0u, 0u, 0u)}; }
+
+// gathered at random (evict_last)
+template <int SB> __device__ __forceinline__ XPiece<SB> x_gather(const uint16_t *x, size_t elem);
+template <> __device__ __forceinline__ XPiece<1> x_gather<1>(const uint16_t *x, size_t elem) {
+    unsigned short h;
+    if (DPPR_PULL_HINTS & 2) asm volatile("ld.global.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(h) : "l"(x + elem), "l"(l2_keep_policy()));
+    else h = x[elem];
+    return XPiece<1>{(uint32_t)h};
+}
+template <> __device__ __forceinline__ XPiece<8> x_gather<8>(const uint16_t *x, size_t elem) {
+    uint4 v;
+    if (DPPR_PULL_HINTS & 2)
+        asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(x + elem), "l"(l2_keep_policy()));
+    else v = *reinterpret_cast<const uint4 *>(x + elem);
+    return XPiece<8>{v};
+}
+// the vertex's own row piece (streamed)
+template <int SB> __device__ __forceinline__ XPiece<SB> x_load(const uint16_t *x, size_t elem);
+template <> __device__ __forceinline__ XPiece<1> x_load<1>(const uint16_t *x, size_t elem) { return XPiece<1>{(uint32_t)__ldcg(x + elem)}; }
+template <> __device__ __forceinline__ XPiece<8> x_load<8>(const uint16_t *x, size_t elem) { return XPiece<8>{__ldcg(reinterpret_cast<const uint4 *>(x + elem))}; }
+template <int SB> __device__ __forceinline__ void x_store(uint16_t *x, size_t elem, const uint32_t (&h)[SB]);
+template <> __device__ __forceinline__ void x_store<1>(uint16_t *x, size_t elem, const uint32_t (&h)[1]) { __stcg(x + elem, (uint16_t)h[0]); }
+template <> __device__ __forceinline__ void x_store<8>(uint16_t *x, size_t elem, const uint32_t (&h)[8]) {
+    __stcg(reinterpret_cast<uint4 *>(x + elem), make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16)));
 }
 
 template <int SB>
-__device__ __forceinline__ void pull_load_x(const double *x, uint32_t w, uint32_t Sp, uint32_t s0, double (&xc)[SB]) {
-    if (SB == 1) {
-        xc[0] = __ldcg(&x[w]);
-    } else {
-        const double2 *px = reinterpret_cast<const double2 *>(x + (size_t)w * Sp + s0);
-#pragma unroll
-        for (int j = 0; j < SB / 2; ++j) {
-            const double2 v = __ldcg(&px[j]);
-            xc[2 * j] = v.x;
-            xc[2 * j + 1] = v.y;
-        }
-    }
-}
-
-// everything that happens once per (vertex, source): deferred pop, new residual, membership in the next frontier
-template <int SB>
-__device__ __forceinline__ uint32_t pull_finish_unit(const PushArgs &a, int phase, uint32_t w, uint32_t s0, uint32_t len,
-                                                     const double (&xc)[SB], const double (&acc)[SB], double *xn,
-                                                     unsigned long long &next_edges) {
-    uint32_t legal = 0;
-    double out[SB];
-    const double scale = (1.0 - a.alpha) / (double)(len + 1u);
+__device__ __forceinline__ void x_accumulate(const XPiece<SB> &v, double (&acc)[SB], uint32_t &nz) {
 #pragma unroll
     for (int j = 0; j < SB; ++j) {
-        out[j] = 0.0;
-        const uint32_t s = s0 + j;
-        if (s < (uint32_t)a.S && (len != 0u || xc[j] != 0.0)) {
-            // During a dense episode a non-zero x entry IS the residual (r[w] is stale until pull_compact restores it):
-            // a vertex that stays in the frontier sweep after sweep -- the steady state -- touches r not at all.
-            const size_t idx = (size_t)s * a.Vp + w;
-            double rw;
-            if (xc[j] != 0.0) {  // w is in the frontier of this sweep: its pop
-                pl_stcs(&a.p[idx], pl_ldcs(&a.p[idx]) + a.alpha * xc[j]);
-                rw = 0.0;
+        const uint32_t h = v.get(j);
+        acc[j] += bf16_value(h);
+        nz += h ? 1u : 0u;
+    }
+}
+
+// ---- geometry ------------------------------------------------------------------------------------------------------
+// A unit = (vertex w, SB sources starting at s0).  G = 2^gshift adjacent lanes share a vertex (their pieces are contiguous);
+// a warp holds 32 / G consecutive vertices, a tile (the granularity of the active-tile list) kThreads / G of them; rows
+// wider than SB * G sources are covered by several chunk groups, each with its own tiles.
+struct PullGeom {
+    uint32_t gs, G, vpw, vpt, nCG, tpc, ntiles;
+};
+template <int SB>
+__device__ __forceinline__ PullGeom pull_geom(const PushArgs &a) {
+    PullGeom q;
+    q.gs = SB == 1 ? 0u : (uint32_t)a.pull_gshift;
+    q.G = 1u << q.gs;
+    q.vpw = 32u >> q.gs;
+    q.vpt = (uint32_t)kThreads >> q.gs;
+    q.nCG = SB == 1 ? 1u : ((uint32_t)a.Sr + SB * q.G - 1u) / (SB * q.G);
+    q.tpc = ((uint32_t)a.V + q.vpt - 1u) / q.vpt;
+    q.ntiles = q.tpc * q.nCG;
+    return q;
+}
+
+constexpr uint32_t kBigDone = 0, kBigChunks = 1, kBigLen = 2;   // HubItem::pad slots used by the grid tier
+
+// everything that happens once per unit: the deferred pop, the new residual, membership in the next frontier.
+// Returns the number of sources of the unit that are in the next frontier.
+template <int SB>
+__device__ __forceinline__ uint32_t pull_finish_unit(const PushArgs &a, int phase, uint32_t w, uint32_t s0, uint32_t len,
+                                                     const XPiece<SB> &xc, const double (&acc)[SB], uint16_t *xn,
+                                                     unsigned long long &next_edges) {
+    const size_t row = (size_t)w * (size_t)a.Sr + s0;
+    uint32_t out[SB];
+    bool touched = xc.any();
+#pragma unroll
+    for (int j = 0; j < SB; ++j) { out[j] = 0u; touched |= acc[j] != 0.0; }
+    uint32_t legal = 0;
+    if (touched) {
+        const double scale = (1.0 - a.alpha) / (double)(len + 1u);
+        if (xc.any()) {  // the pop decided by the previous sweep
+            if (SB == 1) {
+                a.p[row] += a.alpha * bf16_value(xc.get(0));
             } else {
-                rw = pl_ldcs(&a.r[idx]);
-            }
-            rw += acc[j] * scale;
-            if (legal_push(rw, phase, a.eps)) {
-                out[j] = rw;
-                ++legal;
-            } else {
-                pl_stcs(&a.r[idx], rw);
+#pragma unroll
+                for (int j = 0; j < SB; j += 2) {
+                    double2 pv = *reinterpret_cast<double2 *>(a.p + row + j);
+                    pv.x += a.alpha * bf16_value(xc.get(j));
+                    pv.y += a.alpha * bf16_value(xc.get(j + 1));
+                    *reinterpret_cast<double2 *>(a.p + row + j) = pv;
+                }
             }
         }
-    }
-    if (SB == 1) {
-        __stcg(&xn[w], out[0]);
-    } else {
-        double2 *px = reinterpret_cast<double2 *>(xn + (size_t)w * a.Sp + s0);
+        double rw[SB];
+        if (SB == 1) {
+            rw[0] = a.r[row];
+        } else {
 #pragma unroll
-        for (int j = 0; j < SB / 2; ++j) __stcg(&px[j], make_double2(out[2 * j], out[2 * j + 1]));
+            for (int j = 0; j < SB; j += 2) {
+                const double2 rv = *reinterpret_cast<const double2 *>(a.r + row + j);
+                rw[j] = rv.x; rw[j + 1] = rv.y;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < SB; ++j) {
+            rw[j] += acc[j] * scale;
+            if (legal_push(rw[j], phase, a.eps)) {
+                const uint32_t h = bf16_trunc(rw[j]);
+                if (h) {
+                    out[j] = h;
+                    rw[j] -= bf16_value(h);  // the remainder stays behind
+                    ++legal;
+                }
+            }
+        }
+        if (SB == 1) {
+            a.r[row] = rw[0];
+        } else {
+#pragma unroll
+            for (int j = 0; j < SB; j += 2) *reinterpret_cast<double2 *>(a.r + row + j) = make_double2(rw[j], rw[j + 1]);
+        }
     }
+    x_store<SB>(xn, row, out);
     if (legal)  // what a scatter iteration would traverse for w: its in-degree, once per legal source
         next_edges += (unsigned long long)legal * (a.vmeta_out == a.vmeta ? len : __ldg(&a.vmeta[w]).z);
     return legal;
@@ -152,79 +218,72 @@ __device__ __forceinline__ void pull_count_flush(PushSmem &sm, uint32_t mine, un
     }
 }
 
-// Work unit of the dense passes: (vertex w, chunk of SB sources).  With several sources, G = 2^pull_gshift ADJACENT
-// lanes take the G chunks of one chunk group of the same vertex: their 32-byte gathers of a neighbour's row then form one
-// contiguous G*32-byte request (HBM bursts are 64 bytes: a lone 32-byte sector wastes half of one), and the slot loads
-// are a broadcast.  A tile is kThreads / G consecutive vertices x one chunk group.
-struct PullUnit {
-    uint32_t w, s0, g;
-};
-template <int SB>
-__device__ __forceinline__ uint32_t pull_gshift(const PushArgs &a) { return SB == 1 ? 0u : (uint32_t)a.pull_gshift; }
-template <int SB>
-__device__ __forceinline__ uint32_t pull_tiles_per_group(const PushArgs &a) {
-    const uint32_t vpt = (uint32_t)kThreads >> pull_gshift<SB>(a);
-    return ((uint32_t)a.V + vpt - 1) / vpt;
-}
-template <int SB>
-__device__ __forceinline__ PullUnit pull_unit(const PushArgs &a, uint32_t tile, uint32_t tpc, uint32_t &cg) {
-    const uint32_t gs = pull_gshift<SB>(a), G = 1u << gs;
-    cg = tile / tpc;
-    const uint32_t g = threadIdx.x & (G - 1u);
-    return PullUnit{(tile - cg * tpc) * ((uint32_t)kThreads >> gs) + (threadIdx.x >> gs), ((cg << gs) + g) * SB, g};
-}
-
-// entering dense mode: x[0][w] = r[w] where legal, 0 elsewhere; x[1][w] = 0.  Also lists the ACTIVE tiles: a vertex
-// without out-edges receives no adds, so a tile whose 256 vertices have neither out-edges nor a legal residual now
-// stays all-zero in both x buffers for the whole episode and is never visited again.  With the degree-sorted internal
-// order most vertices of a power-law window sit in such tiles (72 % on the Twitter-shaped window).
-// Tiles are visited -- and therefore listed -- in a scrambled order: the heavy tiles (heads of the relabel blocks)
-// sit at a regular stride, which would otherwise hand all of them to the same few CTAs in the sweeps.
+// ---- entering dense mode ---------------------------------------------------------------------------------------------
+// x[0][w] = the part of r[w] that the first sweep pops (where r[w] is legal), the rest stays in r; x[1] = 0.  Also lists
+// the ACTIVE tiles -- a vertex without out-edges receives no adds, so a tile whose vertices have neither out-edges nor a
+// legal residual stays all-zero in both x buffers for the whole episode and is never visited again (72 % of the
+// Twitter-shaped window's vertices) -- and the grid tier: the (vertex, chunk group) pairs whose out-list is cut into chunks.
+// Tiles are listed in a scrambled order: the heavy ones (heads of the relabel blocks) sit at a regular stride.
 template <int SB>
 __device__ void pull_build(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, unsigned int *cnt_out) {
-    const uint32_t V = (uint32_t)a.V, nCG = ((uint32_t)a.Sp / SB) >> pull_gshift<SB>(a);
-    const uint32_t tpc = pull_tiles_per_group<SB>(a), ntiles = tpc * nCG;
+    const PullGeom q = pull_geom<SB>(a);
+    const uint32_t V = (uint32_t)a.V;
     uint32_t legal = 0;
     unsigned long long ep_slots = 0, ep_pairs = 0, ep_units = 0;  // what ONE sweep over the active tiles moves
-    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const uint32_t tile = (uint32_t)(((unsigned long long)t * a.pull_tile_mul) % ntiles);
-        uint32_t cg;
-        const PullUnit un = pull_unit<SB>(a, tile, tpc, cg);
-        const uint32_t w = un.w, s0 = un.s0;
+    for (uint32_t t = blockIdx.x; t < q.ntiles; t += gridDim.x) {
+        const uint32_t tile = (uint32_t)(((unsigned long long)t * a.pull_tile_mul) % q.ntiles);
+        const uint32_t cg = tile / q.tpc;
+        const uint32_t w = (tile - cg * q.tpc) * q.vpt + (threadIdx.x >> q.gs), g = threadIdx.x & (q.G - 1u);
+        const uint32_t s0 = (cg * q.G + g) * SB;
+        const bool have = w < V && s0 < (uint32_t)a.Sr;
         bool active = false;
         uint32_t wlen = 0;
-        if (w < V) {
-            double out[SB];
+        if (have) {
             wlen = (uint32_t)__ldg(&a.outdeg[w]);
             active = wlen != 0;
+            const size_t row = (size_t)w * (size_t)a.Sr + s0;
+            uint32_t out[SB], zero[SB];
+            double rw[SB];
+            bool any = false;
 #pragma unroll
             for (int j = 0; j < SB; ++j) {
-                out[j] = 0.0;
-                if (s0 + j < (uint32_t)a.S) {
-                    const double rw = __ldcg(&a.r[(size_t)(s0 + j) * a.Vp + w]);
-                    if (legal_push(rw, phase, a.eps)) { out[j] = rw; ++legal; active = true; }
+                out[j] = 0u; zero[j] = 0u;
+                rw[j] = __ldcg(&a.r[row + j]);
+                if (legal_push(rw[j], phase, a.eps)) {
+                    const uint32_t h = bf16_trunc(rw[j]);
+                    if (h) { out[j] = h; rw[j] -= bf16_value(h); ++legal; any = true; }
                 }
             }
-            if (SB == 1) {
-                __stcg(&a.x[0][w], out[0]);
-                __stcg(&a.x[1][w], 0.0);
-            } else {
-                double2 *p0 = reinterpret_cast<double2 *>(a.x[0] + (size_t)w * a.Sp + s0);
-                double2 *p1 = reinterpret_cast<double2 *>(a.x[1] + (size_t)w * a.Sp + s0);
+            if (any) {
+                active = true;
 #pragma unroll
-                for (int j = 0; j < SB / 2; ++j) {
-                    __stcg(&p0[j], make_double2(out[2 * j], out[2 * j + 1]));
-                    __stcg(&p1[j], make_double2(0.0, 0.0));
+                for (int j = 0; j < SB; ++j)
+                    if (out[j]) __stcg(&a.r[row + j], rw[j]);
+            }
+            x_store<SB>(a.x[0], row, out);
+            x_store<SB>(a.x[1], row, zero);
+            if (g == 0 && wlen >= (uint32_t)a.pull_big_min) {  // grid tier: one entry per (vertex, chunk group)
+                const uint32_t nch = (wlen + (uint32_t)a.pull_big_chunk - 1u) / (uint32_t)a.pull_big_chunk;
+                const unsigned long long old = atomicAdd(&c->bigpk, (1ull << 32) | nch);
+                const uint32_t hp = (uint32_t)(old >> 32);
+                if (hp < a.bigcap) {
+                    a.big[hp].item = ((unsigned long long)cg << 32) | w;
+                    a.big[hp].chunk0 = (uint32_t)old;
+                    a.big[hp].pad[kBigDone] = 0u;
+                    a.big[hp].pad[kBigChunks] = nch;
+                    a.big[hp].pad[kBigLen] = wlen;
+                } else {
+                    atomicOr(&c->errflags, kErrHubQ);
                 }
             }
         }
         if (__syncthreads_or(active)) {
             if (threadIdx.x == 0) a.tile_list[atomicAdd(&c->ntiles_active, 1u)] = tile;
-            if (w < V && s0 < (uint32_t)a.S) {
-                const uint32_t nreal = min((uint32_t)SB, (uint32_t)a.S - s0);
+            if (have) {
+                const uint32_t nreal = s0 < (uint32_t)a.S ? min((uint32_t)SB, (uint32_t)a.S - s0) : 0u;
                 ep_units += nreal;
                 ep_pairs += (unsigned long long)wlen * nreal;
-                if (un.g == 0) ep_slots += wlen;
+                if (g == 0) ep_slots += wlen;
             }
         }
     }
@@ -242,220 +301,175 @@ __device__ void pull_build(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
     pull_count_flush(sm, legal, cnt_out);
 }
 
-// one sweep.  `gath` counts the gathered x entries that were non-zero: exactly the (edge, source) pairs the push
-// form would have traversed.
-//
-// Work split by out-degree, per tile of 256 consecutive vertices (consecutive internal ids have similar degrees,
-// window.cuh "internal vertex order"):  < warp_min: the owning thread walks its list;  < cta_min: the list goes on a
-// shared list whose entries are dealt to the CTA's warps;  < big_min: the whole CTA walks it;  beyond: grid tier.
-// (An edge-balanced walk with a segmented warp reduction -- the scatter kernel's scheme -- was measured at 207 us
-// per sweep on the Orkut/4 probe against 97 us for this one: the reduction costs more than the imbalance.)
+// ---- list walks ------------------------------------------------------------------------------------------------------
+// entries first, first + step, ... < last of the ring {base, head, mask}: each lane group gathers ITS piece (column c0 of the
+// row) of x[slot], kPullUnroll slots in flight
 template <int SB>
-__device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, const double *xcur, double *xnext,
+__device__ __forceinline__ void pull_walk(const PushArgs &a, const uint16_t *xcur, uint32_t base, uint32_t head, uint32_t mask,
+                                          uint32_t first, uint32_t last, uint32_t step, uint32_t c0, double (&acc)[SB], uint32_t &nz) {
+    uint32_t k = first;
+    for (; k + (kPullUnroll - 1) * step < last; k += kPullUnroll * step) {
+        uint32_t u[kPullUnroll];
+        XPiece<SB> v[kPullUnroll];
+#pragma unroll
+        for (int i = 0; i < kPullUnroll; ++i) u[i] = (uint32_t)pl_ldcs(&a.pool[base + ((head + k + i * step) & mask)]);
+#pragma unroll
+        for (int i = 0; i < kPullUnroll; ++i) v[i] = x_gather<SB>(xcur, (size_t)u[i] * (size_t)a.Sr + c0);
+#pragma unroll
+        for (int i = 0; i < kPullUnroll; ++i) x_accumulate<SB>(v[i], acc, nz);
+    }
+    {   // the remainder, still with all its loads in flight together
+        uint32_t u[kPullUnroll];
+        XPiece<SB> v[kPullUnroll];
+#pragma unroll
+        for (int i = 0; i < kPullUnroll; ++i)
+            u[i] = k + i * step < last ? (uint32_t)pl_ldcs(&a.pool[base + ((head + k + i * step) & mask)]) : 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < kPullUnroll; ++i) v[i] = u[i] != 0xffffffffu ? x_gather<SB>(xcur, (size_t)u[i] * (size_t)a.Sr + c0) : x_zero<SB>();
+#pragma unroll
+        for (int i = 0; i < kPullUnroll; ++i) x_accumulate<SB>(v[i], acc, nz);
+    }
+}
+
+// sum over the lane groups of a warp; afterwards every lane holds the total of its column
+template <int SB>
+__device__ __forceinline__ void pull_reduce_groups(double (&part)[SB], uint32_t G) {
+#pragma unroll
+    for (int j = 0; j < SB; ++j)
+        for (uint32_t off = 16; off >= G; off >>= 1) part[j] += __shfl_xor_sync(kFull, part[j], off);
+}
+
+// ---- one sweep -------------------------------------------------------------------------------------------------------
+// `gath` counts the gathered x entries that were non-zero: exactly the (edge, source) pairs the push form would have
+// traversed.
+template <int SB>
+__device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, const uint16_t *xcur, uint16_t *xnext,
                            unsigned int *cnt_out, unsigned long long *edges_out, unsigned long long &gath) {
-    const uint32_t V = (uint32_t)a.V, Sp = (uint32_t)a.Sp;
-    const uint32_t gs = pull_gshift<SB>(a), G = 1u << gs;
-    const uint32_t tpc = pull_tiles_per_group<SB>(a), ntiles = __ldcg(&c->ntiles_active);
+    const PullGeom q = pull_geom<SB>(a);
+    const uint32_t V = (uint32_t)a.V;
+    const uint32_t lane = lane_id(), grp = lane >> q.gs, g = lane & (q.G - 1u);
     uint32_t legal = 0, nz = 0;
     unsigned long long next_edges = 0;
-    double *list_res = reinterpret_cast<double *>(sm.stage);   // [kThreads / G][G][SB] sums of the listed vertices (the stage is idle during a sweep)
-    double *cta_part = sm.t_ru;                                // [kWarps][G][SB]
-    static_assert(kStage >= kThreads * SB && kTileMax >= kWarps * 8 * SB && kTileMax >= kThreads, "pull.cuh borrows the tile arrays");
-    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const uint32_t tile = __ldcg(&a.tile_list[t]);  // active tiles only, in the scrambled order pull_build listed them
-        uint32_t cg;
-        const PullUnit un = pull_unit<SB>(a, tile, tpc, cg);
-        const uint32_t w = un.w, s0 = un.s0, g = un.g;
-        const bool have = w < V;
-        double xc[SB], acc[SB];
+
+    // ---- grid tier first (the longest tasks): chunks of the long out-lists, one warp per chunk ----
+    {
+        const unsigned long long bp = __ldcg(&c->bigpk);
+        const uint32_t nh = min((uint32_t)(bp >> 32), a.bigcap), nchunks = (uint32_t)bp;
+        const uint32_t gwarp = blockIdx.x * kWarps + warp_id(), nwarps = gridDim.x * kWarps;
+        for (uint32_t cidx = gwarp; cidx < nchunks; cidx += nwarps) {
+            uint32_t lo = 0, hi = nh;  // last list entry with chunk0 <= cidx
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldcg(&a.big[mid].chunk0) <= cidx) lo = mid; else hi = mid;
+            }
+            const unsigned long long item = __ldcg(&a.big[lo].item);
+            const uint32_t w = (uint32_t)item, cg = (uint32_t)(item >> 32);
+            const uint32_t s0 = (cg * q.G + g) * SB;
+            const uint4 m = __ldg(&a.vmeta_out[w]);
+            const uint32_t e0 = (cidx - __ldcg(&a.big[lo].chunk0)) * (uint32_t)a.pull_big_chunk;
+            const uint32_t e1 = min(m.z, e0 + (uint32_t)a.pull_big_chunk);
+            double part[SB];
 #pragma unroll
-        for (int j = 0; j < SB; ++j) { xc[j] = 0.0; acc[j] = 0.0; }
+            for (int j = 0; j < SB; ++j) part[j] = 0.0;
+            if (s0 < (uint32_t)a.Sr) pull_walk<SB>(a, xcur, m.x, m.y, m.w - 1u, e0 + grp, e1, q.vpw, s0, part, nz);
+            pull_reduce_groups<SB>(part, q.G);
+            double *accrow = a.bigacc + (size_t)lo * (size_t)(q.G * SB);
+            if (grp == 0 && s0 < (uint32_t)a.Sr) {
+#pragma unroll
+                for (int j = 0; j < SB; ++j)
+                    if (part[j] != 0.0) atomicAdd(&accrow[g * SB + j], part[j]);
+            }
+            __threadfence();  // the partial sums are out before the chunk is counted
+            __syncwarp();
+            uint32_t done = 0;
+            if (lane == 0) done = atomicAdd(&a.big[lo].pad[kBigDone], 1u) + 1u;
+            done = __shfl_sync(kFull, done, 0);
+            if (done == __ldcg(&a.big[lo].pad[kBigChunks])) {  // this warp completed the vertex: finish it
+                __threadfence();
+                if (grp == 0 && s0 < (uint32_t)a.Sr) {
+                    double acc[SB];
+#pragma unroll
+                    for (int j = 0; j < SB; ++j) {
+                        acc[j] = __ldcg(&accrow[g * SB + j]);
+                        __stcg(&accrow[g * SB + j], 0.0);
+                    }
+                    const XPiece<SB> xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
+                    legal += pull_finish_unit<SB>(a, phase, w, s0, m.z, xc, acc, xnext, next_edges);
+                }
+                if (lane == 0) a.big[lo].pad[kBigDone] = 0u;  // (ready for the next sweep)
+            }
+        }
+    }
+
+    // ---- the active tiles: a warp owns 32 / G consecutive vertices ----
+    const uint32_t ntiles = __ldcg(&c->ntiles_active);
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint32_t tile = __ldcg(&a.tile_list[t]);
+        const uint32_t cg = tile / q.tpc;
+        const uint32_t w = (tile - cg * q.tpc) * q.vpt + warp_id() * q.vpw + grp;
+        const uint32_t s0 = (cg * q.G + g) * SB;
+        const bool have = w < V && s0 < (uint32_t)a.Sr;
+        XPiece<SB> xc = x_zero<SB>();
+        double acc[SB];
+#pragma unroll
+        for (int j = 0; j < SB; ++j) acc[j] = 0.0;
         uint32_t len = 0, base = 0, head = 0, mask = 0;
-        if (have) {
+        if (w < V) {
             len = (uint32_t)pl_ldcs(&a.outdeg[w]);
-            pull_load_x<SB>(xcur, w, Sp, s0, xc);
             if (len) {
                 const uint4 m = pl_ldcs(&a.vmeta_out[w]);
                 base = m.x; head = m.y; len = m.z; mask = m.w - 1u;
             }
         }
-        const int tier = len < (uint32_t)a.pull_warp_min ? 0 : len < (uint32_t)a.pull_cta_min ? 1 : len < (uint32_t)a.pull_big_min ? 2 : 3;
-        // ---- warp and CTA tiers (one list entry per vertex: the G lanes of a group share it) ----
-        const bool listed = tier == 1 || tier == 2;
-        if (__syncthreads_or(listed)) {
-            uint32_t myslot = 0;
-            if (threadIdx.x == 0) sm.pl_n = 0;
-            __syncthreads();
-            if (listed && g == 0) {
-                myslot = atomicAdd(&sm.pl_n, 1u);
-                sm.t_base[myslot] = base; sm.t_head[myslot] = head; sm.t_mask[myslot] = mask; sm.t_off[myslot] = len;
+        if (have) xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
+        const int tier = len >= (uint32_t)a.pull_big_min ? 2 : (len >= (uint32_t)a.pull_warp_min && q.vpw > 1u) ? 1 : 0;
+        if (tier == 0 && have && len) pull_walk<SB>(a, xcur, base, head, mask, 0u, len, 1u, s0, acc, nz);
+        // lists of warp_min or more entries: the whole warp walks them, one after the other
+        unsigned m1 = __ballot_sync(kFull, tier == 1 && g == 0 && w < V);
+        while (m1) {
+            const int L = __ffs(m1) - 1;
+            m1 &= m1 - 1u;
+            const uint32_t eb = __shfl_sync(kFull, base, L), eh = __shfl_sync(kFull, head, L), el = __shfl_sync(kFull, len, L),
+                           em = __shfl_sync(kFull, mask, L);
+            double part[SB];
+#pragma unroll
+            for (int j = 0; j < SB; ++j) part[j] = 0.0;
+            if (s0 < (uint32_t)a.Sr) pull_walk<SB>(a, xcur, eb, eh, em, grp, el, q.vpw, s0, part, nz);
+            pull_reduce_groups<SB>(part, q.G);
+            if (grp == ((uint32_t)L >> q.gs)) {
+#pragma unroll
+                for (int j = 0; j < SB; ++j) acc[j] = part[j];
             }
-            myslot = __shfl_sync(kFull, myslot, lane_id() & ~(G - 1u));
-            __syncthreads();
-            const uint32_t ne = sm.pl_n;
-            for (uint32_t e = warp_id(); e < ne; e += kWarps) {
-                const uint32_t el = sm.t_off[e];
-                if (el >= (uint32_t)a.pull_cta_min) continue;
-                const uint32_t eb = sm.t_base[e], eh = sm.t_head[e], em = sm.t_mask[e];
-                double part[SB];
-#pragma unroll
-                for (int j = 0; j < SB; ++j) part[j] = 0.0;
-#pragma unroll 4
-                for (uint32_t k = lane_id() >> gs; k < el; k += 32u >> gs)
-                    pull_gather<SB>(xcur, (uint32_t)pl_ldcs(&a.pool[eb + ((eh + k) & em)]), Sp, s0, part, nz);
-#pragma unroll
-                for (int j = 0; j < SB; ++j) {
-                    for (uint32_t off = 16; off >= G; off >>= 1) part[j] += __shfl_xor_sync(kFull, part[j], off);
-                    if (lane_id() < G) list_res[((e << gs) + g) * SB + j] = part[j];
-                }
-            }
-            for (uint32_t e = 0; e < ne; ++e) {
-                const uint32_t el = sm.t_off[e];
-                if (el < (uint32_t)a.pull_cta_min) continue;  // (uniform over the CTA)
-                const uint32_t eb = sm.t_base[e], eh = sm.t_head[e], em = sm.t_mask[e];
-                double part[SB];
-#pragma unroll
-                for (int j = 0; j < SB; ++j) part[j] = 0.0;
-#pragma unroll 4
-                for (uint32_t k = threadIdx.x >> gs; k < el; k += (uint32_t)kThreads >> gs)
-                    pull_gather<SB>(xcur, (uint32_t)pl_ldcs(&a.pool[eb + ((eh + k) & em)]), Sp, s0, part, nz);
-#pragma unroll
-                for (int j = 0; j < SB; ++j) {
-                    for (uint32_t off = 16; off >= G; off >>= 1) part[j] += __shfl_xor_sync(kFull, part[j], off);
-                    if (lane_id() < G) cta_part[((warp_id() << gs) + g) * SB + j] = part[j];
-                }
-                __syncthreads();
-                if (threadIdx.x < G * SB) {  // thread = (sub-chunk, source within it)
-                    const uint32_t gg = threadIdx.x / SB, jj = threadIdx.x % SB;
-                    double tsum = 0.0;
-#pragma unroll
-                    for (int ww = 0; ww < kWarps; ++ww) tsum += cta_part[((ww << gs) + gg) * SB + jj];
-                    list_res[((e << gs) + gg) * SB + jj] = tsum;
-                }
-                __syncthreads();
-            }
-            __syncthreads();
-            if (listed) {
-#pragma unroll
-                for (int j = 0; j < SB; ++j) acc[j] = list_res[((myslot << gs) + g) * SB + j];
-            }
-            __syncthreads();  // the list is reused by the next tile
         }
-        // ---- thread tier ----
-        if (tier == 0) {
-#pragma unroll 4
-            for (uint32_t k = 0; k < len; ++k)
-                pull_gather<SB>(xcur, (uint32_t)pl_ldcs(&a.pool[base + ((head + k) & mask)]), Sp, s0, acc, nz);
-        }
-        // ---- grid tier: finished by pull_big_finish after the next grid barrier ----
-        if (tier == 3) {
-            if (g == 0) {  // one entry per (vertex, chunk group)
-                const uint32_t nch = (len + kPullBigChunk - 1) / kPullBigChunk;
-                const unsigned long long old = atomicAdd(&c->bigpk, (1ull << 32) | nch);
-                const uint32_t hp = (uint32_t)(old >> 32);
-                if (hp < a.bigcap) {
-                    __stcg(&a.big[hp].item, ((unsigned long long)cg << 32) | w);
-                    __stcg(&a.big[hp].chunk0, (uint32_t)old);
-                } else {
-                    atomicOr(&c->errflags, kErrHubQ);
-                }
-            }
-        } else if (have) {
-            legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, next_edges);
-        }
+        if (tier != 2 && have) legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, next_edges);
     }
     gath += nz;
     pull_count_flush(sm, legal, cnt_out, next_edges, edges_out);
 }
 
-// chunks of the grid-tier lists, dealt round-robin to the CTAs
+// ---- leaving dense mode ----------------------------------------------------------------------------------------------
+// the non-zero entries of x are pops that were decided but not performed: give them back to r; those (source, vertex)
+// pairs are the (un-popped) frontier of the next scatter iteration
 template <int SB>
-__device__ void pull_big_expand(const PushArgs &a, PushSmem &sm, const double *xcur, unsigned long long bp,
-                                unsigned long long &gath) {
-    const uint32_t nh = min((uint32_t)(bp >> 32), a.bigcap), nchunks = (uint32_t)bp;
-    const uint32_t Sp = (uint32_t)a.Sp;
-    const uint32_t gs = pull_gshift<SB>(a), G = 1u << gs, g = threadIdx.x & (G - 1u);
-    double *cta_part = sm.t_ru;
-    uint32_t nz = 0;
-    for (uint32_t cidx = blockIdx.x; cidx < nchunks; cidx += gridDim.x) {
-        uint32_t lo = 0, hi = nh;  // last list entry with chunk0 <= cidx
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (__ldcg(&a.big[mid].chunk0) <= cidx) lo = mid; else hi = mid;
-        }
-        const unsigned long long item = __ldcg(&a.big[lo].item);
-        const uint32_t c0 = __ldcg(&a.big[lo].chunk0);
-        const uint32_t w = (uint32_t)item, s0 = ((((uint32_t)(item >> 32)) << gs) + g) * SB;
-        const uint4 m = __ldg(&a.vmeta_out[w]);
-        const uint32_t e0 = (cidx - c0) * (uint32_t)kPullBigChunk;
-        const uint32_t e1 = min(m.z, e0 + (uint32_t)kPullBigChunk);
-        double part[SB];
-#pragma unroll
-        for (int j = 0; j < SB; ++j) part[j] = 0.0;
-#pragma unroll 4
-        for (uint32_t k = e0 + (threadIdx.x >> gs); k < e1; k += (uint32_t)kThreads >> gs)
-            pull_gather<SB>(xcur, (uint32_t)pl_ldcs(&a.pool[m.x + ((m.y + k) & (m.w - 1u))]), Sp, s0, part, nz);
-#pragma unroll
-        for (int j = 0; j < SB; ++j) {
-            for (uint32_t off = 16; off >= G; off >>= 1) part[j] += __shfl_xor_sync(kFull, part[j], off);
-            if (lane_id() < G) cta_part[((warp_id() << gs) + g) * SB + j] = part[j];
-        }
-        __syncthreads();
-        if (threadIdx.x < G * SB) {
-            const uint32_t gg = threadIdx.x / SB, jj = threadIdx.x % SB;
-            double t = 0.0;
-#pragma unroll
-            for (int ww = 0; ww < kWarps; ++ww) t += cta_part[((ww << gs) + gg) * SB + jj];
-            atomicAdd(&a.bigacc[(((size_t)lo << gs) + gg) * 4 + jj], t);
-        }
-        __syncthreads();
-    }
-    gath += nz;
-}
-
-template <int SB>
-__device__ void pull_big_finish(const PushArgs &a, PushSmem &sm, int phase, const double *xcur, double *xnext,
-                                unsigned long long bp, unsigned int *cnt_out, unsigned long long *edges_out) {
-    const uint32_t nh = min((uint32_t)(bp >> 32), a.bigcap);
-    const uint32_t gs = pull_gshift<SB>(a), G = 1u << gs;
-    uint32_t legal = 0;
-    unsigned long long next_edges = 0;
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < (nh << gs); i += gridDim.x * kThreads) {
-        const uint32_t h = i >> gs, g = i & (G - 1u);  // thread = (list entry, sub-chunk)
-        const unsigned long long item = __ldcg(&a.big[h].item);
-        const uint32_t w = (uint32_t)item, s0 = ((((uint32_t)(item >> 32)) << gs) + g) * SB;
-        double xc[SB], acc[SB];
-        pull_load_x<SB>(xcur, w, (uint32_t)a.Sp, s0, xc);
-#pragma unroll
-        for (int j = 0; j < SB; ++j) {
-            acc[j] = __ldcg(&a.bigacc[(size_t)i * 4 + j]);
-            __stcg(&a.bigacc[(size_t)i * 4 + j], 0.0);
-        }
-        const uint32_t len = __ldg(&a.vmeta_out[w]).z;
-        legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, next_edges);
-    }
-    pull_count_flush(sm, legal, cnt_out, next_edges, edges_out);
-}
-
-// leaving dense mode: the non-zero entries of x are the (un-popped) frontier of the next scatter iteration
-template <int SB>
-__device__ void pull_compact(const PushArgs &a, PushSmem &sm, PushCtrl *c, const double *x, unsigned long long *qout,
+__device__ void pull_compact(const PushArgs &a, PushSmem &sm, PushCtrl *c, const uint16_t *x, unsigned long long *qout,
                              unsigned int *cnt_out) {
+    const PullGeom q = pull_geom<SB>(a);
     const uint32_t V = (uint32_t)a.V;
-    const uint32_t tpc = pull_tiles_per_group<SB>(a), ntiles = __ldcg(&c->ntiles_active);
+    const uint32_t ntiles = __ldcg(&c->ntiles_active);
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint32_t tile = __ldcg(&a.tile_list[t]);
-        uint32_t cg;
-        const PullUnit un = pull_unit<SB>(a, tile, tpc, cg);
-        const uint32_t w = un.w, s0 = un.s0;
-        double xc[SB];
-#pragma unroll
-        for (int j = 0; j < SB; ++j) xc[j] = 0.0;
-        if (w < V) pull_load_x<SB>(x, w, (uint32_t)a.Sp, s0, xc);
+        const uint32_t cg = tile / q.tpc;
+        const uint32_t w = (tile - cg * q.tpc) * q.vpt + (threadIdx.x >> q.gs), g = threadIdx.x & (q.G - 1u);
+        const uint32_t s0 = (cg * q.G + g) * SB;
+        const bool have = w < V && s0 < (uint32_t)a.Sr;
+        const size_t row = (size_t)w * (size_t)a.Sr + s0;
+        XPiece<SB> xc = x_zero<SB>();
+        if (have) xc = x_load<SB>(x, row);
 #pragma unroll
         for (int j = 0; j < SB; ++j) {
-            if (xc[j] != 0.0) __stcg(&a.r[(size_t)(s0 + j) * a.Vp + w], xc[j]);  // (see pull_finish_unit)
-            stage_push(xc[j] != 0.0, ((unsigned long long)(s0 + j) << 32) | w, sm, qout, cnt_out, a.qcap, a.ctrl);
+            const uint32_t h = xc.get(j);
+            if (h) a.r[row + j] += bf16_value(h);
+            stage_push(h != 0u, ((unsigned long long)(s0 + j) << 32) | w, sm, qout, cnt_out, a.qcap, a.ctrl);
         }
         stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
     }
@@ -486,7 +500,7 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
         for (uint32_t h = blockIdx.x * kThreads + threadIdx.x; h < nh; h += gridDim.x * kThreads) {
             const unsigned long long item = __ldcg(&hin[h].item);
             const double ru = __ldcg(&hin[h].ru);
-            const size_t idx = (size_t)(item >> 32) * a.Vp + (uint32_t)item;
+            const size_t idx = (size_t)(uint32_t)item * (size_t)a.Sr + (item >> 32);
             atomicAdd(&a.r[idx], ru);
             atomicAdd(&a.p[idx], -a.alpha * ru);
         }
@@ -508,8 +522,9 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
         if (n == 0) break;
         if (k > 0) {
             const unsigned long long ne = __ldcg(&c->dedges[k % 3]);
-            const bool leave = (rate > 0.f && sw_known > 0.f) ? (double)ne * (double)rate < 0.8 * (double)sw_known
-                                                               : ne < a.dense_exit_edges;
+            const bool fits = (double)n < 0.5 * (double)a.qcap;  // (the frontier must fit the queue it is compacted into)
+            const bool leave = fits && ((rate > 0.f && sw_known > 0.f) ? (double)ne * (double)rate < 0.8 * (double)sw_known
+                                                                        : ne < a.dense_exit_edges);
             if (leave) break;
         }
         if ((int)iters_done >= a.max_iters) {
@@ -528,14 +543,6 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
         }
         pull_sweep<SB>(a, sm, c, phase, a.x[cur], a.x[cur ^ 1], &c->dcnt[(k + 1) % 3], &c->dedges[(k + 1) % 3], gath);
         if (!grid_barrier(c, gen, sm)) return false;
-        const unsigned long long bp = __ldcg(&c->bigpk);
-        if (bp) {
-            pull_big_expand<SB>(a, sm, a.x[cur], bp, gath);
-            if (!grid_barrier(c, gen, sm)) return false;
-            if (blockIdx.x == 0 && threadIdx.x == 0) c->bigpk = 0;
-            pull_big_finish<SB>(a, sm, phase, a.x[cur], a.x[cur ^ 1], bp, &c->dcnt[(k + 1) % 3], &c->dedges[(k + 1) % 3]);
-            if (!grid_barrier(c, gen, sm)) return false;
-        }
         cur ^= 1;
         ++k;
         ++iters_done;

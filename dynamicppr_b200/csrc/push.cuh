@@ -108,7 +108,8 @@ struct PushArgs {
     double *p;
     double *r;
     int32_t *status;
-    int64_t Vp;
+    int64_t Sr;                  // row stride of p / r / status / x: these arrays are VERTEX-major, [V][Sr], Sr = 1 or S rounded up
+                                 // to a multiple of 8 (padding columns stay zero): element (source s, vertex v) sits at v * Sr + s
     int32_t S;
     const int32_t *src;
     unsigned long long *q[2];
@@ -134,17 +135,16 @@ struct PushArgs {
     int32_t V;
     float avg_indeg;             // E_w / V
     const uint4 *vmeta_out;      // out-lists (the in-lists themselves when the graph is undirected)
-    double *x[2];                // popped residuals of the running / next sweep, vertex-major [V][Sp]
-    int32_t Sp;                  // sources per vertex row of x: 1, or S rounded up to a multiple of 4 << pull_gshift
-    int32_t pull_gshift;         // log2 of the lanes that share a vertex in a sweep (pull.cuh, PullUnit)
+    uint16_t *x[2];              // amounts popped by the running / next sweep, bf16, vertex-major [V][Sr] (pull.cuh)
+    int32_t pull_gshift;         // log2 of the lanes that share a vertex in a sweep (pull.cuh, PullGeom)
     unsigned long long dense_enter_edges;  // an iteration expected to traverse at least this many in-edges runs as a sweep
     unsigned long long dense_exit_edges;   // ... and below this the loop goes back to scatter iterations
-    int32_t pull_warp_min, pull_cta_min, pull_big_min;  // out-degree tiers of a sweep
+    int32_t pull_warp_min, pull_big_min, pull_big_chunk;  // out-degree tiers of a sweep; entries per chunk of the grid tier
     uint32_t pull_tile_mul;      // tile visiting order: tile = (t * mul) mod ntiles, mul coprime to ntiles
     uint32_t *tile_list;         // active tiles of the running dense episode
     HubItem *big;                // grid-tier list
     uint32_t bigcap;
-    double *bigacc;              // [bigcap][4] partial sums of the grid tier (zero between sweeps)
+    double *bigacc;              // [bigcap][lanes per vertex x sources per lane] partial sums of the grid tier (zero between sweeps)
 };
 
 #ifndef DPPR_ITEMS_PER_THREAD
@@ -245,16 +245,12 @@ struct TileOwner {
     const PushSmem &sm;
     uint32_t lo[kEdgeUnroll];
     __device__ __forceinline__ double ru_scaled(int k) const { return sm.t_ru[lo[k]]; }
-    long long Vp;
-    __device__ __forceinline__ unsigned long long sb(int k) const { return (unsigned long long)sm.t_s[lo[k]] * Vp; }
     __device__ __forceinline__ uint32_t s(int k) const { return sm.t_s[lo[k]]; }
 };
 struct HubOwner {
     double ru_scaled_;
-    unsigned long long sb_;
     uint32_t s_;
     __device__ __forceinline__ double ru_scaled(int) const { return ru_scaled_; }
-    __device__ __forceinline__ unsigned long long sb(int) const { return sb_; }
     __device__ __forceinline__ uint32_t s(int) const { return s_; }
 };
 
@@ -271,7 +267,7 @@ __device__ __forceinline__ void push_edges(const PushArgs &a, PushSmem &sm, cons
         old[k] = 0.0; add[k] = 0.0;
         if (active[k]) {
             add[k] = ow.ru_scaled(k) / (double)(dv[k] + 1);  // (1-alpha)*ru/(outdeg(v)+1), gpu/ExpandRev.cuh:71-72
-            old[k] = atomicAdd(&a.r[ow.sb(k) + nbr[k]], add[k]);
+            old[k] = atomicAdd(&a.r[(unsigned long long)nbr[k] * a.Sr + ow.s(k)], add[k]);
         }
     }
 #pragma unroll
@@ -282,7 +278,7 @@ __device__ __forceinline__ void push_edges(const PushArgs &a, PushSmem &sm, cons
             if (VAR == 0 || VAR == 1) {  // threshold crossing, gpu/ExpandRev.cuh:75
                 want = !legal_push(old[k], phase, a.eps) && legal_push(cur, phase, a.eps);
             } else if (legal_push(cur, phase, a.eps)) {  // status stamp, gpu/ExpandRev.cuh:254-257
-                want = atomicExch(&a.status[ow.sb(k) + nbr[k]], level) < level;
+                want = atomicExch(&a.status[(unsigned long long)nbr[k] * a.Sr + ow.s(k)], level) < level;
             }
         }
         stage_push(want, ((unsigned long long)ow.s(k) << 32) | nbr[k], sm, qout, cnt_out, a.qcap, a.ctrl);
@@ -305,7 +301,7 @@ __device__ void seed_pass(const PushArgs &a, PushSmem &sm, int phase, unsigned l
             const uint32_t s = (uint32_t)(j / ncand);
             const uint32_t c = (uint32_t)(j - (unsigned long long)s * ncand);
             const uint32_t u = a.init_mode ? (uint32_t)a.src[s] : a.cand[c];
-            const double x = __ldcg(&a.r[(unsigned long long)s * a.Vp + u]);
+            const double x = __ldcg(&a.r[(unsigned long long)u * a.Sr + s]);
             want = legal_push(x, phase, a.eps);
             item = ((unsigned long long)s << 32) | u;
             if (want) mx = fmax(mx, fabs(x));
@@ -324,7 +320,7 @@ template <int VAR>
 __device__ void pre_pass(const PushArgs &a, const unsigned long long *qin, double *qr, uint32_t n, int level) {
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
         const unsigned long long item = __ldcg(&qin[i]);
-        const unsigned long long idx = (item >> 32) * a.Vp + (uint32_t)item;
+        const unsigned long long idx = (unsigned long long)(uint32_t)item * a.Sr + (item >> 32);
         if (VAR == 1 || VAR == 3) {
             const double x = __ldcg(&a.r[idx]);
             __stcg(&qr[i], x);
@@ -347,7 +343,7 @@ __device__ void post_pass(const PushArgs &a, PushSmem &sm, const unsigned long l
         unsigned long long item = 0;
         if (i < n) {
             item = __ldcg(&qin[i]);
-            const unsigned long long idx = (item >> 32) * a.Vp + (uint32_t)item;
+            const unsigned long long idx = (unsigned long long)(uint32_t)item * a.Sr + (item >> 32);
             const double ru = __ldcg(&qr[i]);
             const double old = atomicAdd(&a.r[idx], -ru);
             want = legal_push(old - ru, phase, a.eps);
@@ -394,7 +390,7 @@ __device__ void expand_hubs(const PushArgs &a, PushSmem &sm, const HubItem *hin,
             active[k] = e < deg;
             nbr[k] = active[k] ? (uint32_t)__ldg(&a.pool[m.x + ((m.y + e) & mask)]) : 0u;
         }
-        const HubOwner ow{ru_scaled, (unsigned long long)s * a.Vp, s};
+        const HubOwner ow{ru_scaled, s};
         push_edges<VAR>(a, sm, ow, nbr, active, qout, cnt_out, phase, level);
         if (threadIdx.x == 0) edges_acc += min(deg - e0, (uint32_t)kHubChunk);
         stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
@@ -444,7 +440,7 @@ __device__ void expand_tiles(const PushArgs &a, PushSmem &sm, const unsigned lon
                 uint32_t deg = 0;
                 if (have[k]) {
                     const uint32_t s = (uint32_t)(item[k] >> 32), v = (uint32_t)item[k];
-                    const unsigned long long idx = (unsigned long long)s * a.Vp + v;
+                    const unsigned long long idx = (unsigned long long)v * a.Sr + s;
                     const uint4 m = __ldg(&a.vmeta[v]);
                     double ru;
                     if (VAR == 0) {
@@ -517,7 +513,7 @@ __device__ void expand_tiles(const PushArgs &a, PushSmem &sm, const unsigned lon
         if (tile == blockIdx.x) DPPR_TL(tl, 3);
         // ---- edges ----
         for (uint32_t e0 = 0; e0 < total; e0 += kHubChunk) {
-            TileOwner ow{sm, {}, a.Vp};
+            TileOwner ow{sm, {}};
             uint32_t nbr[kEdgeUnroll];
             bool active[kEdgeUnroll];
 #pragma unroll
@@ -626,8 +622,13 @@ namespace dppr {
 // ---- the persistent kernel ----------------------------------------------------------------------------
 // DENSE: with the switch to gather sweeps (variant 0 only).  A separate instantiation, so that the scatter-only
 // kernels keep their register allocation.
+#ifndef DPPR_DENSE_MIN_BLOCKS
+#define DPPR_DENSE_MIN_BLOCKS 2
+#endif
+// (the switching kernel gets 128 registers per thread: its sweeps keep kPullUnroll row gathers in flight per lane and
+// must not spill -- round 1's 64-register build issued 5.2 G local loads per refresh on BASELINE configs[3])
 template <int VAR, bool DENSE>
-__global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(const PushArgs a) {
+__global__ void __launch_bounds__(kThreads, DENSE ? DPPR_DENSE_MIN_BLOCKS : DPPR_MIN_BLOCKS) push_persistent(const PushArgs a) {
     __shared__ PushSmem sm;
     PushCtrl *c = a.ctrl;
     if (threadIdx.x == 0) { sm.stage_cnt = 0; sm.abort_flag = 0; }
@@ -765,7 +766,7 @@ __global__ void __launch_bounds__(kThreads, DPPR_MIN_BLOCKS) push_persistent(con
             fresh_phase = false;
             t_prev = 0.0;
             DenseIO io{edges_acc, gath_acc, pops_acc, iters_done, sweeps_done, gen, dense_rate};
-            alive = a.Sp == 1 ? dense_mode<1>(a, sm, c, phase, it, dense_hpk, io) : dense_mode<4>(a, sm, c, phase, it, dense_hpk, io);
+            alive = a.Sr == 1 ? dense_mode<1>(a, sm, c, phase, it, dense_hpk, io) : dense_mode<8>(a, sm, c, phase, it, dense_hpk, io);
             edges_acc = io.edges_acc; gath_acc = io.gath; pops_acc = io.pops_acc;
             iters_done = io.iters_done; sweeps_done = io.sweeps_done; gen = io.gen;
             ++it;
@@ -839,14 +840,14 @@ __global__ void __launch_bounds__(kThreads) push_step_post(const PushArgs a, uin
 
 // ---- state initialisation (gpu/PPRCommon.cuh:13-22) ------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-    state_init(double *__restrict__ p, double *__restrict__ r, int32_t *__restrict__ status, int64_t Vp, int S,
+    state_init(double *__restrict__ p, double *__restrict__ r, int32_t *__restrict__ status, int32_t V, int64_t Sr, int S,
                const int32_t *__restrict__ src) {
-    const int64_t total = Vp * S;
+    const int64_t total = (int64_t)V * Sr;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
-        const int s = (int)(i / Vp);
-        const int64_t v = i - (int64_t)s * Vp;
+        const int64_t v = i / Sr;
+        const int s = (int)(i - v * Sr);
         p[i] = 0.0;
-        r[i] = (v == src[s]) ? 1.0 : 0.0;
+        r[i] = (s < S && v == src[s]) ? 1.0 : 0.0;
         if (status) status[i] = -1;
     }
 }

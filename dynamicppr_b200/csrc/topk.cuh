@@ -84,11 +84,11 @@ __device__ __forceinline__ void top_offer(TopSmem &sm, bool valid, unsigned long
 
 // grid (slices, sources).  partial: [source][slice][k] keys + ids, short lists padded with key 0.
 __global__ void __launch_bounds__(kThreads)
-    topk_partial(const double *__restrict__ p, int64_t Vp, int32_t V, int first_source, const uint32_t *__restrict__ inv, int k,
+    topk_partial(const double *__restrict__ p, int64_t Sr, int32_t V, int first_source, const uint32_t *__restrict__ inv, int k,
                  unsigned long long *__restrict__ pkey, uint32_t *__restrict__ pid) {
     __shared__ TopSmem sm;
     const int s = blockIdx.y;
-    const double *ps = p + (int64_t)(first_source + s) * Vp;
+    const double *ps = p + (first_source + s);  // state is vertex-major: element v of this source sits at v * Sr
     if (threadIdx.x == 0) sm.cnt = 0;
     __syncthreads();
     unsigned long long tau = 0ull;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kThreads)
         for (int j = 0; j < kTopItems; ++j) {
             const int64_t v = base + j * kThreads + threadIdx.x;
             const bool valid = v < hi;
-            const unsigned long long key = valid ? top_key(ps[v]) : 0ull;
+            const unsigned long long key = valid ? top_key(ps[v * Sr]) : 0ull;
             top_offer(sm, valid, key, valid ? (inv ? inv[v] : (uint32_t)v) : 0u, tau);
         }
         __syncthreads();

@@ -21,10 +21,11 @@ __device__ __forceinline__ void atomic_max_double_bits(unsigned long long *dst, 
     atomicMax(dst, (unsigned long long)__double_as_longlong(x));
 }
 
-__global__ void __launch_bounds__(kThreads) val_residual_max(const double *__restrict__ r, int32_t V, unsigned long long *out) {
+// (p, r point at the source's column of the vertex-major state; Sr = row stride)
+__global__ void __launch_bounds__(kThreads) val_residual_max(const double *__restrict__ r, int64_t Sr, int32_t V, unsigned long long *out) {
     double mx = 0.0;
     for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < V; v += (int64_t)gridDim.x * kThreads) {
-        const double x = fabs(r[v]);
+        const double x = fabs(r[v * Sr]);
         mx = (x > mx || x != x) ? x : mx;  // (a NaN wins: it must not pass)
     }
 #pragma unroll
@@ -37,23 +38,23 @@ __global__ void __launch_bounds__(kThreads) val_residual_max(const double *__res
 
 // acc[u] += p[w] for every window edge u -> w: the edge sits in w's in-list as `u`.  One warp per vertex w.
 __global__ void __launch_bounds__(kThreads)
-    val_out_sums(const uint4 *__restrict__ vmeta, const int32_t *__restrict__ pool, const double *__restrict__ p, int32_t V,
+    val_out_sums(const uint4 *__restrict__ vmeta, const int32_t *__restrict__ pool, const double *__restrict__ p, int64_t Sr, int32_t V,
                  double *__restrict__ acc) {
     const int64_t warps = (int64_t)gridDim.x * kWarps;
     for (int64_t w = (int64_t)blockIdx.x * kWarps + warp_id(); w < V; w += warps) {
         const uint4 m = vmeta[w];
-        const double pw = p[w];
+        const double pw = p[w * Sr];
         if (pw == 0.0) continue;
         for (uint32_t k = lane_id(); k < m.z; k += 32) atomicAdd(&acc[pool[m.x + ((m.y + k) & (m.w - 1u))]], pw);
     }
 }
 
 __global__ void __launch_bounds__(kThreads)
-    val_invariant(const double *__restrict__ p, const double *__restrict__ r, const int32_t *__restrict__ outdeg,
+    val_invariant(const double *__restrict__ p, const double *__restrict__ r, int64_t Sr, const int32_t *__restrict__ outdeg,
                   const double *__restrict__ acc, int32_t V, int32_t source, double alpha, unsigned long long *out) {
     double mx = 0.0;
     for (int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x; u < V; u += (int64_t)gridDim.x * kThreads) {
-        const double lhs = p[u] + alpha * r[u] - (u == source ? alpha : 0.0);
+        const double lhs = p[u * Sr] + alpha * r[u * Sr] - (u == source ? alpha : 0.0);
         const double d = fabs(lhs - (1.0 - alpha) * acc[u] / ((double)outdeg[u] + 1.0));
         mx = (d > mx || d != d) ? d : mx;
     }

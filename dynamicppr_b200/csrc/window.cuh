@@ -166,9 +166,9 @@ __global__ void __launch_bounds__(kThreads)
 }
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-    scatter_by_perm(const T *__restrict__ in, const uint32_t *__restrict__ perm, T *__restrict__ out, int32_t V) {
+    scatter_by_perm(const T *__restrict__ in, const uint32_t *__restrict__ perm, T *__restrict__ out, int64_t out_stride, int32_t V) {
     for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < V; v += (int64_t)gridDim.x * kThreads)
-        out[perm ? perm[v] : (uint32_t)v] = in[v];
+        out[(int64_t)(perm ? perm[v] : (uint32_t)v) * out_stride] = in[v];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -63,10 +63,10 @@ typedef struct dppr_tuning {
     int32_t tile_cap;           /* frontier items per tile once a CTA's share exceeds 512; default 128            [DPPR_TILE_CAP] */
     int32_t max_iters;          /* push iterations per refresh before the watchdog fires; default 400000         [DPPR_MAX_ITERS] */
     int32_t dense;              /* gather sweeps (variant 0): 0 auto by window size, 1 always, -1 never           [DPPR_DENSE] */
-    int32_t pull_group;         /* lanes sharing a vertex in a multi-source sweep (1..8); default 8               [DPPR_PULL_GROUP] */
-    int32_t pull_warp_min;      /* out-degree tiers of a sweep; defaults 32 / 1024 / 65536                        [DPPR_PULL_WARP_MIN ...] */
-    int32_t pull_cta_min;
-    int32_t pull_big_min;
+    int32_t pull_group;         /* most lanes sharing a vertex in a multi-source sweep (1..32); default 32        [DPPR_PULL_GROUP] */
+    int32_t pull_warp_min;      /* out-lists from this length are walked by a whole warp; default 32              [DPPR_PULL_WARP_MIN] */
+    int32_t pull_big_min;       /* ... and from this length cut into chunks for the grid; default 4096 / 1024 (1 / several sources) [DPPR_PULL_BIG_MIN] */
+    int32_t pull_big_chunk;     /* entries per chunk; default pull_big_min / 4                                    [DPPR_PULL_BIG_CHUNK] */
     int32_t window_path;        /* 0 auto, 1 multi-kernel window update only, 2 no single-CTA kernel              [DPPR_WINDOW_PATH] */
     int32_t iterlog;            /* 1: keep a per-iteration log of the last refresh (dppr_debug_iterlog)           [DPPR_ITERLOG] */
     int32_t probe_iter;         /* iteration whose per-CTA timeline dppr_debug_ctalog returns; default 10         [DPPR_PROBE_ITER] */

@@ -2,7 +2,7 @@
 level-synchronous engine runs an iteration as a gather sweep over the out-lists instead of scattering atomics.
 Same contract as everywhere else: window graph bit-exact, estimates within 2 eps of the reference CPU push and of
 power iteration, residuals within eps.  The thresholds are forced down through the environment so that tiny graphs
-exercise every tier (thread / warp / CTA / grid) and the switch in both directions."""
+exercise every tier (lane group / warp / grid) and the switch in both directions."""
 import numpy as np
 import pytest
 
@@ -23,11 +23,13 @@ def transpose_csr(V, rp, ci):
     return out_rp.astype(np.int32), dst[order].astype(np.int32)
 
 
-def force_dense(monkeypatch, div="1e15", tiers=(3, 6, 12)):
+def force_dense(monkeypatch, div="1e15", tiers=(3, 12, 5)):
+    """tiers = (warp_min, big_min, big_chunk): out-lists from warp_min entries are walked by a whole warp, from big_min
+    entries they are cut into chunks of big_chunk entries that any warp of the grid takes (csrc/pull.cuh)"""
     monkeypatch.setenv("DPPR_DENSE_DIV", div)        # 1e15: enter at any frontier size >= 1
     monkeypatch.setenv("DPPR_DENSE_MIN_EDGES", "0")  # (by default small windows never switch)
-    for name, v in zip(("WARP", "CTA", "BIG"), tiers):
-        monkeypatch.setenv(f"DPPR_PULL_{name}_MIN", str(v))
+    for name, v in zip(("WARP_MIN", "BIG_MIN", "BIG_CHUNK"), tiers):
+        monkeypatch.setenv(f"DPPR_PULL_{name}", str(v))
 
 
 def check_out_lists(eng, V, rp, ci, directed, tag):
@@ -41,8 +43,8 @@ def check_out_lists(eng, V, rp, ci, directed, tag):
     np.testing.assert_array_equal(out[1], eci, err_msg=tag + " (out col_ind)")
 
 
-@pytest.mark.parametrize("tiers", [(3, 6, 12), (2, 2, 2), (1000000, 1000000, 1000000), (1, 1, 1000000), (1, 1000000, 1000000)],
-                         ids=["all-tiers", "grid-tier", "thread-tier", "cta-tier", "warp-tier"])
+@pytest.mark.parametrize("tiers", [(3, 12, 5), (2, 2, 1), (1000000, 1000000, 1000000), (1, 1000000, 1000000), (4, 4, 3)],
+                         ids=["all-tiers", "grid-tier-chunks-of-1", "lane-tier", "warp-tier", "grid-tier"])
 @pytest.mark.parametrize("path", GOLDEN, ids=GOLDEN_IDS)
 def test_golden_with_forced_dense_iterations(path, tiers, monkeypatch):
     force_dense(monkeypatch, tiers=tiers)
@@ -126,7 +128,7 @@ def test_top_degree_source_undirected_dense(div, monkeypatch):
 def test_directed_out_lists_follow_the_window(window_path, monkeypatch):
     """directed R-MAT stream: the out-lists are maintained by each of the three launch shapes of the window update;
     the dense sweeps read them"""
-    force_dense(monkeypatch, div="256", tiers=(8, 64, 512))
+    force_dense(monkeypatch, div="256", tiers=(8, 512, 128))
     if window_path != "fused":
         monkeypatch.setenv("DPPR_FUSED_WINDOW", "0")
     if window_path == "multikernel":
@@ -141,7 +143,7 @@ def test_directed_out_lists_follow_the_window(window_path, monkeypatch):
 
 def test_multi_source_dense_matches_single_source_oracles(monkeypatch):
     """7 sources -> rows of 8 in x (one padding column), two source chunks per vertex"""
-    force_dense(monkeypatch, div="1e15", tiers=(4, 32, 200))
+    force_dense(monkeypatch, div="1e15", tiers=(4, 200, 64))
     for directed in (False, True):
         V, M = 6_000, 50_000
         edges = graphgen.rmat_directed(V, M, seed=5) if directed else graphgen.powerlaw_undirected(V, M, seed=77)
@@ -172,11 +174,12 @@ def test_multi_source_dense_matches_single_source_oracles(monkeypatch):
         assert sweeps > 0
 
 
-@pytest.mark.parametrize("group", ["1", "8"])
+@pytest.mark.parametrize("group", ["1", "2", "32"])
 def test_many_sources_lane_groups(group, monkeypatch):
-    """33 sources -> 9 chunks of 4: with DPPR_PULL_GROUP=8 eight adjacent lanes share a vertex (rows of 64, two chunk
-    groups, 31 padding columns); with 1 every lane has its own vertex.  Same answers either way."""
-    force_dense(monkeypatch, div="1e15", tiers=(4, 24, 120))
+    """33 sources -> rows of 40 = 5 pieces of 8: with DPPR_PULL_GROUP=32 eight adjacent lanes share a vertex (one chunk
+    group, 3 idle lanes of 8); with 2 two lanes share it (3 chunk groups); with 1 every lane has its own vertex (5 chunk
+    groups).  Same answers every way."""
+    force_dense(monkeypatch, div="1e15", tiers=(4, 120, 16))
     monkeypatch.setenv("DPPR_PULL_GROUP", group)
     V, M, directed = 2_500, 30_000, True
     edges = graphgen.rmat_directed(V, M, seed=11)

@@ -191,14 +191,14 @@ def test_bad_ids_are_rejected_before_they_reach_the_device():
 
 
 def _drifting_hub_stream(V, M, period, rng):
-    """every `period` edges a new set of 8 hubs attracts half of all endpoints: the sum over vertices of the PEAK window
+    """every `period` edges a new set of 8 hubs attracts a tenth of all endpoints: the sum over vertices of the PEAK window
     degree grows with the length of the stream while the live degree sum stays W"""
     e = rng.integers(0, V, size=(M, 2)).astype(np.int32)
     for start in range(0, M, period):
         hubs = rng.integers(0, V, size=8)
         sl = slice(start, min(M, start + period))
         n = sl.stop - sl.start
-        pick = rng.random(n) < 0.5
+        pick = rng.random(n) < 0.1
         e[sl, 1][pick] = hubs[rng.integers(0, 8, size=int(pick.sum()))]
     return e
 
@@ -206,8 +206,9 @@ def _drifting_hub_stream(V, M, period, rng):
 @pytest.mark.parametrize("directed,dense", [(True, 0), (False, 0), (True, 1)], ids=["directed", "undirected", "directed+outlists"])
 def test_pool_is_reused_when_hubs_drift(directed, dense):
     """>= 20 windows of a stream with drifting hubs at pool_factor 2: rings that shrank give their ranges back and the
-    bump pointer stops advancing; the window graph stays bit-exact"""
-    V, W, B = 20_000, 40_000, 2_000
+    bump pointer stops advancing; the window graph stays bit-exact.  (44 generations of hubs x 8 hubs x ~2 k slots of growth
+    ladder = 7e5 slots if nothing were reused; the pool has 8.4e4.)"""
+    V, W, B = 4_000, 40_000, 2_000
     rng = np.random.default_rng(5)
     M = W + 22 * W
     edges = _drifting_hub_stream(V, M, W // 2, rng)
