@@ -74,7 +74,7 @@ Tuning resolve_tuning(const dppr_tuning &t) {
     return r;
 }
 
-template <int VAR, bool DENSE = false>
+template <int VAR, int DENSE = 0>
 void *persistent_kernel() { return (void *)push_persistent<VAR, DENSE>; }
 
 }  // namespace
@@ -161,7 +161,7 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     DPPR_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
 
     // cooperative grid per variant: every CTA must be co-resident for the software grid barrier
-    void *kern[4] = {dense_ ? persistent_kernel<0, true>() : persistent_kernel<0>(), persistent_kernel<1>(),
+    void *kern[4] = {dense_ ? (S_ == 1 ? persistent_kernel<0, 1>() : persistent_kernel<0, 8>()) : persistent_kernel<0>(), persistent_kernel<1>(),
                      persistent_kernel<2>(), persistent_kernel<3>()};
     for (int v = 0; v < 4; ++v) {
         int per_sm = 0;
@@ -236,7 +236,8 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
         }
         const int lanes_sources = S_ == 1 ? 1 : 8 << pull_gshift_;                 // sources one pass over a vertex covers
         const int n_cg = (int)((Sr_ + lanes_sources - 1) / lanes_sources);          // chunk groups
-        tile_list_.alloc((size_t)div_up(V_, kThreads >> pull_gshift_) * n_cg);
+        tile_cap_ = (uint32_t)div_up(V_, kThreads >> pull_gshift_) * (uint32_t)n_cg;
+        tile_list_.alloc((size_t)tile_cap_ * 3);
         bigcap_ = (uint32_t)std::min<int64_t>((Ew_ / pull_big_min_ + 64) * n_cg, 1 << 24);
         big_.alloc(bigcap_);
         bigacc_.alloc((size_t)bigcap_ * lanes_sources);
@@ -564,7 +565,7 @@ void Engine::launch_push(bool init_mode) {
     if (dense_) a.dense_enter_edges = (unsigned long long)std::max(1.0, ((double)Ew_ + 2.0 * (double)V_) * (double)S_ / tn_.dense_div);
     a.dense_exit_edges = a.dense_enter_edges / 2;
     a.pull_warp_min = tn_.pull_warp_min; a.pull_big_min = pull_big_min_; a.pull_big_chunk = pull_big_chunk_;
-    a.big = big_.ptr; a.bigcap = bigcap_; a.bigacc = bigacc_.ptr; a.tile_list = tile_list_.ptr;
+    a.big = big_.ptr; a.bigcap = bigcap_; a.bigacc = bigacc_.ptr; a.tile_list = tile_list_.ptr; a.tile_list_cap = tile_cap_;
     {
         const int lanes_sources = S_ == 1 ? 1 : 8 << pull_gshift_;
         const uint64_t ntiles = (uint64_t)div_up(V_, kThreads >> pull_gshift_) * (uint64_t)((Sr_ + lanes_sources - 1) / lanes_sources);
@@ -585,7 +586,7 @@ void Engine::launch_push(bool init_mode) {
     void *params[] = {(void *)&a};
     void *kern = nullptr;
     switch (cfg_.variant) {
-        case 0: kern = dense_ ? persistent_kernel<0, true>() : persistent_kernel<0>(); break;
+        case 0: kern = dense_ ? (S_ == 1 ? persistent_kernel<0, 1>() : persistent_kernel<0, 8>()) : persistent_kernel<0>(); break;
         case 1: kern = persistent_kernel<1>(); break;
         case 2: kern = persistent_kernel<2>(); break;
         default: kern = persistent_kernel<3>(); break;
@@ -926,7 +927,9 @@ void Engine::set_state(int32_t s, const double *p, const double *r) {
         const double *h = which == 0 ? p : r;
         if (!h) continue;
         double *dst = (which == 0 ? p_.ptr : r_.ptr) + s;
-        DPPR_CUDA(cudaMemcpy(tmp.ptr, h, sizeof(double) * (size_t)V_, cudaMemcpyHostToDevice));
+        // (on the engine's stream: a pageable cudaMemcpy on the legacy stream may return before its DMA has finished, and the
+        // engine's non-blocking stream does not order against it)
+        DPPR_CUDA(cudaMemcpyAsync(tmp.ptr, h, sizeof(double) * (size_t)V_, cudaMemcpyHostToDevice, st_));
         scatter_by_perm<double><<<grid_for(V_), kThreads, 0, st_>>>(tmp.ptr, perm_.ptr, dst, Sr_, V_); ++launch_counter();
         DPPR_CUDA(cudaStreamSynchronize(st_));
     }

@@ -24,7 +24,7 @@
 //     entry (16 B = 8 sources per lane, up to 32 lanes = 512 B per request), and the per-vertex work (r row, p row, x
 //     row) is coalesced too.
 //   * no CTA-wide barrier in a sweep: a WARP owns 32 / G consecutive vertices (G = lanes per vertex).  Short lists are
-//     walked by the owning lane group with kPullUnroll independent gathers in flight; lists of warp_min or more entries
+//     walked by the owning lane group with several (PullUnroll) independent gathers in flight; lists of warp_min or more entries
 //     are walked by the whole warp and reduced by shuffles; lists of big_min or more entries are cut into chunks that any
 //     warp of the grid takes, partial sums meet in `bigacc` by FP64 atomics and the warp that completes the last chunk
 //     finishes the vertex.  One grid barrier per sweep.
@@ -36,10 +36,14 @@
 
 namespace dppr {
 
-#ifndef DPPR_PULL_UNROLL
-#define DPPR_PULL_UNROLL 8
+#ifndef DPPR_PULL_UNROLL1
+#define DPPR_PULL_UNROLL1 8
 #endif
-constexpr int kPullUnroll = DPPR_PULL_UNROLL;   // independent row gathers in flight per lane
+#ifndef DPPR_PULL_UNROLL8
+#define DPPR_PULL_UNROLL8 4
+#endif
+// independent gathers in flight per lane: 2-byte entries with one source, 16-byte row pieces with several
+template <int SB> struct PullUnroll { static constexpr int value = SB == 1 ? DPPR_PULL_UNROLL1 : DPPR_PULL_UNROLL8; };
 
 // ---- bf16 pop amounts ----------------------------------------------------------------------------------------------
 // truncation towards zero: |x| <= |r| and the remainder keeps the sign of r (a phase never creates residual of the
@@ -277,8 +281,28 @@ __device__ void pull_build(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
                 }
             }
         }
-        if (__syncthreads_or(active)) {
-            if (threadIdx.x == 0) a.tile_list[atomicAdd(&c->ntiles_active, 1u)] = tile;
+        // the tile's weight (out-list entries its vertices hold) decides its class: heavy tiles are handed out first
+        {
+            uint32_t wsum = (have && g == 0) ? wlen : 0u;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) wsum += __shfl_xor_sync(kFull, wsum, off);
+            const bool wact = __any_sync(kFull, active);
+            if (threadIdx.x == 0) { sm.pl_cnt = 0; sm.pl_n = 0; }
+            __syncthreads();
+            if (lane_id() == 0) {
+                if (wsum) atomicAdd(&sm.pl_cnt, wsum);
+                if (wact) atomicOr(&sm.pl_n, 1u);
+            }
+            __syncthreads();
+        }
+        const bool tile_active = sm.pl_n != 0;
+        if (tile_active) {
+            if (threadIdx.x == 0) {
+                const double mean = (double)a.avg_indeg * (double)q.vpt;  // (entries per tile if all lists were equal)
+                const int cls = (double)sm.pl_cnt >= 4.0 * mean ? 0 : (double)sm.pl_cnt >= 1.5 * mean ? 1 : 2;
+                a.tile_list[(size_t)cls * a.tile_list_cap + atomicAdd(&c->ntiles_b[cls], 1u)] = tile;
+                atomicAdd(&c->ntiles_active, 1u);
+            }
             if (have) {
                 const uint32_t nreal = s0 < (uint32_t)a.S ? min((uint32_t)SB, (uint32_t)a.S - s0) : 0u;
                 ep_units += nreal;
@@ -286,6 +310,7 @@ __device__ void pull_build(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
                 if (g == 0) ep_slots += wlen;
             }
         }
+        __syncthreads();  // (sm.pl_* are reused by the next tile)
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -307,6 +332,7 @@ __device__ void pull_build(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
 template <int SB>
 __device__ __forceinline__ void pull_walk(const PushArgs &a, const uint16_t *xcur, uint32_t base, uint32_t head, uint32_t mask,
                                           uint32_t first, uint32_t last, uint32_t step, uint32_t c0, double (&acc)[SB], uint32_t &nz) {
+    constexpr int kPullUnroll = PullUnroll<SB>::value;
     uint32_t k = first;
     for (; k + (kPullUnroll - 1) * step < last; k += kPullUnroll * step) {
         uint32_t u[kPullUnroll];
@@ -340,23 +366,44 @@ __device__ __forceinline__ void pull_reduce_groups(double (&part)[SB], uint32_t 
 }
 
 // ---- one sweep -------------------------------------------------------------------------------------------------------
+// Work items -- first the chunks of the grid tier (the longest tasks), then the active tiles, heavy classes first -- are
+// handed out one at a time to WARPS by an atomic counter (round 2: with the static tile -> CTA assignment 20-35 % of a
+// sweep was spent waiting at its closing barrier).  A warp processes a whole tile (kThreads / G vertices, 32 / G at a
+// time); the index of its next item is requested before the current one is processed, so the atomic's round trip is hidden.
 // `gath` counts the gathered x entries that were non-zero: exactly the (edge, source) pairs the push form would have
 // traversed.
 template <int SB>
+__device__ __forceinline__ uint32_t pull_tile_at(const PushArgs &a, uint32_t j, uint32_t n0, uint32_t n1) {
+    if (j < n0) return __ldcg(&a.tile_list[j]);
+    j -= n0;
+    if (j < n1) return __ldcg(&a.tile_list[(size_t)a.tile_list_cap + j]);
+    return __ldcg(&a.tile_list[2 * (size_t)a.tile_list_cap + (j - n1)]);
+}
+
+template <int SB>
 __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, const uint16_t *xcur, uint16_t *xnext,
-                           unsigned int *cnt_out, unsigned long long *edges_out, unsigned long long &gath) {
+                           unsigned int *cnt_out, unsigned long long *edges_out, unsigned long long &gath, uint32_t sweep_index) {
     const PullGeom q = pull_geom<SB>(a);
     const uint32_t V = (uint32_t)a.V;
     const uint32_t lane = lane_id(), grp = lane >> q.gs, g = lane & (q.G - 1u);
     uint32_t legal = 0, nz = 0;
     unsigned long long next_edges = 0;
+    const unsigned long long bp = __ldcg(&c->bigpk);
+    const uint32_t nh = min((uint32_t)(bp >> 32), a.bigcap), nchunks = nh ? (uint32_t)bp : 0u;
+    const uint32_t n0 = __ldcg(&c->ntiles_b[0]), n1 = __ldcg(&c->ntiles_b[1]), n2 = __ldcg(&c->ntiles_b[2]);
+    const uint32_t nwork = nchunks + n0 + n1 + n2;
+    unsigned int *next = &c->work_next[sweep_index & 1u];
+    if (blockIdx.x == 0 && threadIdx.x == 0) c->work_next[(sweep_index + 1u) & 1u] = 0u;  // (idle during this sweep)
 
-    // ---- grid tier first (the longest tasks): chunks of the long out-lists, one warp per chunk ----
-    {
-        const unsigned long long bp = __ldcg(&c->bigpk);
-        const uint32_t nh = min((uint32_t)(bp >> 32), a.bigcap), nchunks = (uint32_t)bp;
-        const uint32_t gwarp = blockIdx.x * kWarps + warp_id(), nwarps = gridDim.x * kWarps;
-        for (uint32_t cidx = gwarp; cidx < nchunks; cidx += nwarps) {
+    uint32_t j = 0;
+    if (lane == 0) j = atomicAdd(next, 1u);
+    j = __shfl_sync(kFull, j, 0);
+    while (j < nwork) {
+        uint32_t jn = 0;
+        if (lane == 0) jn = atomicAdd(next, 1u);  // consumed at the bottom of the loop
+        if (j < nchunks) {
+            // ---- a chunk of a long out-list ----
+            const uint32_t cidx = j;
             uint32_t lo = 0, hi = nh;  // last list entry with chunk0 <= cidx
             while (hi - lo > 1) {
                 const uint32_t mid = (lo + hi) >> 1;
@@ -370,14 +417,14 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
             const uint32_t e1 = min(m.z, e0 + (uint32_t)a.pull_big_chunk);
             double part[SB];
 #pragma unroll
-            for (int j = 0; j < SB; ++j) part[j] = 0.0;
+            for (int jj = 0; jj < SB; ++jj) part[jj] = 0.0;
             if (s0 < (uint32_t)a.Sr) pull_walk<SB>(a, xcur, m.x, m.y, m.w - 1u, e0 + grp, e1, q.vpw, s0, part, nz);
             pull_reduce_groups<SB>(part, q.G);
             double *accrow = a.bigacc + (size_t)lo * (size_t)(q.G * SB);
             if (grp == 0 && s0 < (uint32_t)a.Sr) {
 #pragma unroll
-                for (int j = 0; j < SB; ++j)
-                    if (part[j] != 0.0) atomicAdd(&accrow[g * SB + j], part[j]);
+                for (int jj = 0; jj < SB; ++jj)
+                    if (part[jj] != 0.0) atomicAdd(&accrow[g * SB + jj], part[jj]);
             }
             __threadfence();  // the partial sums are out before the chunk is counted
             __syncwarp();
@@ -389,59 +436,58 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
                 if (grp == 0 && s0 < (uint32_t)a.Sr) {
                     double acc[SB];
 #pragma unroll
-                    for (int j = 0; j < SB; ++j) {
-                        acc[j] = __ldcg(&accrow[g * SB + j]);
-                        __stcg(&accrow[g * SB + j], 0.0);
+                    for (int jj = 0; jj < SB; ++jj) {
+                        acc[jj] = __ldcg(&accrow[g * SB + jj]);
+                        __stcg(&accrow[g * SB + jj], 0.0);
                     }
                     const XPiece<SB> xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
                     legal += pull_finish_unit<SB>(a, phase, w, s0, m.z, xc, acc, xnext, next_edges);
                 }
                 if (lane == 0) a.big[lo].pad[kBigDone] = 0u;  // (ready for the next sweep)
             }
-        }
-    }
-
-    // ---- the active tiles: a warp owns 32 / G consecutive vertices ----
-    const uint32_t ntiles = __ldcg(&c->ntiles_active);
-    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const uint32_t tile = __ldcg(&a.tile_list[t]);
-        const uint32_t cg = tile / q.tpc;
-        const uint32_t w = (tile - cg * q.tpc) * q.vpt + warp_id() * q.vpw + grp;
-        const uint32_t s0 = (cg * q.G + g) * SB;
-        const bool have = w < V && s0 < (uint32_t)a.Sr;
-        XPiece<SB> xc = x_zero<SB>();
-        double acc[SB];
+        } else {
+            // ---- a tile: kThreads / G consecutive vertices, 32 / G at a time ----
+            const uint32_t tile = pull_tile_at<SB>(a, j - nchunks, n0, n1);
+            const uint32_t cg = tile / q.tpc;
+            const uint32_t w0 = (tile - cg * q.tpc) * q.vpt;
+            const uint32_t s0 = (cg * q.G + g) * SB;
+            for (uint32_t sub = 0; sub < (uint32_t)kWarps; ++sub) {
+                const uint32_t w = w0 + sub * q.vpw + grp;
+                if (w0 + sub * q.vpw >= V) break;  // (warp-uniform)
+                const bool have = w < V && s0 < (uint32_t)a.Sr;
+                XPiece<SB> xc = x_zero<SB>();
+                double acc[SB];
 #pragma unroll
-        for (int j = 0; j < SB; ++j) acc[j] = 0.0;
-        uint32_t len = 0, base = 0, head = 0, mask = 0;
-        if (w < V) {
-            len = (uint32_t)pl_ldcs(&a.outdeg[w]);
-            if (len) {
-                const uint4 m = pl_ldcs(&a.vmeta_out[w]);
-                base = m.x; head = m.y; len = m.z; mask = m.w - 1u;
+                for (int jj = 0; jj < SB; ++jj) acc[jj] = 0.0;
+                uint32_t len = 0, base = 0, head = 0, mask = 0;
+                if (w < V) {
+                    const uint4 m = pl_ldcs(&a.vmeta_out[w]);  // (the length of an out-list IS the out-degree)
+                    base = m.x; head = m.y; len = m.z; mask = m.w - 1u;
+                }
+                if (have) xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
+                const int tier = len >= (uint32_t)a.pull_big_min ? 2 : (len >= (uint32_t)a.pull_warp_min && q.vpw > 1u) ? 1 : 0;
+                if (tier == 0 && have && len) pull_walk<SB>(a, xcur, base, head, mask, 0u, len, 1u, s0, acc, nz);
+                // lists of warp_min or more entries: the whole warp walks them, one after the other
+                unsigned m1 = __ballot_sync(kFull, tier == 1 && g == 0 && w < V);
+                while (m1) {
+                    const int L = __ffs(m1) - 1;
+                    m1 &= m1 - 1u;
+                    const uint32_t eb = __shfl_sync(kFull, base, L), eh = __shfl_sync(kFull, head, L), el = __shfl_sync(kFull, len, L),
+                                   em = __shfl_sync(kFull, mask, L);
+                    double part[SB];
+#pragma unroll
+                    for (int jj = 0; jj < SB; ++jj) part[jj] = 0.0;
+                    if (s0 < (uint32_t)a.Sr) pull_walk<SB>(a, xcur, eb, eh, em, grp, el, q.vpw, s0, part, nz);
+                    pull_reduce_groups<SB>(part, q.G);
+                    if (grp == ((uint32_t)L >> q.gs)) {
+#pragma unroll
+                        for (int jj = 0; jj < SB; ++jj) acc[jj] = part[jj];
+                    }
+                }
+                if (tier != 2 && have) legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, next_edges);
             }
         }
-        if (have) xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
-        const int tier = len >= (uint32_t)a.pull_big_min ? 2 : (len >= (uint32_t)a.pull_warp_min && q.vpw > 1u) ? 1 : 0;
-        if (tier == 0 && have && len) pull_walk<SB>(a, xcur, base, head, mask, 0u, len, 1u, s0, acc, nz);
-        // lists of warp_min or more entries: the whole warp walks them, one after the other
-        unsigned m1 = __ballot_sync(kFull, tier == 1 && g == 0 && w < V);
-        while (m1) {
-            const int L = __ffs(m1) - 1;
-            m1 &= m1 - 1u;
-            const uint32_t eb = __shfl_sync(kFull, base, L), eh = __shfl_sync(kFull, head, L), el = __shfl_sync(kFull, len, L),
-                           em = __shfl_sync(kFull, mask, L);
-            double part[SB];
-#pragma unroll
-            for (int j = 0; j < SB; ++j) part[j] = 0.0;
-            if (s0 < (uint32_t)a.Sr) pull_walk<SB>(a, xcur, eb, eh, em, grp, el, q.vpw, s0, part, nz);
-            pull_reduce_groups<SB>(part, q.G);
-            if (grp == ((uint32_t)L >> q.gs)) {
-#pragma unroll
-                for (int j = 0; j < SB; ++j) acc[j] = part[j];
-            }
-        }
-        if (tier != 2 && have) legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, next_edges);
+        j = __shfl_sync(kFull, jn, 0);
     }
     gath += nz;
     pull_count_flush(sm, legal, cnt_out, next_edges, edges_out);
@@ -455,9 +501,9 @@ __device__ void pull_compact(const PushArgs &a, PushSmem &sm, PushCtrl *c, const
                              unsigned int *cnt_out) {
     const PullGeom q = pull_geom<SB>(a);
     const uint32_t V = (uint32_t)a.V;
-    const uint32_t ntiles = __ldcg(&c->ntiles_active);
+    const uint32_t n0 = __ldcg(&c->ntiles_b[0]), n1 = __ldcg(&c->ntiles_b[1]), ntiles = n0 + n1 + __ldcg(&c->ntiles_b[2]);
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const uint32_t tile = __ldcg(&a.tile_list[t]);
+        const uint32_t tile = pull_tile_at<SB>(a, t, n0, n1);
         const uint32_t cg = tile / q.tpc;
         const uint32_t w = (tile - cg * q.tpc) * q.vpt + (threadIdx.x >> q.gs), g = threadIdx.x & (q.G - 1u);
         const uint32_t s0 = (cg * q.G + g) * SB;
@@ -488,6 +534,8 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
         c->dedges[0] = 0; c->dedges[1] = 0; c->dedges[2] = 0;
         c->bigpk = 0;
         c->ntiles_active = 0;
+        c->ntiles_b[0] = 0; c->ntiles_b[1] = 0; c->ntiles_b[2] = 0;
+        c->work_next[0] = 0; c->work_next[1] = 0;
         c->ep_slots = 0; c->ep_pairs = 0; c->ep_units = 0;
     }
     // ... and are simply UN-popped instead of being scattered edge by edge: r[u] += ru, p[u] -= a ru (one thread per hub;
@@ -541,7 +589,7 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
                 a.iterlog[iters_done] = make_uint4(n, 0xffffffffu, (uint32_t)t, (uint32_t)(t >> 32));
             }
         }
-        pull_sweep<SB>(a, sm, c, phase, a.x[cur], a.x[cur ^ 1], &c->dcnt[(k + 1) % 3], &c->dedges[(k + 1) % 3], gath);
+        pull_sweep<SB>(a, sm, c, phase, a.x[cur], a.x[cur ^ 1], &c->dcnt[(k + 1) % 3], &c->dedges[(k + 1) % 3], gath, k);
         if (!grid_barrier(c, gen, sm)) return false;
         cur ^= 1;
         ++k;

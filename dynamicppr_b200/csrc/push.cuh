@@ -75,7 +75,9 @@ struct PushCtrl {
     unsigned long long dedges[3];  // dense mode (pull.cuh): in-edges a scatter iteration over the next frontier would traverse
     unsigned int dcnt[3];          // dense mode: frontier sizes, rotating like cnt
     unsigned int sweeps;           // dense sweeps of this refresh
-    unsigned int ntiles_active;    // dense mode: length of tile_list
+    unsigned int ntiles_active;    // dense mode: active tiles of the running episode = sum of ntiles_b
+    unsigned int ntiles_b[3];      // ... by weight class (heavy first): tile_list holds three lists of tile_list_cap entries
+    unsigned int work_next[2];     // dense mode: next work item (grid-tier chunk, then tile) of the running sweep, by sweep parity
     unsigned int pad0;
     unsigned long long bigpk;      // dense mode: grid-tier list of the running sweep, (entries << 32) | chunks
     unsigned long long gath;       // dense sweeps: gathered x entries that were non-zero = the (edge, source) pairs a scatter
@@ -141,7 +143,8 @@ struct PushArgs {
     unsigned long long dense_exit_edges;   // ... and below this the loop goes back to scatter iterations
     int32_t pull_warp_min, pull_big_min, pull_big_chunk;  // out-degree tiers of a sweep; entries per chunk of the grid tier
     uint32_t pull_tile_mul;      // tile visiting order: tile = (t * mul) mod ntiles, mul coprime to ntiles
-    uint32_t *tile_list;         // active tiles of the running dense episode
+    uint32_t *tile_list;         // active tiles of the running dense episode: [3][tile_list_cap], heavy tiles first
+    uint32_t tile_list_cap;
     HubItem *big;                // grid-tier list
     uint32_t bigcap;
     double *bigacc;              // [bigcap][lanes per vertex x sources per lane] partial sums of the grid tier (zero between sweeps)
@@ -620,15 +623,20 @@ __device__ __forceinline__ bool grid_barrier(PushCtrl *c, GridBar &gb, Smem &sm,
 namespace dppr {
 
 // ---- the persistent kernel ----------------------------------------------------------------------------
-// DENSE: with the switch to gather sweeps (variant 0 only).  A separate instantiation, so that the scatter-only
+// DENSE != 0: with the switch to gather sweeps (variant 0 only).  Separate instantiations, so that the scatter-only
 // kernels keep their register allocation.
-#ifndef DPPR_DENSE_MIN_BLOCKS
-#define DPPR_DENSE_MIN_BLOCKS 2
+#ifndef DPPR_DENSE1_MIN_BLOCKS
+#define DPPR_DENSE1_MIN_BLOCKS 4
 #endif
-// (the switching kernel gets 128 registers per thread: its sweeps keep kPullUnroll row gathers in flight per lane and
-// must not spill -- round 1's 64-register build issued 5.2 G local loads per refresh on BASELINE configs[3])
-template <int VAR, bool DENSE>
-__global__ void __launch_bounds__(kThreads, DENSE ? DPPR_DENSE_MIN_BLOCKS : DPPR_MIN_BLOCKS) push_persistent(const PushArgs a) {
+#ifndef DPPR_DENSE8_MIN_BLOCKS
+#define DPPR_DENSE8_MIN_BLOCKS 2
+#endif
+// DENSE = sources a lane of a sweep takes: 0 (scatter only), 1 (one source) or 8 (several).  The multi-source switching
+// kernel gets 128 registers per thread: its sweeps keep several 16-byte row pieces in flight per lane and must not
+// spill -- round 1's 64-register build issued 5.2 G local loads per refresh on BASELINE configs[3].
+template <int VAR, int DENSE>
+__global__ void __launch_bounds__(kThreads, DENSE == 8 ? DPPR_DENSE8_MIN_BLOCKS : DENSE == 1 ? DPPR_DENSE1_MIN_BLOCKS : DPPR_MIN_BLOCKS)
+    push_persistent(const PushArgs a) {
     __shared__ PushSmem sm;
     PushCtrl *c = a.ctrl;
     if (threadIdx.x == 0) { sm.stage_cnt = 0; sm.abort_flag = 0; }
@@ -739,7 +747,7 @@ __global__ void __launch_bounds__(kThreads, DENSE ? DPPR_DENSE_MIN_BLOCKS : DPPR
                     if (!(alive = grid_barrier(c, gen, sm))) break;
                     post_pass(a, sm, qin, a.qr[it & 1], n, qout, &c->cnt[(it + 1) % 3], phase);
                 }
-                if (!(alive = grid_barrier<DENSE>(c, gen, sm, DENSE ? (uint32_t)((edges_acc - edges_before) >> 6) : 0u))) break;
+                if (!(alive = grid_barrier<(DENSE != 0)>(c, gen, sm, DENSE ? (uint32_t)((edges_acc - edges_before) >> 6) : 0u))) break;
                 if (DENSE) {
                     const double t_all = 64.0 * (double)sm.bar_units;  // tiles + hub chunks, grid-wide
                     t_prev = fmax(0.0, t_all - 0.75 * (double)kHubChunk * (double)(uint32_t)hpk);
@@ -766,7 +774,7 @@ __global__ void __launch_bounds__(kThreads, DENSE ? DPPR_DENSE_MIN_BLOCKS : DPPR
             fresh_phase = false;
             t_prev = 0.0;
             DenseIO io{edges_acc, gath_acc, pops_acc, iters_done, sweeps_done, gen, dense_rate};
-            alive = a.Sr == 1 ? dense_mode<1>(a, sm, c, phase, it, dense_hpk, io) : dense_mode<8>(a, sm, c, phase, it, dense_hpk, io);
+            alive = dense_mode<(DENSE ? DENSE : 1)>(a, sm, c, phase, it, dense_hpk, io);
             edges_acc = io.edges_acc; gath_acc = io.gath; pops_acc = io.pops_acc;
             iters_done = io.iters_done; sweeps_done = io.sweeps_done; gen = io.gen;
             ++it;
