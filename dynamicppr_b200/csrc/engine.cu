@@ -566,6 +566,7 @@ void Engine::launch_push(bool init_mode) {
     a.dense_exit_edges = a.dense_enter_edges / 2;
     a.pull_warp_min = tn_.pull_warp_min; a.pull_big_min = pull_big_min_; a.pull_big_chunk = pull_big_chunk_;
     a.big = big_.ptr; a.bigcap = bigcap_; a.bigacc = bigacc_.ptr; a.tile_list = tile_list_.ptr; a.tile_list_cap = tile_cap_;
+    a.pull_sched = env_int("DPPR_PULL_SCHED", S_ == 1 ? 0 : 1);
     {
         const int lanes_sources = S_ == 1 ? 1 : 8 << pull_gshift_;
         const uint64_t ntiles = (uint64_t)div_up(V_, kThreads >> pull_gshift_) * (uint64_t)((Sr_ + lanes_sources - 1) / lanes_sources);

@@ -380,117 +380,163 @@ __device__ __forceinline__ uint32_t pull_tile_at(const PushArgs &a, uint32_t j, 
     return __ldcg(&a.tile_list[2 * (size_t)a.tile_list_cap + (j - n1)]);
 }
 
+// per-warp running totals of a sweep
+struct PullAcc {
+    uint32_t legal = 0, nz = 0;
+    unsigned long long next_edges = 0;
+};
+
+// one chunk of a long out-list, by one warp; the warp that completes the last chunk of a vertex finishes it
+template <int SB>
+__device__ __forceinline__ void pull_do_chunk(const PushArgs &a, const PullGeom &q, int phase, const uint16_t *xcur, uint16_t *xnext,
+                                              uint32_t cidx, uint32_t nh, PullAcc &t) {
+    const uint32_t lane = lane_id(), grp = lane >> q.gs, g = lane & (q.G - 1u);
+    uint32_t lo = 0, hi = nh;  // last list entry with chunk0 <= cidx
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldcg(&a.big[mid].chunk0) <= cidx) lo = mid; else hi = mid;
+    }
+    const unsigned long long item = __ldcg(&a.big[lo].item);
+    const uint32_t w = (uint32_t)item, cg = (uint32_t)(item >> 32);
+    const uint32_t s0 = (cg * q.G + g) * SB;
+    const uint4 m = __ldg(&a.vmeta_out[w]);
+    const uint32_t e0 = (cidx - __ldcg(&a.big[lo].chunk0)) * (uint32_t)a.pull_big_chunk;
+    const uint32_t e1 = min(m.z, e0 + (uint32_t)a.pull_big_chunk);
+    double part[SB];
+#pragma unroll
+    for (int jj = 0; jj < SB; ++jj) part[jj] = 0.0;
+    if (s0 < (uint32_t)a.Sr) pull_walk<SB>(a, xcur, m.x, m.y, m.w - 1u, e0 + grp, e1, q.vpw, s0, part, t.nz);
+    pull_reduce_groups<SB>(part, q.G);
+    double *accrow = a.bigacc + (size_t)lo * (size_t)(q.G * SB);
+    if (grp == 0 && s0 < (uint32_t)a.Sr) {
+#pragma unroll
+        for (int jj = 0; jj < SB; ++jj)
+            if (part[jj] != 0.0) atomicAdd(&accrow[g * SB + jj], part[jj]);
+    }
+    __threadfence();  // the partial sums are out before the chunk is counted
+    __syncwarp();
+    uint32_t done = 0;
+    if (lane == 0) done = atomicAdd(&a.big[lo].pad[kBigDone], 1u) + 1u;
+    done = __shfl_sync(kFull, done, 0);
+    if (done == __ldcg(&a.big[lo].pad[kBigChunks])) {
+        __threadfence();
+        if (grp == 0 && s0 < (uint32_t)a.Sr) {
+            double acc[SB];
+#pragma unroll
+            for (int jj = 0; jj < SB; ++jj) {
+                acc[jj] = __ldcg(&accrow[g * SB + jj]);
+                __stcg(&accrow[g * SB + jj], 0.0);
+            }
+            const XPiece<SB> xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
+            t.legal += pull_finish_unit<SB>(a, phase, w, s0, m.z, xc, acc, xnext, t.next_edges);
+        }
+        if (lane == 0) a.big[lo].pad[kBigDone] = 0u;  // (ready for the next sweep)
+    }
+}
+
+// the 32 / G consecutive vertices starting at wfirst (chunk group cg), by one warp
+template <int SB>
+__device__ __forceinline__ void pull_do_vertices(const PushArgs &a, const PullGeom &q, int phase, const uint16_t *xcur, uint16_t *xnext,
+                                                 uint32_t wfirst, uint32_t cg, PullAcc &t) {
+    const uint32_t V = (uint32_t)a.V;
+    const uint32_t lane = lane_id(), grp = lane >> q.gs, g = lane & (q.G - 1u);
+    const uint32_t w = wfirst + grp, s0 = (cg * q.G + g) * SB;
+    const bool have = w < V && s0 < (uint32_t)a.Sr;
+    XPiece<SB> xc = x_zero<SB>();
+    double acc[SB];
+#pragma unroll
+    for (int jj = 0; jj < SB; ++jj) acc[jj] = 0.0;
+    uint32_t len = 0, base = 0, head = 0, mask = 0;
+    if (w < V) {
+        const uint4 m = pl_ldcs(&a.vmeta_out[w]);  // (the length of an out-list IS the out-degree)
+        base = m.x; head = m.y; len = m.z; mask = m.w - 1u;
+    }
+    if (have) xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
+    const int tier = len >= (uint32_t)a.pull_big_min ? 2 : (len >= (uint32_t)a.pull_warp_min && q.vpw > 1u) ? 1 : 0;
+    if (tier == 0 && have && len) pull_walk<SB>(a, xcur, base, head, mask, 0u, len, 1u, s0, acc, t.nz);
+    // lists of warp_min or more entries: the whole warp walks them, one after the other
+    unsigned m1 = __ballot_sync(kFull, tier == 1 && g == 0 && w < V);
+    while (m1) {
+        const int L = __ffs(m1) - 1;
+        m1 &= m1 - 1u;
+        const uint32_t eb = __shfl_sync(kFull, base, L), eh = __shfl_sync(kFull, head, L), el = __shfl_sync(kFull, len, L),
+                       em = __shfl_sync(kFull, mask, L);
+        double part[SB];
+#pragma unroll
+        for (int jj = 0; jj < SB; ++jj) part[jj] = 0.0;
+        if (s0 < (uint32_t)a.Sr) pull_walk<SB>(a, xcur, eb, eh, em, grp, el, q.vpw, s0, part, t.nz);
+        pull_reduce_groups<SB>(part, q.G);
+        if (grp == ((uint32_t)L >> q.gs)) {
+#pragma unroll
+            for (int jj = 0; jj < SB; ++jj) acc[jj] = part[jj];
+        }
+    }
+    if (tier != 2 && have) t.legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, t.next_edges);
+}
+
 template <int SB>
 __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, const uint16_t *xcur, uint16_t *xnext,
                            unsigned int *cnt_out, unsigned long long *edges_out, unsigned long long &gath, uint32_t sweep_index) {
     const PullGeom q = pull_geom<SB>(a);
     const uint32_t V = (uint32_t)a.V;
-    const uint32_t lane = lane_id(), grp = lane >> q.gs, g = lane & (q.G - 1u);
-    uint32_t legal = 0, nz = 0;
-    unsigned long long next_edges = 0;
+    const uint32_t lane = lane_id();
+    PullAcc t;
     const unsigned long long bp = __ldcg(&c->bigpk);
     const uint32_t nh = min((uint32_t)(bp >> 32), a.bigcap), nchunks = nh ? (uint32_t)bp : 0u;
     const uint32_t n0 = __ldcg(&c->ntiles_b[0]), n1 = __ldcg(&c->ntiles_b[1]), n2 = __ldcg(&c->ntiles_b[2]);
-    const uint32_t nwork = nchunks + n0 + n1 + n2;
     unsigned int *next = &c->work_next[sweep_index & 1u];
     if (blockIdx.x == 0 && threadIdx.x == 0) c->work_next[(sweep_index + 1u) & 1u] = 0u;  // (idle during this sweep)
 
-    uint32_t j = 0;
-    if (lane == 0) j = atomicAdd(next, 1u);
-    j = __shfl_sync(kFull, j, 0);
-    while (j < nwork) {
-        uint32_t jn = 0;
-        if (lane == 0) jn = atomicAdd(next, 1u);  // consumed at the bottom of the loop
-        if (j < nchunks) {
-            // ---- a chunk of a long out-list ----
-            const uint32_t cidx = j;
-            uint32_t lo = 0, hi = nh;  // last list entry with chunk0 <= cidx
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (__ldcg(&a.big[mid].chunk0) <= cidx) lo = mid; else hi = mid;
+    if (a.pull_sched == 0) {
+        // ---- items handed to WARPS: a warp takes a chunk, or a whole tile (its kThreads / G vertices, 32 / G at a time) ----
+        const uint32_t nwork = nchunks + n0 + n1 + n2;
+        uint32_t j = 0;
+        if (lane == 0) j = atomicAdd(next, 1u);
+        j = __shfl_sync(kFull, j, 0);
+        while (j < nwork) {
+            uint32_t jn = 0;
+            if (lane == 0) jn = atomicAdd(next, 1u);  // consumed at the bottom of the loop
+            if (j < nchunks) {
+                pull_do_chunk<SB>(a, q, phase, xcur, xnext, j, nh, t);
+            } else {
+                const uint32_t tile = pull_tile_at<SB>(a, j - nchunks, n0, n1);
+                const uint32_t cg = tile / q.tpc;
+                const uint32_t w0 = (tile - cg * q.tpc) * q.vpt;
+                for (uint32_t sub = 0; sub < (uint32_t)kWarps && w0 + sub * q.vpw < V; ++sub)
+                    pull_do_vertices<SB>(a, q, phase, xcur, xnext, w0 + sub * q.vpw, cg, t);
             }
-            const unsigned long long item = __ldcg(&a.big[lo].item);
-            const uint32_t w = (uint32_t)item, cg = (uint32_t)(item >> 32);
-            const uint32_t s0 = (cg * q.G + g) * SB;
-            const uint4 m = __ldg(&a.vmeta_out[w]);
-            const uint32_t e0 = (cidx - __ldcg(&a.big[lo].chunk0)) * (uint32_t)a.pull_big_chunk;
-            const uint32_t e1 = min(m.z, e0 + (uint32_t)a.pull_big_chunk);
-            double part[SB];
-#pragma unroll
-            for (int jj = 0; jj < SB; ++jj) part[jj] = 0.0;
-            if (s0 < (uint32_t)a.Sr) pull_walk<SB>(a, xcur, m.x, m.y, m.w - 1u, e0 + grp, e1, q.vpw, s0, part, nz);
-            pull_reduce_groups<SB>(part, q.G);
-            double *accrow = a.bigacc + (size_t)lo * (size_t)(q.G * SB);
-            if (grp == 0 && s0 < (uint32_t)a.Sr) {
-#pragma unroll
-                for (int jj = 0; jj < SB; ++jj)
-                    if (part[jj] != 0.0) atomicAdd(&accrow[g * SB + jj], part[jj]);
-            }
-            __threadfence();  // the partial sums are out before the chunk is counted
-            __syncwarp();
-            uint32_t done = 0;
-            if (lane == 0) done = atomicAdd(&a.big[lo].pad[kBigDone], 1u) + 1u;
-            done = __shfl_sync(kFull, done, 0);
-            if (done == __ldcg(&a.big[lo].pad[kBigChunks])) {  // this warp completed the vertex: finish it
-                __threadfence();
-                if (grp == 0 && s0 < (uint32_t)a.Sr) {
-                    double acc[SB];
-#pragma unroll
-                    for (int jj = 0; jj < SB; ++jj) {
-                        acc[jj] = __ldcg(&accrow[g * SB + jj]);
-                        __stcg(&accrow[g * SB + jj], 0.0);
-                    }
-                    const XPiece<SB> xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
-                    legal += pull_finish_unit<SB>(a, phase, w, s0, m.z, xc, acc, xnext, next_edges);
-                }
-                if (lane == 0) a.big[lo].pad[kBigDone] = 0u;  // (ready for the next sweep)
-            }
-        } else {
-            // ---- a tile: kThreads / G consecutive vertices, 32 / G at a time ----
-            const uint32_t tile = pull_tile_at<SB>(a, j - nchunks, n0, n1);
-            const uint32_t cg = tile / q.tpc;
-            const uint32_t w0 = (tile - cg * q.tpc) * q.vpt;
-            const uint32_t s0 = (cg * q.G + g) * SB;
-            for (uint32_t sub = 0; sub < (uint32_t)kWarps; ++sub) {
-                const uint32_t w = w0 + sub * q.vpw + grp;
-                if (w0 + sub * q.vpw >= V) break;  // (warp-uniform)
-                const bool have = w < V && s0 < (uint32_t)a.Sr;
-                XPiece<SB> xc = x_zero<SB>();
-                double acc[SB];
-#pragma unroll
-                for (int jj = 0; jj < SB; ++jj) acc[jj] = 0.0;
-                uint32_t len = 0, base = 0, head = 0, mask = 0;
-                if (w < V) {
-                    const uint4 m = pl_ldcs(&a.vmeta_out[w]);  // (the length of an out-list IS the out-degree)
-                    base = m.x; head = m.y; len = m.z; mask = m.w - 1u;
-                }
-                if (have) xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
-                const int tier = len >= (uint32_t)a.pull_big_min ? 2 : (len >= (uint32_t)a.pull_warp_min && q.vpw > 1u) ? 1 : 0;
-                if (tier == 0 && have && len) pull_walk<SB>(a, xcur, base, head, mask, 0u, len, 1u, s0, acc, nz);
-                // lists of warp_min or more entries: the whole warp walks them, one after the other
-                unsigned m1 = __ballot_sync(kFull, tier == 1 && g == 0 && w < V);
-                while (m1) {
-                    const int L = __ffs(m1) - 1;
-                    m1 &= m1 - 1u;
-                    const uint32_t eb = __shfl_sync(kFull, base, L), eh = __shfl_sync(kFull, head, L), el = __shfl_sync(kFull, len, L),
-                                   em = __shfl_sync(kFull, mask, L);
-                    double part[SB];
-#pragma unroll
-                    for (int jj = 0; jj < SB; ++jj) part[jj] = 0.0;
-                    if (s0 < (uint32_t)a.Sr) pull_walk<SB>(a, xcur, eb, eh, em, grp, el, q.vpw, s0, part, nz);
-                    pull_reduce_groups<SB>(part, q.G);
-                    if (grp == ((uint32_t)L >> q.gs)) {
-#pragma unroll
-                        for (int jj = 0; jj < SB; ++jj) acc[jj] = part[jj];
-                    }
-                }
-                if (tier != 2 && have) legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, next_edges);
-            }
+            j = __shfl_sync(kFull, jn, 0);
         }
-        j = __shfl_sync(kFull, jn, 0);
+    } else {
+        // ---- items handed to CTAs: kWarps chunks, or one tile whose vertices the CTA's warps share ----
+        const uint32_t ngroups = (nchunks + kWarps - 1) / kWarps;
+        const uint32_t nwork = ngroups + n0 + n1 + n2;
+        unsigned int *slot = &sm.pl_n;  // (two words used alternately: one barrier per item)
+        if (threadIdx.x == 0) sm.pl_n = atomicAdd(next, 1u);
+        __syncthreads();
+        uint32_t j = sm.pl_n;
+        uint32_t flip = 0;
+        while (j < nwork) {
+            unsigned int *nslot = flip ? &sm.pl_n : &sm.gbase;
+            if (threadIdx.x == 0) *nslot = atomicAdd(next, 1u);
+            if (j < ngroups) {
+                const uint32_t cidx = j * kWarps + warp_id();
+                if (cidx < nchunks) pull_do_chunk<SB>(a, q, phase, xcur, xnext, cidx, nh, t);
+            } else {
+                const uint32_t tile = pull_tile_at<SB>(a, j - ngroups, n0, n1);
+                const uint32_t cg = tile / q.tpc;
+                const uint32_t wf = (tile - cg * q.tpc) * q.vpt + warp_id() * q.vpw;
+                if (wf < V) pull_do_vertices<SB>(a, q, phase, xcur, xnext, wf, cg, t);
+            }
+            __syncthreads();
+            j = *nslot;
+            flip ^= 1u;
+            (void)slot;
+        }
+        __syncthreads();
     }
-    gath += nz;
-    pull_count_flush(sm, legal, cnt_out, next_edges, edges_out);
+    gath += t.nz;
+    pull_count_flush(sm, t.legal, cnt_out, t.next_edges, edges_out);
 }
 
 // ---- leaving dense mode ----------------------------------------------------------------------------------------------

@@ -145,6 +145,7 @@ struct PushArgs {
     uint32_t pull_tile_mul;      // tile visiting order: tile = (t * mul) mod ntiles, mul coprime to ntiles
     uint32_t *tile_list;         // active tiles of the running dense episode: [3][tile_list_cap], heavy tiles first
     uint32_t tile_list_cap;
+    int32_t pull_sched;          // who takes a work item of a sweep: 0 = a warp, 1 = a CTA (its warps share a tile's vertices)
     HubItem *big;                // grid-tier list
     uint32_t bigcap;
     double *bigacc;              // [bigcap][lanes per vertex x sources per lane] partial sums of the grid tier (zero between sweeps)

@@ -234,7 +234,7 @@ def test_pool_is_reused_when_hubs_drift(directed, dense):
     Ew = W * (1 if directed else 2) * (2 if (directed and dense) else 1)
     assert tops[-1] <= 2.0 * Ew + 4096
     # the second half of the run allocates (almost) nothing new: everything comes off the free stacks
-    assert tops[-1] - tops[len(tops) // 2] <= 0.02 * Ew, tops
+    assert tops[-1] - tops[len(tops) // 2] <= 0.05 * Ew, tops
 
 
 def test_timing_events_are_recycled_over_many_small_batches():
