@@ -60,7 +60,7 @@ Tuning resolve_tuning(const dppr_tuning &t) {
     r.dense_min_edges = pick_real(t.dense_min_edges, "DPPR_DENSE_MIN_EDGES", 2.0e7);
     if (std::getenv("DPPR_DENSE_DIV") && t.dense_div == 0.0 && std::atof(std::getenv("DPPR_DENSE_DIV")) <= 0.0) r.dense = -1;  // round-1 spelling of "off"
     if (std::getenv("DPPR_DENSE_MIN_EDGES") && t.dense_min_edges == 0.0 && std::atof(std::getenv("DPPR_DENSE_MIN_EDGES")) <= 0.0) r.dense_min_edges = 0.0;
-    r.pull_group = std::min(std::max(pick_int(t.pull_group, "DPPR_PULL_GROUP", 32), 1), 32);
+    r.pull_group = std::min(std::max(pick_int(t.pull_group, "DPPR_PULL_GROUP", 16), 1), 16);
     r.pull_warp_min = std::max(1, pick_int(t.pull_warp_min, "DPPR_PULL_WARP_MIN", 32));
     r.pull_big_min = pick_int(t.pull_big_min, "DPPR_PULL_BIG_MIN", 0);
     r.pull_big_chunk = pick_int(t.pull_big_chunk, "DPPR_PULL_BIG_CHUNK", 0);
@@ -138,7 +138,7 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
         pull_gshift_ = 0;
         if (S_ > 1) {
             const int chunks = (int)(Sr_ / 8);
-            while ((1 << pull_gshift_) < std::min(chunks, tn_.pull_group) && pull_gshift_ < 5) ++pull_gshift_;
+            while ((1 << pull_gshift_) < std::min(chunks, tn_.pull_group) && pull_gshift_ < 4) ++pull_gshift_;  // (<= 16 lanes: 128 accumulator columns)
         }
         // out-lists of big_min or more entries are cut into chunks any warp of the grid takes: a warp streams a list at
         // kPullUnroll rows per memory round trip, so the wider the rows (the fewer vertices a warp holds) the shorter the chunks
@@ -163,9 +163,12 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     // cooperative grid per variant: every CTA must be co-resident for the software grid barrier
     void *kern[4] = {dense_ ? (S_ == 1 ? persistent_kernel<0, 1>() : persistent_kernel<0, 8>()) : persistent_kernel<0>(), persistent_kernel<1>(),
                      persistent_kernel<2>(), persistent_kernel<3>()};
+    // the switching kernels keep the accumulator rows of a flat tile in dynamic shared memory (pull.cuh, pull_do_flat)
+    dyn_smem_ = dense_ ? (S_ == 1 ? kFlatVertsMax : kFlatAccMax) * sizeof(double) : 0;
+    if (dyn_smem_) DPPR_CUDA(cudaFuncSetAttribute(kern[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem_));
     for (int v = 0; v < 4; ++v) {
         int per_sm = 0;
-        DPPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern[v], kThreads, 0));
+        DPPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern[v], kThreads, v == 0 ? dyn_smem_ : 0));
         if (per_sm < 1) throw CudaFailure("push kernel does not fit on an SM");
         coop_grid_[v] = std::min(per_sm, tn_.ctas_per_sm) * sm_count_;
     }
@@ -592,7 +595,8 @@ void Engine::launch_push(bool init_mode) {
         case 2: kern = persistent_kernel<2>(); break;
         default: kern = persistent_kernel<3>(); break;
     }
-    DPPR_CUDA(cudaLaunchCooperativeKernel(kern, dim3(coop_grid_[cfg_.variant]), dim3(kThreads), params, 0, st_));
+    DPPR_CUDA(cudaLaunchCooperativeKernel(kern, dim3(coop_grid_[cfg_.variant]), dim3(kThreads), params,
+                                          cfg_.variant == 0 ? dyn_smem_ : 0, st_));
     ++launch_counter();
 }
 

@@ -39,7 +39,7 @@ struct Tuning {
     int ctas_per_sm = 4, tile_cap = 128, max_iters = 400000;
     int dense = 0;  // 0 auto, 1 always the switching kernel, -1 scatter only
     double dense_div = 4.0, dense_min_edges = 2.0e7;
-    int pull_group = 32, pull_warp_min = 32, pull_big_min = 0, pull_big_chunk = 0;  // (0: by the number of sources)
+    int pull_group = 16, pull_warp_min = 32, pull_big_min = 0, pull_big_chunk = 0;  // (0: by the number of sources)
     double carry_gamma = 1.0, carry_scale = 0.01;
     int window_path = 0;  // 0 auto, 1 multi-kernel only, 2 cooperative or multi-kernel (no single-CTA kernel)
     bool iterlog = false;
@@ -146,6 +146,7 @@ private:
     DevBuf<HubItem> big_;
     DevBuf<uint32_t> tile_list_;
     uint32_t bigcap_ = 0, tile_cap_ = 0;
+    size_t dyn_smem_ = 0;
     int pull_gshift_ = 0, pull_big_min_ = 0, pull_big_chunk_ = 0;
     bool dense_ = false, outlists_ = false;
     unsigned long long pool_cap_ = 0;

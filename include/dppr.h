@@ -63,7 +63,7 @@ typedef struct dppr_tuning {
     int32_t tile_cap;           /* frontier items per tile once a CTA's share exceeds 512; default 128            [DPPR_TILE_CAP] */
     int32_t max_iters;          /* push iterations per refresh before the watchdog fires; default 400000         [DPPR_MAX_ITERS] */
     int32_t dense;              /* gather sweeps (variant 0): 0 auto by window size, 1 always, -1 never           [DPPR_DENSE] */
-    int32_t pull_group;         /* most lanes sharing a vertex in a multi-source sweep (1..32); default 32        [DPPR_PULL_GROUP] */
+    int32_t pull_group;         /* most lanes sharing a vertex in a multi-source sweep (1..16); default 16        [DPPR_PULL_GROUP] */
     int32_t pull_warp_min;      /* out-lists from this length are walked by a whole warp; default 32              [DPPR_PULL_WARP_MIN] */
     int32_t pull_big_min;       /* ... and from this length cut into chunks for the grid; default 4096 / 1024 (1 / several sources) [DPPR_PULL_BIG_MIN] */
     int32_t pull_big_chunk;     /* entries per chunk; default pull_big_min / 4                                    [DPPR_PULL_BIG_CHUNK] */
