@@ -24,8 +24,9 @@ Printed JSON (one line, rank 0):
              H2D inside the timed region) plus the read-back a query needs: the step record and the top-16 estimates
              of every source on the rank (dppr_get_topk, D2H).
   roofline   the persistent push kernel: algorithmic bytes of what it did (scatter iterations: 24 B per traversed
-             in-edge + 56 B per pop; gather sweeps: 4 B per out-list entry walked + 8 B per (entry, source)
-             gather + 16 B per (vertex, source) unit + 16 B per pop) / CUDA-event time of that kernel, against the
+             in-edge + 56 B per pop; gather sweeps: 4 B per out-list entry walked + 2 B (bf16) per (entry,
+             source) gather + 4 B per (vertex, source) unit (x read + x write) + 32 B per pop (r and p rows read and
+             written)) / CUDA-event time of that kernel, against the
              measured HBM copy bandwidth (MEASURED_PEAKS.json).  `traffic` = DRAM bytes per launch from the committed
              ncu capture of the same kernel on the same config (profiles/traffic.json), else null.
   cpu_baseline  the reference's own CPU implementation (oracle/_ref/ref_harness_omp: unmodified reference classes,
@@ -361,7 +362,7 @@ def main():
         Ts, Fd = f("scatter_edges"), f("dense_pops")
         L, Ls, U = f("dense_slots"), f("dense_pairs"), f("dense_units")
         push_s = float(f("ms_push").sum()) * 1e-3
-        alg_bytes = float((24.0 * Ts + 56.0 * (F - Fd) + 4.0 * L + 8.0 * Ls + 16.0 * U + 16.0 * Fd).sum())
+        alg_bytes = float((24.0 * Ts + 56.0 * (F - Fd) + 4.0 * L + 2.0 * Ls + 4.0 * U + 32.0 * Fd).sum())
         peak, peak_src = measured_hbm_peak()
         achieved = alg_bytes / push_s / 1e9
         dense = bool(f("dense_sweeps").sum() > 0)
@@ -378,7 +379,7 @@ def main():
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes / K, "launch_ms": push_s * 1e3 / K,
                     "scatter_form_equivalent_GBps": float((24.0 * T + 56.0 * F).sum()) / push_s / 1e9,
-                    "note": ("bytes = 24 T_scatter + 56 F_scatter + 4 slots + 8 (slot, source) gathers + 16 (vertex, source) units + 16 F_dense "
+                    "note": ("bytes = 24 T_scatter + 56 F_scatter + 4 slots + 2 (slot, source) bf16 gathers + 4 (vertex, source) units + 32 F_dense "
                              "(DESIGN.md 3.3); 'scatter_form_equivalent' credits every gathered non-zero pair the 24 B a scatter would move "
                              "and is NOT the roofline figure" if dense else
                              "scatter iterations only: 24 B per traversed in-edge + 56 B per pop; L2-resident working set: bound by dependent "
