@@ -516,6 +516,12 @@ __device__ void pull_do_flat(const PushArgs &a, const PullGeom &q, PushSmem &sm,
     const FlatView f = flat_view(sm);
     const uint32_t V = (uint32_t)a.V, cols = q.G * SB, nv = ntl * q.vpt;
     const uint32_t tid = threadIdx.x;
+#ifdef DPPR_PULL_PROF
+    unsigned long long tp0 = global_ns(), tp1, tp2, tp3, tp4;
+#define DPPR_PP(x) x = global_ns()
+#else
+#define DPPR_PP(x)
+#endif
     // ---- ring metadata of the nv vertices; lists of the grid tier are not walked here ----
     uint32_t mylen = 0;
     if (tid < nv) {
@@ -534,6 +540,11 @@ __device__ void pull_do_flat(const PushArgs &a, const PullGeom &q, PushSmem &sm,
     if (tid == 0) f.offs[nv] = total;
     for (uint32_t i = tid; i < nv * cols; i += kThreads) f.acc[i] = 0.0;
     __syncthreads();
+    DPPR_PP(tp1);
+#ifdef DPPR_PULL_PROF
+    tp2 = tp1; tp3 = tp1;
+    unsigned long long stage_ns = 0, gather_ns = 0;
+#endif
     // ---- the concatenated edge list, kFlatEdges at a time ----
     const uint32_t lane_g = tid & (q.G - 1u), group = tid >> q.gs, ngroups = (uint32_t)kThreads >> q.gs;
     for (uint32_t r0 = 0; r0 < total; r0 += kFlatEdges) {
@@ -549,6 +560,9 @@ __device__ void pull_do_flat(const PushArgs &a, const PullGeom &q, PushSmem &sm,
             f.ev[i] = (uint16_t)lo;
         }
         __syncthreads();
+#ifdef DPPR_PULL_PROF
+        tp2 = global_ns(); stage_ns += tp2 - tp3;
+#endif
         // equal contiguous ranges, one per lane group; register sums while the owner stays the same
         const uint32_t per = (nr + ngroups - 1) / ngroups;
         const uint32_t lo = min(nr, group * per), hi = min(nr, lo + per);
@@ -586,7 +600,11 @@ __device__ void pull_do_flat(const PushArgs &a, const PullGeom &q, PushSmem &sm,
                 if (acc[jj] != 0.0) atomicAdd(&f.acc[cur * cols + lane_g * SB + jj], acc[jj]);
         }
         __syncthreads();
+#ifdef DPPR_PULL_PROF
+        tp3 = global_ns(); gather_ns += tp3 - tp2;
+#endif
     }
+    DPPR_PP(tp4);
     // ---- per-unit work, coalesced over the rows of the tile ----
     for (uint32_t idx = tid; idx < nv * q.G; idx += kThreads) {
         const uint32_t lv = idx >> q.gs, g = idx & (q.G - 1u);
@@ -600,6 +618,12 @@ __device__ void pull_do_flat(const PushArgs &a, const PullGeom &q, PushSmem &sm,
         }
     }
     __syncthreads();  // (the shared arrays are reused by the next item)
+#ifdef DPPR_PULL_PROF
+    if (tid == 0 && a.ctalog) {  // per CTA: items, ns in setup / staging / gather / finish, edges
+        unsigned long long *row = a.ctalog + (size_t)blockIdx.x * 8;
+        row[0] += 1; row[1] += tp1 - tp0; row[2] += stage_ns; row[3] += gather_ns; row[4] += global_ns() - tp4; row[5] += total;
+    }
+#endif
 }
 
 template <int SB>
@@ -651,9 +675,16 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
             if (j < ngroups) {
                 const uint32_t cidx = j * kWarps + warp_id();
                 if (cidx < nchunks) pull_do_chunk<SB>(a, q, phase, xcur, xnext, cidx, nh, t);
-            } else {
+            } else if (a.pull_sched == 1) {
                 const uint32_t firstt = (j - ngroups) * tpi;
                 pull_do_flat<SB>(a, q, sm, phase, xcur, xnext, firstt, min(tpi, ntl - firstt), n0, n1, t);
+            } else {  // the tiles' vertices shared by the CTA's warps, 32 / G per warp
+                for (uint32_t tt = (j - ngroups) * tpi; tt < min(ntl, (j - ngroups + 1) * tpi); ++tt) {
+                    const uint32_t tile = pull_tile_at<SB>(a, tt, n0, n1);
+                    const uint32_t cg = tile / q.tpc;
+                    const uint32_t wf = (tile - cg * q.tpc) * q.vpt + warp_id() * q.vpw;
+                    if (wf < V) pull_do_vertices<SB>(a, q, phase, xcur, xnext, wf, cg, t);
+                }
             }
             __syncthreads();
             j = *nslot;
