@@ -332,28 +332,25 @@ __device__ void pull_build(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
 template <int SB>
 __device__ __forceinline__ void pull_walk(const PushArgs &a, const uint16_t *xcur, uint32_t base, uint32_t head, uint32_t mask,
                                           uint32_t first, uint32_t last, uint32_t step, uint32_t c0, double (&acc)[SB], uint32_t &nz) {
-    constexpr int kPullUnroll = PullUnroll<SB>::value;
-    uint32_t k = first;
-    for (; k + (kPullUnroll - 1) * step < last; k += kPullUnroll * step) {
-        uint32_t u[kPullUnroll];
-        XPiece<SB> v[kPullUnroll];
+    // software-pipelined: the slots of round i + 1 are requested together with the row pieces of round i, so a round
+    // costs one memory round trip, not two (slot -> row piece)
+    constexpr int U = PullUnroll<SB>::value;
+    if (first >= last) return;
+    uint32_t u[U];
 #pragma unroll
-        for (int i = 0; i < kPullUnroll; ++i) u[i] = (uint32_t)pl_ldcs(&a.pool[base + ((head + k + i * step) & mask)]);
+    for (int i = 0; i < U; ++i) u[i] = first + i * step < last ? (uint32_t)pl_ldcs(&a.pool[base + ((head + first + i * step) & mask)]) : 0xffffffffu;
+    for (uint32_t k = first; k < last; k += U * step) {
+        XPiece<SB> v[U];
+        uint32_t un[U];
 #pragma unroll
-        for (int i = 0; i < kPullUnroll; ++i) v[i] = x_gather<SB>(xcur, (size_t)u[i] * (size_t)a.Sr + c0);
+        for (int i = 0; i < U; ++i) v[i] = u[i] != 0xffffffffu ? x_gather<SB>(xcur, (size_t)u[i] * (size_t)a.Sr + c0) : x_zero<SB>();
+        const uint32_t kn = k + U * step;
 #pragma unroll
-        for (int i = 0; i < kPullUnroll; ++i) x_accumulate<SB>(v[i], acc, nz);
-    }
-    {   // the remainder, still with all its loads in flight together
-        uint32_t u[kPullUnroll];
-        XPiece<SB> v[kPullUnroll];
+        for (int i = 0; i < U; ++i) un[i] = kn + i * step < last ? (uint32_t)pl_ldcs(&a.pool[base + ((head + kn + i * step) & mask)]) : 0xffffffffu;
 #pragma unroll
-        for (int i = 0; i < kPullUnroll; ++i)
-            u[i] = k + i * step < last ? (uint32_t)pl_ldcs(&a.pool[base + ((head + k + i * step) & mask)]) : 0xffffffffu;
+        for (int i = 0; i < U; ++i) x_accumulate<SB>(v[i], acc, nz);
 #pragma unroll
-        for (int i = 0; i < kPullUnroll; ++i) v[i] = u[i] != 0xffffffffu ? x_gather<SB>(xcur, (size_t)u[i] * (size_t)a.Sr + c0) : x_zero<SB>();
-#pragma unroll
-        for (int i = 0; i < kPullUnroll; ++i) x_accumulate<SB>(v[i], acc, nz);
+        for (int i = 0; i < U; ++i) u[i] = un[i];
     }
 }
 
