@@ -145,6 +145,9 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
         pull_big_min_ = tn_.pull_big_min > 0 ? tn_.pull_big_min : (S_ == 1 ? 4096 : 1024);
         pull_big_min_ = std::max(pull_big_min_, tn_.pull_warp_min);
         pull_big_chunk_ = tn_.pull_big_chunk > 0 ? tn_.pull_big_chunk : std::max(32, pull_big_min_ / 4);
+        // who takes a work item of a sweep (pull.cuh): 0 a warp, 1 a CTA working on a flat edge list, 2 a CTA whose warps share
+        // the tile's vertices.  Measured (profiles/README.md): one source 0, several sources 2.
+        pull_sched_ = env_int("DPPR_PULL_SCHED", S_ == 1 ? 0 : 2);
     }
 
     int ndev = 0;
@@ -272,6 +275,7 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
         if (cfg_.variant != DPPR_OPTIMIZED) qr_[i].alloc(qcap_);
         hub_[i].alloc(hcap_);
     }
+    if (dense_) qalt_.alloc(qcap_);
     ctrl_.alloc(1);
     DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, sizeof(PushCtrl), st_));
     dev_record_.alloc(1);
@@ -544,6 +548,7 @@ void Engine::launch_push(bool init_mode) {
     a.p = p_.ptr; a.r = r_.ptr; a.status = status_.ptr;
     a.Sr = Sr_; a.S = S_; a.src = src_.ptr;
     for (int i = 0; i < 2; ++i) { a.q[i] = q_[i].ptr; a.qr[i] = qr_[i].ptr; a.hub[i] = hub_[i].ptr; }
+    a.qalt = qalt_.ptr;
     a.qcap = qcap_; a.hcap = hcap_;
     a.cand = segB_.vertex; a.ncand = segB_.count;
     a.ctrl = ctrl_.ptr;
@@ -569,7 +574,7 @@ void Engine::launch_push(bool init_mode) {
     a.dense_exit_edges = a.dense_enter_edges / 2;
     a.pull_warp_min = tn_.pull_warp_min; a.pull_big_min = pull_big_min_; a.pull_big_chunk = pull_big_chunk_;
     a.big = big_.ptr; a.bigcap = bigcap_; a.bigacc = bigacc_.ptr; a.tile_list = tile_list_.ptr; a.tile_list_cap = tile_cap_;
-    a.pull_sched = env_int("DPPR_PULL_SCHED", S_ == 1 ? 0 : 1);
+    a.pull_sched = pull_sched_;
     {
         const int lanes_sources = S_ == 1 ? 1 : 8 << pull_gshift_;
         const uint64_t ntiles = (uint64_t)div_up(V_, kThreads >> pull_gshift_) * (uint64_t)((Sr_ + lanes_sources - 1) / lanes_sources);

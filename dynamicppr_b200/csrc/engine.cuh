@@ -147,7 +147,7 @@ private:
     DevBuf<uint32_t> tile_list_;
     uint32_t bigcap_ = 0, tile_cap_ = 0;
     size_t dyn_smem_ = 0;
-    int pull_gshift_ = 0, pull_big_min_ = 0, pull_big_chunk_ = 0;
+    int pull_gshift_ = 0, pull_big_min_ = 0, pull_big_chunk_ = 0, pull_sched_ = 0;
     bool dense_ = false, outlists_ = false;
     unsigned long long pool_cap_ = 0;
     // batch scratch
@@ -169,7 +169,7 @@ private:
     DevBuf<double> p_, r_;
     DevBuf<int32_t> status_, src_;
     // push
-    DevBuf<unsigned long long> q_[2];
+    DevBuf<unsigned long long> q_[2], qalt_;
     DevBuf<double> qr_[2];
     DevBuf<HubItem> hub_[2];
     uint32_t qcap_ = 0, hcap_ = 0;

@@ -142,6 +142,12 @@ __device__ __forceinline__ PullGeom pull_geom(const PushArgs &a) {
 
 constexpr uint32_t kBigDone = 0, kBigChunks = 1, kBigLen = 2;   // HubItem::pad slots used by the grid tier
 
+// A sweep pushes residuals of BOTH signs (the reference's two phases exist for the scatter form, whose threshold-crossing
+// dedupe needs same-signed adds within a phase; a gather decides every (vertex, source) exactly once per sweep).  After a
+// batch the repaired residuals have both signs and decay by the same linear process: one episode takes them down together
+// instead of one ~40-sweep episode per phase.
+__device__ __forceinline__ bool dense_legal(double x, double eps) { return fabs(x) > eps; }
+
 // everything that happens once per unit: the deferred pop, the new residual, membership in the next frontier.
 // Returns the number of sources of the unit that are in the next frontier.
 template <int SB>
@@ -182,7 +188,7 @@ __device__ __forceinline__ uint32_t pull_finish_unit(const PushArgs &a, int phas
 #pragma unroll
         for (int j = 0; j < SB; ++j) {
             rw[j] += acc[j] * scale;
-            if (legal_push(rw[j], phase, a.eps)) {
+            if (dense_legal(rw[j], a.eps)) {
                 const uint32_t h = bf16_trunc(rw[j]);
                 if (h) {
                     out[j] = h;
@@ -253,7 +259,7 @@ __device__ void pull_build(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
             for (int j = 0; j < SB; ++j) {
                 out[j] = 0u; zero[j] = 0u;
                 rw[j] = __ldcg(&a.r[row + j]);
-                if (legal_push(rw[j], phase, a.eps)) {
+                if (dense_legal(rw[j], a.eps)) {
                     const uint32_t h = bf16_trunc(rw[j]);
                     if (h) { out[j] = h; rw[j] -= bf16_value(h); ++legal; any = true; }
                 }
@@ -695,7 +701,8 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
 
 // ---- leaving dense mode ----------------------------------------------------------------------------------------------
 // the non-zero entries of x are pops that were decided but not performed: give them back to r; those (source, vertex)
-// pairs are the (un-popped) frontier of the next scatter iteration
+// pairs whose residual has the sign of the running phase are the (un-popped) frontier of the next scatter iteration, the
+// others wait in qalt for the next phase
 template <int SB>
 __device__ void pull_compact(const PushArgs &a, PushSmem &sm, PushCtrl *c, const uint16_t *x, unsigned long long *qout,
                              unsigned int *cnt_out) {
@@ -714,8 +721,18 @@ __device__ void pull_compact(const PushArgs &a, PushSmem &sm, PushCtrl *c, const
 #pragma unroll
         for (int j = 0; j < SB; ++j) {
             const uint32_t h = xc.get(j);
-            if (h) a.r[row + j] += bf16_value(h);
-            stage_push(h != 0u, ((unsigned long long)(s0 + j) << 32) | w, sm, qout, cnt_out, a.qcap, a.ctrl);
+            bool mine = false;
+            if (h) {
+                const double rw = a.r[row + j] + bf16_value(h);
+                a.r[row + j] = rw;
+                mine = legal_push(rw, phase, a.eps);
+                if (!mine && dense_legal(rw, a.eps)) {  // the other sign: a seed of the next phase
+                    const unsigned pos = atomicAdd(&c->nalt, 1u);
+                    if (pos < a.qcap) a.qalt[pos] = ((unsigned long long)(s0 + j) << 32) | w;
+                    else atomicOr(&a.ctrl->errflags, kErrQueue);
+                }
+            }
+            stage_push(mine, ((unsigned long long)(s0 + j) << 32) | w, sm, qout, cnt_out, a.qcap, a.ctrl);
         }
         stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
     }

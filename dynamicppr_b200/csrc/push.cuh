@@ -78,6 +78,8 @@ struct PushCtrl {
     unsigned int ntiles_active;    // dense mode: active tiles of the running episode = sum of ntiles_b
     unsigned int ntiles_b[3];      // ... by weight class (heavy first): tile_list holds three lists of tile_list_cap entries
     unsigned int work_next[2];     // dense mode: next work item (grid-tier chunk, then tile) of the running sweep, by sweep parity
+    unsigned int nalt;             // dense mode: items in qalt (residuals of the OTHER sign left by an episode: seeds of the next phase)
+    unsigned int pad3;
     unsigned int pad0;
     unsigned long long bigpk;      // dense mode: grid-tier list of the running sweep, (entries << 32) | chunks
     unsigned long long gath;       // dense sweeps: gathered x entries that were non-zero = the (edge, source) pairs a scatter
@@ -115,6 +117,7 @@ struct PushArgs {
     int32_t S;
     const int32_t *src;
     unsigned long long *q[2];
+    unsigned long long *qalt;    // (dense kernels) frontier items of the other sign an episode left behind, see pull_compact
     double *qr[2];
     uint32_t qcap;
     HubItem *hub[2];
@@ -291,9 +294,9 @@ __device__ __forceinline__ void push_edges(const PushArgs &a, PushSmem &sm, cons
 
 // ---- seeds --------------------------------------------------------------------------------------
 __device__ void seed_pass(const PushArgs &a, PushSmem &sm, int phase, unsigned long long *qout,
-                          unsigned int *cnt_out) {
+                          unsigned int *cnt_out, bool with_candidates = true) {
     const uint32_t ncand = a.init_mode ? 1u : __ldcg(a.ncand);
-    const unsigned long long total = (unsigned long long)ncand * (unsigned)a.S;
+    const unsigned long long total = with_candidates ? (unsigned long long)ncand * (unsigned)a.S : 0ull;
     const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
     const unsigned long long rounds = (total + stride - 1) / stride;
     double mx = 0.0;
@@ -314,6 +317,27 @@ __device__ void seed_pass(const PushArgs &a, PushSmem &sm, int phase, unsigned l
         if ((rd & 3) == 3) stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
     }
     stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
+    if (a.qalt) {
+        // residuals of this phase's sign that a dense episode of the previous phase left behind (pull_compact): a sweep
+        // pushes both signs, so they may sit anywhere, not only at repaired vertices.  (A pair that is also a candidate is
+        // seeded twice: its second pop finds an exact zero and expands nothing.)
+        const unsigned long long nalt = __ldcg(&a.ctrl->nalt);
+        const unsigned long long rounds2 = (nalt + stride - 1) / stride;
+        for (unsigned long long rd = 0; rd < rounds2; ++rd) {
+            const unsigned long long j = rd * stride + (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
+            bool want = false;
+            unsigned long long item = 0;
+            if (j < nalt) {
+                item = __ldcg(&a.qalt[j]);
+                const double x = __ldcg(&a.r[(unsigned long long)(uint32_t)item * a.Sr + (item >> 32)]);
+                want = legal_push(x, phase, a.eps);
+                if (want) mx = fmax(mx, fabs(x));
+            }
+            stage_push(want, item, sm, qout, cnt_out, a.qcap, a.ctrl);
+            if ((rd & 3) == 3) stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
+        }
+        stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, off));
     if (lane_id() == 0 && mx > 0.0) atomicMax(&a.ctrl->theta0[phase], (unsigned long long)__double_as_longlong(mx));
@@ -627,14 +651,15 @@ namespace dppr {
 // DENSE != 0: with the switch to gather sweeps (variant 0 only).  Separate instantiations, so that the scatter-only
 // kernels keep their register allocation.
 #ifndef DPPR_DENSE1_MIN_BLOCKS
-#define DPPR_DENSE1_MIN_BLOCKS 4
+#define DPPR_DENSE1_MIN_BLOCKS 3
 #endif
 #ifndef DPPR_DENSE8_MIN_BLOCKS
-#define DPPR_DENSE8_MIN_BLOCKS 2
+#define DPPR_DENSE8_MIN_BLOCKS 3
 #endif
-// DENSE = sources a lane of a sweep takes: 0 (scatter only), 1 (one source) or 8 (several).  The multi-source switching
-// kernel gets 128 registers per thread: its sweeps keep several 16-byte row pieces in flight per lane and must not
-// spill -- round 1's 64-register build issued 5.2 G local loads per refresh on BASELINE configs[3].
+// DENSE = sources a lane of a sweep takes: 0 (scatter only), 1 (one source) or 8 (several).  The switching kernels run
+// 3 CTAs per SM (80 registers): scripts/micro/gather_mlp.cu shows that the random-row bandwidth of an SM grows with its
+// resident WARPS, not with the loads a warp keeps in flight, while round 1's 64-register build spilled (5.2 G local loads
+// per refresh on BASELINE configs[3]); 3 x 8 warps with 4 / 8 gathers per lane measured best (profiles/README.md).
 template <int VAR, int DENSE>
 __global__ void __launch_bounds__(kThreads, DENSE == 8 ? DPPR_DENSE8_MIN_BLOCKS : DENSE == 1 ? DPPR_DENSE1_MIN_BLOCKS : DPPR_MIN_BLOCKS)
     push_persistent(const PushArgs a) {
@@ -648,10 +673,15 @@ __global__ void __launch_bounds__(kThreads, DENSE == 8 ? DPPR_DENSE8_MIN_BLOCKS 
     float rate_reg = DENSE ? fmaxf(__ldcg(&c->rate_ns[0]), __ldcg(&c->rate_ns[1])) : 0.f;  // block 0 / thread 0: running estimate
     const int level0 = __ldcg(&c->level);
     uint32_t it = 0, iters_done = 0;  // `it` indexes the rotating slots (skips one value per phase change)
+    // Phases alternate in sign: 0 pushes residuals above eps, 1 those below -eps (the reference runs exactly these two,
+    // gpu/PPRGPU.cuh:128-163).  A dense episode pushes BOTH signs at once and may leave residuals of the other sign behind
+    // (qalt): they seed the next phase, and further phases run while an episode keeps leaving some (normally none do).
     const int nphases = a.init_mode ? 1 : 2;
     bool alive = true;
-    for (int phase = 0; phase < nphases && alive; ++phase) {
-        if (phase > 0) {
+    for (int phase_i = 0; phase_i < 8 && alive; ++phase_i) {
+        const int phase = phase_i & 1;
+        if (phase_i >= nphases && !(DENSE && __ldcg(&c->nalt) != 0u)) break;  // (uniform: nalt is stable between the barriers)
+        if (phase_i > 0) {
             // Phase change.  Slow CTAs may still be polling cnt[it % 3] (== 0) to leave the loop below,
             // so the new seeds must not land in that slot: skip one iteration index.  The slots the
             // skipped iteration would have cleared are cleared here -- their last readers passed the
@@ -662,8 +692,9 @@ __global__ void __launch_bounds__(kThreads, DENSE == 8 ? DPPR_DENSE8_MIN_BLOCKS 
             }
             ++it;
         }
-        seed_pass(a, sm, phase, a.q[it & 1], &c->cnt[it % 3]);
+        seed_pass(a, sm, phase, a.q[it & 1], &c->cnt[it % 3], phase_i < nphases);  // (extra phases: only what an episode left)
         if (!(alive = grid_barrier(c, gen, sm))) break;
+        if (DENSE && blockIdx.x == 0 && threadIdx.x == 0) c->nalt = 0u;  // consumed; episodes of this phase append from 0
         const bool carrying = VAR == 0 && a.carry_gamma > 0.0 && a.carry_gamma < 1.0;
         double theta = carrying ? __longlong_as_double((long long)__ldcg(&c->theta0[phase])) * a.carry_scale : a.eps;
         uint32_t n_prev = 0;
