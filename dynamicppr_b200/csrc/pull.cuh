@@ -704,7 +704,7 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
 // pairs whose residual has the sign of the running phase are the (un-popped) frontier of the next scatter iteration, the
 // others wait in qalt for the next phase
 template <int SB>
-__device__ void pull_compact(const PushArgs &a, PushSmem &sm, PushCtrl *c, const uint16_t *x, unsigned long long *qout,
+__device__ void pull_compact(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, const uint16_t *x, unsigned long long *qout,
                              unsigned int *cnt_out) {
     const PullGeom q = pull_geom<SB>(a);
     const uint32_t V = (uint32_t)a.V;
@@ -820,7 +820,7 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
         c->units += (unsigned long long)k * __ldcg(&c->ep_units);
     }
     if (__ldcg(&c->dcnt[k % 3]) != 0)
-        pull_compact<SB>(a, sm, c, a.x[cur], a.q[(it + 1) & 1], &c->cnt[(it + 1) % 3]);
+        pull_compact<SB>(a, sm, c, phase, a.x[cur], a.q[(it + 1) & 1], &c->cnt[(it + 1) % 3]);
     return grid_barrier(c, gen, sm);
 }
 
