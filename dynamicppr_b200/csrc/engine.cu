@@ -66,6 +66,8 @@ Tuning resolve_tuning(const dppr_tuning &t) {
     r.pull_big_chunk = pick_int(t.pull_big_chunk, "DPPR_PULL_BIG_CHUNK", 0);
     r.carry_gamma = pick_real(t.carry_gamma, "DPPR_CARRY_GAMMA", 1.0);
     r.carry_scale = pick_real(t.carry_scale, "DPPR_CARRY_SCALE", 0.01);
+    r.dense_accel = pick_int(t.dense_accel, "DPPR_DENSE_ACCEL", 0);
+    r.accel_frac = env_real("DPPR_ACCEL_FRAC", 0.5);
     r.window_path = pick_int(t.window_path, "DPPR_WINDOW_PATH", 0);
     if (t.window_path == 0 && !env_int("DPPR_COOP_WINDOW", 1)) r.window_path = 1;   // round-1 spellings
     else if (t.window_path == 0 && !env_int("DPPR_FUSED_WINDOW", 1)) r.window_path = 2;
@@ -575,6 +577,7 @@ void Engine::launch_push(bool init_mode) {
     a.pull_warp_min = tn_.pull_warp_min; a.pull_big_min = pull_big_min_; a.pull_big_chunk = pull_big_chunk_;
     a.big = big_.ptr; a.bigcap = bigcap_; a.bigacc = bigacc_.ptr; a.tile_list = tile_list_.ptr; a.tile_list_cap = tile_cap_;
     a.pull_sched = pull_sched_;
+    a.accel_frac = (D_ == 2 && tn_.dense_accel >= 0) ? tn_.accel_frac : 0.0;
     {
         const int lanes_sources = S_ == 1 ? 1 : 8 << pull_gshift_;
         const uint64_t ntiles = (uint64_t)div_up(V_, kThreads >> pull_gshift_) * (uint64_t)((Sr_ + lanes_sources - 1) / lanes_sources);

@@ -148,6 +148,8 @@ struct PushArgs {
     uint32_t pull_tile_mul;      // tile visiting order: tile = (t * mul) mod ntiles, mul coprime to ntiles
     uint32_t *tile_list;         // active tiles of the running dense episode: [3][tile_list_cap], heavy tiles first
     uint32_t tile_list_cap;
+    double accel_frac;           // Chebyshev-accelerated sweeps while the frontier holds at least this fraction of all (vertex, source)
+                                 // pairs; 0 = never (directed windows: the spectrum is not real)
     int32_t pull_sched;          // who takes a work item of a sweep: 0 = a warp, 1 = a CTA (its warps share a tile's vertices)
     HubItem *big;                // grid-tier list
     uint32_t bigcap;

@@ -74,7 +74,8 @@ typedef struct dppr_tuning {
     double dense_min_edges;     /* auto: window entries x sources from which the switching kernel is used; 2e7   [DPPR_DENSE_MIN_EDGES] */
     double carry_gamma;         /* variant 0 threshold schedule; default off (1.0)                               [DPPR_CARRY_GAMMA] */
     double carry_scale;         /* default 0.01                                                                   [DPPR_CARRY_SCALE] */
-    int32_t reserved[8];
+    int32_t dense_accel;        /* Chebyshev-accelerated sweeps on undirected windows: 0/1 on (default), -1 off       [DPPR_DENSE_ACCEL] */
+    int32_t reserved[7];
 } dppr_tuning;
 
 typedef struct dppr_engine dppr_engine;
