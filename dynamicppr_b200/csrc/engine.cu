@@ -169,7 +169,7 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     void *kern[4] = {dense_ ? (S_ == 1 ? persistent_kernel<0, 1>() : persistent_kernel<0, 8>()) : persistent_kernel<0>(), persistent_kernel<1>(),
                      persistent_kernel<2>(), persistent_kernel<3>()};
     // the switching kernels keep the accumulator rows of a flat tile in dynamic shared memory (pull.cuh, pull_do_flat)
-    dyn_smem_ = dense_ ? (S_ == 1 ? kFlatVertsMax : kFlatAccMax) * sizeof(double) : 0;
+    dyn_smem_ = dense_ ? ((S_ == 1 ? kFlatVertsMax : kFlatAccMax) + 2) * sizeof(double) : 0;
     if (dyn_smem_) DPPR_CUDA(cudaFuncSetAttribute(kern[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem_));
     for (int v = 0; v < 4; ++v) {
         int per_sm = 0;

@@ -386,11 +386,17 @@ __device__ __forceinline__ uint32_t pull_tile_at(const PushArgs &a, uint32_t j, 
     return __ldcg(&a.tile_list[2 * (size_t)a.tile_list_cap + (j - n1)]);
 }
 
+// relaxation factor of the running sweep: kept in shared memory (set by dense_body), not in registers -- the gather loops
+// run at the register limit
+__device__ __forceinline__ double sm_omega(const PushArgs &) {
+    extern __shared__ __align__(16) unsigned char dppr_dyn_smem[];
+    return *reinterpret_cast<const double *>(dppr_dyn_smem);
+}
+
 // per-warp running totals of a sweep
 struct PullAcc {
     uint32_t legal = 0, nz = 0;
     unsigned long long next_edges = 0;
-    double omega = 1.0;  // relaxation factor of the running sweep (dense_body)
 };
 
 // one chunk of a long out-list, by one warp; the warp that completes the last chunk of a vertex finishes it
@@ -435,7 +441,7 @@ __device__ __forceinline__ void pull_do_chunk(const PushArgs &a, const PullGeom 
                 __stcg(&accrow[g * SB + jj], 0.0);
             }
             const XPiece<SB> xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
-            t.legal += pull_finish_unit<SB>(a, phase, w, s0, m.z, xc, acc, xnext, t.next_edges, t.omega);
+            t.legal += pull_finish_unit<SB>(a, phase, w, s0, m.z, xc, acc, xnext, t.next_edges, sm_omega(a));
         }
         if (lane == 0) a.big[lo].pad[kBigDone] = 0u;  // (ready for the next sweep)
     }
@@ -478,7 +484,7 @@ __device__ __forceinline__ void pull_do_vertices(const PushArgs &a, const PullGe
             for (int jj = 0; jj < SB; ++jj) acc[jj] = part[jj];
         }
     }
-    if (tier != 2 && have) t.legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, t.next_edges, t.omega);
+    if (tier != 2 && have) t.legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, t.next_edges, sm_omega(a));
 }
 
 // ---- flat tiles (work items handed to CTAs) ------------------------------------------------------------------------
@@ -511,7 +517,7 @@ __device__ __forceinline__ FlatView flat_view(PushSmem &sm) {
     f.offs = sm.h_c0;
     f.cgv = sm.h_c0 + 512;
     f.base = sm.t_base; f.head = sm.t_head; f.mask = sm.t_mask; f.lenr = sm.t_off; f.wv = sm.t_s;
-    f.acc = reinterpret_cast<double *>(dppr_dyn_smem);
+    f.acc = reinterpret_cast<double *>(dppr_dyn_smem) + 2;  // ([0] = relaxation factor of the sweep)
     return f;
 }
 
@@ -621,7 +627,7 @@ __device__ void pull_do_flat(const PushArgs &a, const PullGeom &q, PushSmem &sm,
 #pragma unroll
             for (int jj = 0; jj < SB; ++jj) acc[jj] = f.acc[lv * cols + g * SB + jj];
             const XPiece<SB> xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
-            t.legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, t.next_edges, t.omega);
+            t.legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, t.next_edges, sm_omega(a));
         }
     }
     __syncthreads();  // (the shared arrays are reused by the next item)
@@ -635,13 +641,11 @@ __device__ void pull_do_flat(const PushArgs &a, const PullGeom &q, PushSmem &sm,
 
 template <int SB>
 __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, const uint16_t *xcur, uint16_t *xnext,
-                           unsigned int *cnt_out, unsigned long long *edges_out, unsigned long long &gath, uint32_t sweep_index,
-                           double omega) {
+                           unsigned int *cnt_out, unsigned long long *edges_out, unsigned long long &gath, uint32_t sweep_index) {
     const PullGeom q = pull_geom<SB>(a);
     const uint32_t V = (uint32_t)a.V;
     const uint32_t lane = lane_id();
     PullAcc t;
-    t.omega = omega;
     const unsigned long long bp = __ldcg(&c->bigpk);
     const uint32_t nh = min((uint32_t)(bp >> 32), a.bigcap), nchunks = nh ? (uint32_t)bp : 0u;
     const uint32_t n0 = __ldcg(&c->ntiles_b[0]), n1 = __ldcg(&c->ntiles_b[1]), n2 = __ldcg(&c->ntiles_b[2]);
@@ -809,6 +813,12 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
             kacc = 0;
             omega = 1.0;
         }
+        {
+            extern __shared__ __align__(16) unsigned char dppr_dyn_smem[];
+            __syncthreads();
+            if (threadIdx.x == 0) *reinterpret_cast<double *>(dppr_dyn_smem) = omega;
+            __syncthreads();
+        }
         if (k > 0) {
             const unsigned long long ne = __ldcg(&c->dedges[k % 3]);
             const bool fits = (double)n < 0.5 * (double)a.qcap;  // (the frontier must fit the queue it is compacted into)
@@ -830,7 +840,7 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
                 a.iterlog[iters_done] = make_uint4(n, 0xffffffffu, (uint32_t)t, (uint32_t)(t >> 32));
             }
         }
-        pull_sweep<SB>(a, sm, c, phase, a.x[cur], a.x[cur ^ 1], &c->dcnt[(k + 1) % 3], &c->dedges[(k + 1) % 3], gath, k, omega);
+        pull_sweep<SB>(a, sm, c, phase, a.x[cur], a.x[cur ^ 1], &c->dcnt[(k + 1) % 3], &c->dedges[(k + 1) % 3], gath, k);
         if (!grid_barrier(c, gen, sm)) return false;
         cur ^= 1;
         ++k;
