@@ -142,6 +142,13 @@ __device__ __forceinline__ PullGeom pull_geom(const PushArgs &a) {
 
 constexpr uint32_t kBigDone = 0, kBigChunks = 1, kBigLen = 2;   // HubItem::pad slots used by the grid tier
 
+// relaxation factor of an accelerated sweep: kept in shared memory (set by dense_body), not in registers -- the gather
+// loops run at the register limit
+__device__ __forceinline__ double sm_omega() {
+    extern __shared__ __align__(16) unsigned char dppr_dyn_smem[];
+    return *reinterpret_cast<const double *>(dppr_dyn_smem);
+}
+
 // A sweep pushes residuals of BOTH signs (the reference's two phases exist for the scatter form, whose threshold-crossing
 // dedupe needs same-signed adds within a phase; a gather decides every (vertex, source) exactly once per sweep).  After a
 // batch the repaired residuals have both signs and decay by the same linear process: one episode takes them down together
@@ -150,10 +157,10 @@ __device__ __forceinline__ bool dense_legal(double x, double eps) { return fabs(
 
 // everything that happens once per unit: the deferred pop, the new residual, membership in the next frontier.
 // Returns the number of sources of the unit that are in the next frontier.
-template <int SB>
+template <int SB, bool ACCEL>
 __device__ __forceinline__ uint32_t pull_finish_unit(const PushArgs &a, int phase, uint32_t w, uint32_t s0, uint32_t len,
                                                      const XPiece<SB> &xc, const double (&acc)[SB], uint16_t *xn,
-                                                     unsigned long long &next_edges, double omega = 1.0) {
+                                                     unsigned long long &next_edges) {
     const size_t row = (size_t)w * (size_t)a.Sr + s0;
     uint32_t out[SB];
     bool touched = xc.any();
@@ -191,7 +198,11 @@ __device__ __forceinline__ uint32_t pull_finish_unit(const PushArgs &a, int phas
             if (dense_legal(rw[j], a.eps)) {
                 // Chebyshev semi-iteration (dense_body): push d_k = w r_k + (w - 1) d_{k-1}, d_{k-1} = what this unit popped in
                 // this sweep.  w = 1 is the plain push of the whole residual.
-                const double want = omega == 1.0 ? rw[j] : omega * rw[j] + (omega - 1.0) * bf16_value(xc.get(j));
+                double want = rw[j];
+                if (ACCEL) {
+                    const double omega = sm_omega();
+                    want = omega * rw[j] + (omega - 1.0) * bf16_value(xc.get(j));
+                }
                 const uint32_t h = bf16_trunc(want);
                 if (h) {
                     out[j] = h;
@@ -386,13 +397,6 @@ __device__ __forceinline__ uint32_t pull_tile_at(const PushArgs &a, uint32_t j, 
     return __ldcg(&a.tile_list[2 * (size_t)a.tile_list_cap + (j - n1)]);
 }
 
-// relaxation factor of the running sweep: kept in shared memory (set by dense_body), not in registers -- the gather loops
-// run at the register limit
-__device__ __forceinline__ double sm_omega(const PushArgs &) {
-    extern __shared__ __align__(16) unsigned char dppr_dyn_smem[];
-    return *reinterpret_cast<const double *>(dppr_dyn_smem);
-}
-
 // per-warp running totals of a sweep
 struct PullAcc {
     uint32_t legal = 0, nz = 0;
@@ -400,7 +404,7 @@ struct PullAcc {
 };
 
 // one chunk of a long out-list, by one warp; the warp that completes the last chunk of a vertex finishes it
-template <int SB>
+template <int SB, bool ACCEL>
 __device__ __forceinline__ void pull_do_chunk(const PushArgs &a, const PullGeom &q, int phase, const uint16_t *xcur, uint16_t *xnext,
                                               uint32_t cidx, uint32_t nh, PullAcc &t) {
     const uint32_t lane = lane_id(), grp = lane >> q.gs, g = lane & (q.G - 1u);
@@ -441,14 +445,14 @@ __device__ __forceinline__ void pull_do_chunk(const PushArgs &a, const PullGeom 
                 __stcg(&accrow[g * SB + jj], 0.0);
             }
             const XPiece<SB> xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
-            t.legal += pull_finish_unit<SB>(a, phase, w, s0, m.z, xc, acc, xnext, t.next_edges, sm_omega(a));
+            t.legal += pull_finish_unit<SB, ACCEL>(a, phase, w, s0, m.z, xc, acc, xnext, t.next_edges);
         }
         if (lane == 0) a.big[lo].pad[kBigDone] = 0u;  // (ready for the next sweep)
     }
 }
 
 // the 32 / G consecutive vertices starting at wfirst (chunk group cg), by one warp
-template <int SB>
+template <int SB, bool ACCEL>
 __device__ __forceinline__ void pull_do_vertices(const PushArgs &a, const PullGeom &q, int phase, const uint16_t *xcur, uint16_t *xnext,
                                                  uint32_t wfirst, uint32_t cg, PullAcc &t) {
     const uint32_t V = (uint32_t)a.V;
@@ -484,7 +488,7 @@ __device__ __forceinline__ void pull_do_vertices(const PushArgs &a, const PullGe
             for (int jj = 0; jj < SB; ++jj) acc[jj] = part[jj];
         }
     }
-    if (tier != 2 && have) t.legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, t.next_edges, sm_omega(a));
+    if (tier != 2 && have) t.legal += pull_finish_unit<SB, ACCEL>(a, phase, w, s0, len, xc, acc, xnext, t.next_edges);
 }
 
 // ---- flat tiles (work items handed to CTAs) ------------------------------------------------------------------------
@@ -522,7 +526,7 @@ __device__ __forceinline__ FlatView flat_view(PushSmem &sm) {
 }
 
 // `ntl` tiles starting at position `first` of the class-ordered tile list, all their vertices at once.  CTA-wide.
-template <int SB>
+template <int SB, bool ACCEL>
 __device__ void pull_do_flat(const PushArgs &a, const PullGeom &q, PushSmem &sm, int phase, const uint16_t *xcur, uint16_t *xnext,
                              uint32_t first, uint32_t ntl, uint32_t n0, uint32_t n1, PullAcc &t) {
     constexpr int U = PullUnroll<SB>::value;
@@ -627,7 +631,7 @@ __device__ void pull_do_flat(const PushArgs &a, const PullGeom &q, PushSmem &sm,
 #pragma unroll
             for (int jj = 0; jj < SB; ++jj) acc[jj] = f.acc[lv * cols + g * SB + jj];
             const XPiece<SB> xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
-            t.legal += pull_finish_unit<SB>(a, phase, w, s0, len, xc, acc, xnext, t.next_edges, sm_omega(a));
+            t.legal += pull_finish_unit<SB, ACCEL>(a, phase, w, s0, len, xc, acc, xnext, t.next_edges);
         }
     }
     __syncthreads();  // (the shared arrays are reused by the next item)
@@ -639,7 +643,7 @@ __device__ void pull_do_flat(const PushArgs &a, const PullGeom &q, PushSmem &sm,
 #endif
 }
 
-template <int SB>
+template <int SB, bool ACCEL>
 __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, const uint16_t *xcur, uint16_t *xnext,
                            unsigned int *cnt_out, unsigned long long *edges_out, unsigned long long &gath, uint32_t sweep_index) {
     const PullGeom q = pull_geom<SB>(a);
@@ -662,13 +666,13 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
             uint32_t jn = 0;
             if (lane == 0) jn = atomicAdd(next, 1u);  // consumed at the bottom of the loop
             if (j < nchunks) {
-                pull_do_chunk<SB>(a, q, phase, xcur, xnext, j, nh, t);
+                pull_do_chunk<SB, ACCEL>(a, q, phase, xcur, xnext, j, nh, t);
             } else {
                 const uint32_t tile = pull_tile_at<SB>(a, j - nchunks, n0, n1);
                 const uint32_t cg = tile / q.tpc;
                 const uint32_t w0 = (tile - cg * q.tpc) * q.vpt;
                 for (uint32_t sub = 0; sub < (uint32_t)kWarps && w0 + sub * q.vpw < V; ++sub)
-                    pull_do_vertices<SB>(a, q, phase, xcur, xnext, w0 + sub * q.vpw, cg, t);
+                    pull_do_vertices<SB, ACCEL>(a, q, phase, xcur, xnext, w0 + sub * q.vpw, cg, t);
             }
             j = __shfl_sync(kFull, jn, 0);
         }
@@ -687,16 +691,16 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
             if (threadIdx.x == 0) *nslot = atomicAdd(next, 1u);
             if (j < ngroups) {
                 const uint32_t cidx = j * kWarps + warp_id();
-                if (cidx < nchunks) pull_do_chunk<SB>(a, q, phase, xcur, xnext, cidx, nh, t);
+                if (cidx < nchunks) pull_do_chunk<SB, ACCEL>(a, q, phase, xcur, xnext, cidx, nh, t);
             } else if (a.pull_sched == 1) {
                 const uint32_t firstt = (j - ngroups) * tpi;
-                pull_do_flat<SB>(a, q, sm, phase, xcur, xnext, firstt, min(tpi, ntl - firstt), n0, n1, t);
+                pull_do_flat<SB, ACCEL>(a, q, sm, phase, xcur, xnext, firstt, min(tpi, ntl - firstt), n0, n1, t);
             } else {  // the tiles' vertices shared by the CTA's warps, 32 / G per warp
                 for (uint32_t tt = (j - ngroups) * tpi; tt < min(ntl, (j - ngroups + 1) * tpi); ++tt) {
                     const uint32_t tile = pull_tile_at<SB>(a, tt, n0, n1);
                     const uint32_t cg = tile / q.tpc;
                     const uint32_t wf = (tile - cg * q.tpc) * q.vpt + warp_id() * q.vpw;
-                    if (wf < V) pull_do_vertices<SB>(a, q, phase, xcur, xnext, wf, cg, t);
+                    if (wf < V) pull_do_vertices<SB, ACCEL>(a, q, phase, xcur, xnext, wf, cg, t);
                 }
             }
             __syncthreads();
@@ -826,7 +830,7 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
                                                                         : ne < a.dense_exit_edges);
             if (leave) break;
         }
-        if ((int)iters_done >= a.max_iters) {
+        if ((int)iters_done >= a.max_iters || k >= 4096u) {  // (an episode needs a few dozen sweeps)
             if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&c->errflags, kErrWatchdog);
             return false;
         }
@@ -840,7 +844,8 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
                 a.iterlog[iters_done] = make_uint4(n, 0xffffffffu, (uint32_t)t, (uint32_t)(t >> 32));
             }
         }
-        pull_sweep<SB>(a, sm, c, phase, a.x[cur], a.x[cur ^ 1], &c->dcnt[(k + 1) % 3], &c->dedges[(k + 1) % 3], gath, k);
+        if (omega != 1.0) pull_sweep<SB, true>(a, sm, c, phase, a.x[cur], a.x[cur ^ 1], &c->dcnt[(k + 1) % 3], &c->dedges[(k + 1) % 3], gath, k);
+        else pull_sweep<SB, false>(a, sm, c, phase, a.x[cur], a.x[cur ^ 1], &c->dcnt[(k + 1) % 3], &c->dedges[(k + 1) % 3], gath, k);
         if (!grid_barrier(c, gen, sm)) return false;
         cur ^= 1;
         ++k;
