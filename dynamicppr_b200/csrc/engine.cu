@@ -147,9 +147,6 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
         pull_big_min_ = tn_.pull_big_min > 0 ? tn_.pull_big_min : (S_ == 1 ? 4096 : 1024);
         pull_big_min_ = std::max(pull_big_min_, tn_.pull_warp_min);
         pull_big_chunk_ = tn_.pull_big_chunk > 0 ? tn_.pull_big_chunk : std::max(32, pull_big_min_ / 4);
-        // who takes a work item of a sweep (pull.cuh): 0 a warp, 1 a CTA working on a flat edge list, 2 a CTA whose warps share
-        // the tile's vertices.  Measured (profiles/README.md): one source 0, several sources 2.
-        pull_sched_ = env_int("DPPR_PULL_SCHED", S_ == 1 ? 0 : 2);
     }
 
     int ndev = 0;
@@ -168,8 +165,8 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     // cooperative grid per variant: every CTA must be co-resident for the software grid barrier
     void *kern[4] = {dense_ ? (S_ == 1 ? persistent_kernel<0, 1>() : persistent_kernel<0, 8>()) : persistent_kernel<0>(), persistent_kernel<1>(),
                      persistent_kernel<2>(), persistent_kernel<3>()};
-    // the switching kernels keep the accumulator rows of a flat tile in dynamic shared memory (pull.cuh, pull_do_flat)
-    dyn_smem_ = dense_ ? ((S_ == 1 ? kFlatVertsMax : kFlatAccMax) + 2) * sizeof(double) : 0;
+    // the switching kernels keep the relaxation factor of an accelerated sweep in (dynamic) shared memory (pull.cuh)
+    dyn_smem_ = dense_ ? 16 : 0;
     if (dyn_smem_) DPPR_CUDA(cudaFuncSetAttribute(kern[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem_));
     for (int v = 0; v < 4; ++v) {
         int per_sm = 0;
@@ -576,7 +573,6 @@ void Engine::launch_push(bool init_mode) {
     a.dense_exit_edges = a.dense_enter_edges / 2;
     a.pull_warp_min = tn_.pull_warp_min; a.pull_big_min = pull_big_min_; a.pull_big_chunk = pull_big_chunk_;
     a.big = big_.ptr; a.bigcap = bigcap_; a.bigacc = bigacc_.ptr; a.tile_list = tile_list_.ptr; a.tile_list_cap = tile_cap_;
-    a.pull_sched = pull_sched_;
     a.accel_frac = (D_ == 2 && tn_.dense_accel >= 0) ? tn_.accel_frac : 0.0;
     {
         const int lanes_sources = S_ == 1 ? 1 : 8 << pull_gshift_;

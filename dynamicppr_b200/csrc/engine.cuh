@@ -149,7 +149,7 @@ private:
     DevBuf<uint32_t> tile_list_;
     uint32_t bigcap_ = 0, tile_cap_ = 0;
     size_t dyn_smem_ = 0;
-    int pull_gshift_ = 0, pull_big_min_ = 0, pull_big_chunk_ = 0, pull_sched_ = 0;
+    int pull_gshift_ = 0, pull_big_min_ = 0, pull_big_chunk_ = 0;
     bool dense_ = false, outlists_ = false;
     unsigned long long pool_cap_ = 0;
     // batch scratch

@@ -384,9 +384,9 @@ __device__ __forceinline__ void pull_reduce_groups(double (&part)[SB], uint32_t 
 
 // ---- one sweep -------------------------------------------------------------------------------------------------------
 // Work items -- first the chunks of the grid tier (the longest tasks), then the active tiles, heavy classes first -- are
-// handed out one at a time to WARPS by an atomic counter (round 2: with the static tile -> CTA assignment 20-35 % of a
-// sweep was spent waiting at its closing barrier).  A warp processes a whole tile (kThreads / G vertices, 32 / G at a
-// time); the index of its next item is requested before the current one is processed, so the atomic's round trip is hidden.
+// handed out one at a time by an atomic counter (round 2: with the static tile -> CTA assignment 20-35 % of a sweep was
+// spent waiting at its closing barrier); the index of the next item is requested before the current one is processed, so
+// the atomic's round trip is hidden.
 // `gath` counts the gathered x entries that were non-zero: exactly the (edge, source) pairs the push form would have
 // traversed.
 template <int SB>
@@ -491,158 +491,6 @@ __device__ __forceinline__ void pull_do_vertices(const PushArgs &a, const PullGe
     if (tier != 2 && have) t.legal += pull_finish_unit<SB, ACCEL>(a, phase, w, s0, len, xc, acc, xnext, t.next_edges);
 }
 
-// ---- flat tiles (work items handed to CTAs) ------------------------------------------------------------------------
-// Round 2, second pass: ncu on BASELINE configs[3] (125 sources) showed the warp-owned walks stuck at 28 % of DRAM peak --
-// per pair of vertices a chain of five dependent round trips (ring metadata -> slots -> row gathers -> r / p rows ->
-// stores) with nothing else in flight, and lanes idling behind the longest list of their warp.  Here a CTA takes
-// kFlatVerts vertices at once, concatenates their out-lists into ONE edge list in shared memory (owner found by binary
-// search over the prefix-summed lengths, slots read coalesced), cuts that list into equal contiguous ranges, one per lane
-// group, and every group streams its range with PullUnroll row pieces in flight, summing in registers while the owner stays
-// the same and flushing into a shared-memory accumulator row (FP64 shared atomics) when it changes: all lanes gather all the
-// time, whatever the degree distribution.  The per-unit work (pull_finish_unit) then runs coalesced over the tile's rows.
-constexpr int kFlatEdges = kStage * 2;       // edges staged per round (eu overlays PushSmem::stage)
-constexpr int kFlatVertsMax = 256;
-constexpr int kFlatAccMax = 4096;            // accumulator doubles of the multi-source kernel (dynamic shared memory)
-static_assert(kFlatEdges * 4 <= kStage * 8 && kFlatEdges * 2 <= kTileMax * 8 && kFlatVertsMax <= kTileMax && kHubSmem >= 1024,
-              "pull.cuh overlays its staging arrays on the scatter path's tile arrays");
-
-struct FlatView {      // shared memory of a flat tile: the scatter path's arrays are idle during a sweep
-    uint32_t *eu;      // [kFlatEdges] neighbour of the staged edge
-    uint16_t *ev;      // [kFlatEdges] local index of its owner
-    uint32_t *offs;    // [nv + 1] prefix of the list lengths
-    uint32_t *base, *head, *mask, *lenr, *wv, *cgv;  // per local vertex: ring geometry, real list length, vertex id, chunk group
-    double *acc;       // [nv][cols] (dynamic shared memory)
-};
-__device__ __forceinline__ FlatView flat_view(PushSmem &sm) {
-    extern __shared__ __align__(16) unsigned char dppr_dyn_smem[];
-    FlatView f;
-    f.eu = reinterpret_cast<uint32_t *>(sm.stage);
-    f.ev = reinterpret_cast<uint16_t *>(sm.t_ru);
-    f.offs = sm.h_c0;
-    f.cgv = sm.h_c0 + 512;
-    f.base = sm.t_base; f.head = sm.t_head; f.mask = sm.t_mask; f.lenr = sm.t_off; f.wv = sm.t_s;
-    f.acc = reinterpret_cast<double *>(dppr_dyn_smem) + 2;  // ([0] = relaxation factor of the sweep)
-    return f;
-}
-
-// `ntl` tiles starting at position `first` of the class-ordered tile list, all their vertices at once.  CTA-wide.
-template <int SB, bool ACCEL>
-__device__ void pull_do_flat(const PushArgs &a, const PullGeom &q, PushSmem &sm, int phase, const uint16_t *xcur, uint16_t *xnext,
-                             uint32_t first, uint32_t ntl, uint32_t n0, uint32_t n1, PullAcc &t) {
-    constexpr int U = PullUnroll<SB>::value;
-    const FlatView f = flat_view(sm);
-    const uint32_t V = (uint32_t)a.V, cols = q.G * SB, nv = ntl * q.vpt;
-    const uint32_t tid = threadIdx.x;
-#ifdef DPPR_PULL_PROF
-    unsigned long long tp0 = global_ns(), tp1, tp2, tp3, tp4;
-#define DPPR_PP(x) x = global_ns()
-#else
-#define DPPR_PP(x)
-#endif
-    // ---- ring metadata of the nv vertices; lists of the grid tier are not walked here ----
-    uint32_t mylen = 0;
-    if (tid < nv) {
-        const uint32_t tile = pull_tile_at<SB>(a, first + tid / q.vpt, n0, n1);
-        const uint32_t cg = tile / q.tpc;
-        const uint32_t w = (tile - cg * q.tpc) * q.vpt + tid % q.vpt;
-        uint4 m = make_uint4(0u, 0u, 0u, 1u);
-        if (w < V) m = pl_ldcs(&a.vmeta_out[w]);
-        f.base[tid] = m.x; f.head[tid] = m.y; f.mask[tid] = m.w - 1u; f.lenr[tid] = m.z;
-        f.wv[tid] = w; f.cgv[tid] = cg;
-        mylen = m.z >= (uint32_t)a.pull_big_min ? 0u : m.z;
-    }
-    uint32_t total;
-    const uint32_t off = block_exclusive_sum<uint32_t>(mylen, sm.scan, total);
-    if (tid < nv) f.offs[tid] = off;
-    if (tid == 0) f.offs[nv] = total;
-    for (uint32_t i = tid; i < nv * cols; i += kThreads) f.acc[i] = 0.0;
-    __syncthreads();
-    DPPR_PP(tp1);
-#ifdef DPPR_PULL_PROF
-    tp2 = tp1; tp3 = tp1;
-    unsigned long long stage_ns = 0, gather_ns = 0;
-#endif
-    // ---- the concatenated edge list, kFlatEdges at a time ----
-    const uint32_t lane_g = tid & (q.G - 1u), group = tid >> q.gs, ngroups = (uint32_t)kThreads >> q.gs;
-    for (uint32_t r0 = 0; r0 < total; r0 += kFlatEdges) {
-        const uint32_t nr = min((uint32_t)kFlatEdges, total - r0);
-        for (uint32_t i = tid; i < nr; i += kThreads) {
-            const uint32_t e = r0 + i;
-            uint32_t lo = 0, hi = nv;  // last vertex with offs <= e (zero-length lists share an offset with their successor)
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (f.offs[mid] <= e) lo = mid; else hi = mid;
-            }
-            f.eu[i] = (uint32_t)pl_ldcs(&a.pool[f.base[lo] + ((f.head[lo] + (e - f.offs[lo])) & f.mask[lo])]);
-            f.ev[i] = (uint16_t)lo;
-        }
-        __syncthreads();
-#ifdef DPPR_PULL_PROF
-        tp2 = global_ns(); stage_ns += tp2 - tp3;
-#endif
-        // equal contiguous ranges, one per lane group; register sums while the owner stays the same
-        const uint32_t per = (nr + ngroups - 1) / ngroups;
-        const uint32_t lo = min(nr, group * per), hi = min(nr, lo + per);
-        uint32_t cur = 0xffffffffu;
-        double acc[SB];
-#pragma unroll
-        for (int jj = 0; jj < SB; ++jj) acc[jj] = 0.0;
-        for (uint32_t i = lo; i < hi; i += U) {
-            uint32_t lv[U];
-            XPiece<SB> v[U];
-#pragma unroll
-            for (int k = 0; k < U; ++k) {
-                lv[k] = i + k < hi ? (uint32_t)f.ev[i + k] : 0xffffffffu;
-                const uint32_t c0 = lv[k] != 0xffffffffu ? (f.cgv[lv[k]] * q.G + lane_g) * SB : (uint32_t)a.Sr;
-                v[k] = c0 < (uint32_t)a.Sr ? x_gather<SB>(xcur, (size_t)f.eu[i + k] * (size_t)a.Sr + c0) : x_zero<SB>();
-            }
-#pragma unroll
-            for (int k = 0; k < U; ++k) {
-                if (lv[k] != cur) {
-                    if (cur != 0xffffffffu) {
-#pragma unroll
-                        for (int jj = 0; jj < SB; ++jj) {
-                            if (acc[jj] != 0.0) atomicAdd(&f.acc[cur * cols + lane_g * SB + jj], acc[jj]);
-                            acc[jj] = 0.0;
-                        }
-                    }
-                    cur = lv[k];
-                }
-                if (lv[k] != 0xffffffffu) x_accumulate<SB>(v[k], acc, t.nz);
-            }
-        }
-        if (cur != 0xffffffffu) {
-#pragma unroll
-            for (int jj = 0; jj < SB; ++jj)
-                if (acc[jj] != 0.0) atomicAdd(&f.acc[cur * cols + lane_g * SB + jj], acc[jj]);
-        }
-        __syncthreads();
-#ifdef DPPR_PULL_PROF
-        tp3 = global_ns(); gather_ns += tp3 - tp2;
-#endif
-    }
-    DPPR_PP(tp4);
-    // ---- per-unit work, coalesced over the rows of the tile ----
-    for (uint32_t idx = tid; idx < nv * q.G; idx += kThreads) {
-        const uint32_t lv = idx >> q.gs, g = idx & (q.G - 1u);
-        const uint32_t w = f.wv[lv], s0 = (f.cgv[lv] * q.G + g) * SB, len = f.lenr[lv];
-        if (w < V && s0 < (uint32_t)a.Sr && len < (uint32_t)a.pull_big_min) {
-            double acc[SB];
-#pragma unroll
-            for (int jj = 0; jj < SB; ++jj) acc[jj] = f.acc[lv * cols + g * SB + jj];
-            const XPiece<SB> xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
-            t.legal += pull_finish_unit<SB, ACCEL>(a, phase, w, s0, len, xc, acc, xnext, t.next_edges);
-        }
-    }
-    __syncthreads();  // (the shared arrays are reused by the next item)
-#ifdef DPPR_PULL_PROF
-    if (tid == 0 && a.ctalog) {  // per CTA: items, ns in setup / staging / gather / finish, edges
-        unsigned long long *row = a.ctalog + (size_t)blockIdx.x * 8;
-        row[0] += 1; row[1] += tp1 - tp0; row[2] += stage_ns; row[3] += gather_ns; row[4] += global_ns() - tp4; row[5] += total;
-    }
-#endif
-}
-
 template <int SB, bool ACCEL>
 __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, const uint16_t *xcur, uint16_t *xnext,
                            unsigned int *cnt_out, unsigned long long *edges_out, unsigned long long &gath, uint32_t sweep_index) {
@@ -656,8 +504,8 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
     unsigned int *next = &c->work_next[sweep_index & 1u];
     if (blockIdx.x == 0 && threadIdx.x == 0) c->work_next[(sweep_index + 1u) & 1u] = 0u;  // (idle during this sweep)
 
-    if (a.pull_sched == 0) {
-        // ---- items handed to WARPS: a warp takes a chunk, or a whole tile (its kThreads / G vertices, 32 / G at a time) ----
+    if (SB == 1) {
+        // ---- one source: items handed to WARPS -- a warp takes a chunk, or a whole tile (256 vertices, 32 at a time) ----
         const uint32_t nwork = nchunks + n0 + n1 + n2;
         uint32_t j = 0;
         if (lane == 0) j = atomicAdd(next, 1u);
@@ -677,7 +525,9 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
             j = __shfl_sync(kFull, jn, 0);
         }
     } else {
-        // ---- items handed to CTAs: kWarps chunks of the grid tier, or kFlat tiles processed flat (pull_do_flat) ----
+        // ---- several sources: items handed to CTAs -- kWarps chunks of the grid tier, or tiles whose vertices the CTA's
+        // warps share (32 / G each).  (Measured on BASELINE configs[3], 125 sources: 498 ms per batch against 573 ms with a
+        // flat, edge-balanced list per CTA and 683 ms with whole tiles per warp, profiles/README.md.) ----
         const uint32_t tpi = max(1u, 32u / q.vpt);  // tiles per item: at least 32 vertices
         const uint32_t ntl = n0 + n1 + n2;
         const uint32_t ngroups = (nchunks + kWarps - 1) / kWarps;
@@ -692,10 +542,7 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
             if (j < ngroups) {
                 const uint32_t cidx = j * kWarps + warp_id();
                 if (cidx < nchunks) pull_do_chunk<SB, ACCEL>(a, q, phase, xcur, xnext, cidx, nh, t);
-            } else if (a.pull_sched == 1) {
-                const uint32_t firstt = (j - ngroups) * tpi;
-                pull_do_flat<SB, ACCEL>(a, q, sm, phase, xcur, xnext, firstt, min(tpi, ntl - firstt), n0, n1, t);
-            } else {  // the tiles' vertices shared by the CTA's warps, 32 / G per warp
+            } else {
                 for (uint32_t tt = (j - ngroups) * tpi; tt < min(ntl, (j - ngroups + 1) * tpi); ++tt) {
                     const uint32_t tile = pull_tile_at<SB>(a, tt, n0, n1);
                     const uint32_t cg = tile / q.tpc;

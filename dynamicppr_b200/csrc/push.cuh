@@ -150,7 +150,6 @@ struct PushArgs {
     uint32_t tile_list_cap;
     double accel_frac;           // Chebyshev-accelerated sweeps while the frontier holds at least this fraction of all (vertex, source)
                                  // pairs; 0 = never (directed windows: the spectrum is not real)
-    int32_t pull_sched;          // who takes a work item of a sweep: 0 = a warp, 1 = a CTA (its warps share a tile's vertices)
     HubItem *big;                // grid-tier list
     uint32_t bigcap;
     double *bigacc;              // [bigcap][lanes per vertex x sources per lane] partial sums of the grid tier (zero between sweeps)
