@@ -166,13 +166,16 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     void *kern[4] = {dense_ ? (S_ == 1 ? persistent_kernel<0, 1>() : persistent_kernel<0, 8>()) : persistent_kernel<0>(), persistent_kernel<1>(),
                      persistent_kernel<2>(), persistent_kernel<3>()};
     // the switching kernels keep the relaxation factor of an accelerated sweep in (dynamic) shared memory (pull.cuh)
-    dyn_smem_ = dense_ ? 16 : 0;
+    dyn_smem_ = dense_ ? (size_t)env_int("DPPR_DYN_SMEM", 16) : 0;
+    if (dyn_smem_ < 16 && dense_) dyn_smem_ = 16;
+    if (const char *cv = std::getenv("DPPR_CARVEOUT")) DPPR_CUDA(cudaFuncSetAttribute(kern[0], cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(cv)));
     if (dyn_smem_) DPPR_CUDA(cudaFuncSetAttribute(kern[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem_));
     for (int v = 0; v < 4; ++v) {
         int per_sm = 0;
         DPPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern[v], kThreads, v == 0 ? dyn_smem_ : 0));
         if (per_sm < 1) throw CudaFailure("push kernel does not fit on an SM");
         coop_grid_[v] = std::min(per_sm, tn_.ctas_per_sm) * sm_count_;
+        if (env_int("DPPR_DEBUG", 0)) std::fprintf(stderr, "[dppr] variant %d: %d CTAs per SM fit, grid %d\n", v, per_sm, coop_grid_[v]);
     }
     {
         int per_sm = 0;

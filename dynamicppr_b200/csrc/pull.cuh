@@ -249,7 +249,7 @@ __device__ __forceinline__ void pull_count_flush(PushSmem &sm, uint32_t mine, un
 // Twitter-shaped window's vertices) -- and the grid tier: the (vertex, chunk group) pairs whose out-list is cut into chunks.
 // Tiles are listed in a scrambled order: the heavy ones (heads of the relabel blocks) sit at a regular stride.
 template <int SB>
-__device__ void pull_build(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, unsigned int *cnt_out) {
+__device__ __noinline__ void pull_build(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, unsigned int *cnt_out) {
     const PullGeom q = pull_geom<SB>(a);
     const uint32_t V = (uint32_t)a.V;
     uint32_t legal = 0;
@@ -492,7 +492,7 @@ __device__ __forceinline__ void pull_do_vertices(const PushArgs &a, const PullGe
 }
 
 template <int SB, bool ACCEL>
-__device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, const uint16_t *xcur, uint16_t *xnext,
+__device__ __noinline__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, const uint16_t *xcur, uint16_t *xnext,
                            unsigned int *cnt_out, unsigned long long *edges_out, unsigned long long &gath, uint32_t sweep_index) {
     const PullGeom q = pull_geom<SB>(a);
     const uint32_t V = (uint32_t)a.V;
@@ -565,7 +565,7 @@ __device__ void pull_sweep(const PushArgs &a, PushSmem &sm, PushCtrl *c, int pha
 // pairs whose residual has the sign of the running phase are the (un-popped) frontier of the next scatter iteration, the
 // others wait in qalt for the next phase
 template <int SB>
-__device__ void pull_compact(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, const uint16_t *x, unsigned long long *qout,
+__device__ __noinline__ void pull_compact(const PushArgs &a, PushSmem &sm, PushCtrl *c, int phase, const uint16_t *x, unsigned long long *qout,
                              unsigned int *cnt_out) {
     const PullGeom q = pull_geom<SB>(a);
     const uint32_t V = (uint32_t)a.V;
