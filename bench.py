@@ -374,7 +374,7 @@ def main():
                 traffic, traffic_note = ent.get("dram_bytes_per_launch"), ent.get("source")
         except Exception:
             pass
-        kname = f"push_persistent<{a.variant}, {'true' if (dense or (a.variant == 0 and cfg.index in (4, 5))) else 'false'}>"
+        kname = f"push_persistent<{a.variant}, {(1 if len(my_sources) == 1 else 8) if (dense or (a.variant == 0 and cfg.index in (4, 5))) else 0}>"
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes / K, "launch_ms": push_s * 1e3 / K,

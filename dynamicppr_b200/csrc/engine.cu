@@ -67,7 +67,7 @@ Tuning resolve_tuning(const dppr_tuning &t) {
     r.carry_gamma = pick_real(t.carry_gamma, "DPPR_CARRY_GAMMA", 1.0);
     r.carry_scale = pick_real(t.carry_scale, "DPPR_CARRY_SCALE", 0.01);
     r.dense_accel = pick_int(t.dense_accel, "DPPR_DENSE_ACCEL", 0);
-    r.accel_frac = env_real("DPPR_ACCEL_FRAC", 0.5);
+    r.accel_frac = env_real("DPPR_ACCEL_FRAC", 0.9);
     r.window_path = pick_int(t.window_path, "DPPR_WINDOW_PATH", 0);
     if (t.window_path == 0 && !env_int("DPPR_COOP_WINDOW", 1)) r.window_path = 1;   // round-1 spellings
     else if (t.window_path == 0 && !env_int("DPPR_FUSED_WINDOW", 1)) r.window_path = 2;
