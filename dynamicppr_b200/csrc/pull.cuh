@@ -597,7 +597,7 @@ __device__ __noinline__ void pull_compact(const PushArgs &a, PushSmem &sm, PushC
                 a.r[row + j] = rw;
                 mine = legal_push(rw, phase, a.eps);
                 if (!mine && dense_legal(rw, a.eps)) {  // the other sign: a seed of the next phase
-                    const unsigned pos = atomicAdd(&c->nalt, 1u);
+                    const unsigned pos = atomicAdd(&c->nalt[phase ^ 1], 1u);
                     if (pos < a.qcap) a.qalt[pos] = ((unsigned long long)(s0 + j) << 32) | w;
                     else atomicOr(&a.ctrl->errflags, kErrQueue);
                 }

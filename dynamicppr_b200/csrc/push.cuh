@@ -78,8 +78,9 @@ struct PushCtrl {
     unsigned int ntiles_active;    // dense mode: active tiles of the running episode = sum of ntiles_b
     unsigned int ntiles_b[3];      // ... by weight class (heavy first): tile_list holds three lists of tile_list_cap entries
     unsigned int work_next[2];     // dense mode: next work item (grid-tier chunk, then tile) of the running sweep, by sweep parity
-    unsigned int nalt;             // dense mode: items in qalt (residuals of the OTHER sign left by an episode: seeds of the next phase)
-    unsigned int pad3;
+    unsigned int nalt[2];          // dense mode: items in qalt -- residuals of the OTHER sign an episode left behind, the seeds of the
+                                   // next phase.  Indexed by the parity of the phase that CONSUMES them: the word a phase reads is never
+                                   // the one being reset or appended to between the same two grid barriers
     unsigned int pad0;
     unsigned long long bigpk;      // dense mode: grid-tier list of the running sweep, (entries << 32) | chunks
     unsigned long long gath;       // dense sweeps: gathered x entries that were non-zero = the (edge, source) pairs a scatter
@@ -322,7 +323,7 @@ __device__ void seed_pass(const PushArgs &a, PushSmem &sm, int phase, unsigned l
         // residuals of this phase's sign that a dense episode of the previous phase left behind (pull_compact): a sweep
         // pushes both signs, so they may sit anywhere, not only at repaired vertices.  (A pair that is also a candidate is
         // seeded twice: its second pop finds an exact zero and expands nothing.)
-        const unsigned long long nalt = __ldcg(&a.ctrl->nalt);
+        const unsigned long long nalt = __ldcg(&a.ctrl->nalt[phase]);
         const unsigned long long rounds2 = (nalt + stride - 1) / stride;
         for (unsigned long long rd = 0; rd < rounds2; ++rd) {
             const unsigned long long j = rd * stride + (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
@@ -681,7 +682,9 @@ __global__ void __launch_bounds__(kThreads, DENSE == 8 ? DPPR_DENSE8_MIN_BLOCKS 
     bool alive = true;
     for (int phase_i = 0; phase_i < 8 && alive; ++phase_i) {
         const int phase = phase_i & 1;
-        if (phase_i >= nphases && !(DENSE && __ldcg(&c->nalt) != 0u)) break;  // (uniform: nalt is stable between the barriers)
+        if (phase_i >= nphases && !(DENSE && __ldcg(&c->nalt[phase]) != 0u)) break;  // (uniform: this word was last written before
+        // the barrier that ended the previous phase; it is reset below, after the next barrier, and appended to only by
+        // episodes of the NEXT phase)
         if (phase_i > 0) {
             // Phase change.  Slow CTAs may still be polling cnt[it % 3] (== 0) to leave the loop below,
             // so the new seeds must not land in that slot: skip one iteration index.  The slots the
@@ -695,7 +698,7 @@ __global__ void __launch_bounds__(kThreads, DENSE == 8 ? DPPR_DENSE8_MIN_BLOCKS 
         }
         seed_pass(a, sm, phase, a.q[it & 1], &c->cnt[it % 3], phase_i < nphases);  // (extra phases: only what an episode left)
         if (!(alive = grid_barrier(c, gen, sm))) break;
-        if (DENSE && blockIdx.x == 0 && threadIdx.x == 0) c->nalt = 0u;  // consumed; episodes of this phase append from 0
+        if (DENSE && blockIdx.x == 0 && threadIdx.x == 0) c->nalt[phase] = 0u;  // consumed (episodes of this phase fill nalt[phase ^ 1])
         const bool carrying = VAR == 0 && a.carry_gamma > 0.0 && a.carry_gamma < 1.0;
         double theta = carrying ? __longlong_as_double((long long)__ldcg(&c->theta0[phase])) * a.carry_scale : a.eps;
         uint32_t n_prev = 0;
