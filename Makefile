@@ -18,10 +18,14 @@ $(LIBDIR)/libdppr.so: $(CSRC)/engine.cu $(CSRC)/capi.cu $(HDRS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) $(PTXAS_V) $(DPPR_DEFS) -shared -o $@ $(CSRC)/capi.cu -lcudart
 
-cli: $(BINDIR)/pagerank
-$(BINDIR)/pagerank: $(wildcard $(HOST)/*.cpp) $(wildcard $(HOST)/*.h) include/dppr.h $(LIBDIR)/libdppr.so
+cli: $(BINDIR)/pagerank $(BINDIR)/workload
+$(BINDIR)/pagerank: $(HOST)/main.cpp $(wildcard $(HOST)/*.h) include/dppr.h $(LIBDIR)/libdppr.so
 	@mkdir -p $(BINDIR)
-	$(CXX) -O2 -std=c++17 -Wall -Iinclude -I$(HOST) -o $@ $(wildcard $(HOST)/*.cpp) -L$(LIBDIR) -ldppr -Wl,-rpath,'$$ORIGIN/../lib' -lpthread
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude -I$(HOST) -o $@ $(HOST)/main.cpp -L$(LIBDIR) -ldppr -Wl,-rpath,'$$ORIGIN/../lib' -lpthread
+# drop-in for the reference's source picker (workload/Workload.cpp)
+$(BINDIR)/workload: $(HOST)/workload_main.cpp $(HOST)/SourcePicker.h include/dppr.h $(LIBDIR)/libdppr.so
+	@mkdir -p $(BINDIR)
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude -I$(HOST) -o $@ $(HOST)/workload_main.cpp -L$(LIBDIR) -ldppr -Wl,-rpath,'$$ORIGIN/../lib' -lpthread
 
 oracle:
 	$(MAKE) -C oracle all

@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "dppr_get_estimates", "dppr_get_residuals", "dppr_copy_estimates_device", "dppr_export_window_csr", "dppr_export_window_out_csr",
     "dppr_window_csr_entries", "dppr_set_state", "dppr_repair_only", "dppr_test_sort_pairs",
     "dppr_test_exclusive_scan", "dppr_test_relabel_slot", "dppr_debug_iterlog", "dppr_debug_ctalog", "dppr_kernel_launches",
-    "dppr_wait_event", "dppr_get_topk", "dppr_validate", "dppr_check_window_device",
+    "dppr_wait_event", "dppr_get_topk", "dppr_validate", "dppr_check_window_device", "dppr_check_window",
 ]
 
 
@@ -108,6 +108,7 @@ def load_library():
     L.dppr_get_topk.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, i32p, f64p]
     L.dppr_validate.argtypes = [vp, C.c_int32, f64p, f64p]
     L.dppr_check_window_device.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64)]
+    L.dppr_check_window.argtypes = [vp, i32p, C.c_int64, C.POINTER(C.c_int64)]
     L.dppr_get_batch_stats.argtypes = [vp, C.c_int64, C.POINTER(BatchStats)]
     L.dppr_batches_done.argtypes = [vp]; L.dppr_batches_done.restype = C.c_int64
     L.dppr_get_estimates.argtypes = [vp, C.c_int32, f64p]
@@ -248,6 +249,13 @@ class DynamicPPR:
         a, b = C.c_double(0.0), C.c_double(0.0)
         self._check(self.L.dppr_validate(self.h, source_index, C.byref(a), C.byref(b) if invariant else None))
         return a.value, b.value
+
+    def check_window(self, edges):
+        """same as check_window_device for W window edges in host memory"""
+        e = self._pairs(edges)
+        bad = C.c_int64(-1)
+        self._check(self.L.dppr_check_window(self.h, _i32(e), len(e), C.byref(bad)))
+        return int(bad.value)
 
     def check_window_device(self, device_ptr, n):
         """entries of the canonical window graph that differ from the one built from these W device-resident edges"""

@@ -155,6 +155,16 @@ int dppr_validate(dppr_engine *e, int32_t s, double *max_abs_residual, double *m
 int dppr_check_window_device(dppr_engine *e, const int32_t *dpairs, int64_t n, int64_t *mismatches) {
     return guarded(e, [&](dppr::Engine &g) { g.check_window_device(dpairs, n, mismatches); });
 }
+int dppr_check_window(dppr_engine *e, const int32_t *pairs, int64_t n, int64_t *mismatches) {
+    return guarded(e, [&](dppr::Engine &g) {
+        if (!pairs || n <= 0) throw dppr::InvalidArgument("null or empty window");
+        dppr::DevBuf<int2> tmp;
+        tmp.alloc((size_t)n);
+        DPPR_CUDA(cudaMemcpy(tmp.ptr, pairs, sizeof(int2) * (size_t)n, cudaMemcpyHostToDevice));
+        DPPR_CUDA(cudaDeviceSynchronize());
+        g.check_window_device((const int32_t *)tmp.ptr, n, mismatches);
+    });
+}
 int dppr_get_batch_stats(dppr_engine *e, int64_t k, dppr_batch_stats *out) {
     return guarded(e, [&](dppr::Engine &g) { g.get_stats(k, out); });
 }

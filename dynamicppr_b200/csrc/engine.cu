@@ -76,8 +76,19 @@ Tuning resolve_tuning(const dppr_tuning &t) {
     return r;
 }
 
-template <int VAR, int DENSE = 0>
-void *persistent_kernel() { return (void *)push_persistent<VAR, DENSE>; }
+template <int VAR>
+void *persistent_kernel_v(int dense) {
+    return dense == 8 ? (void *)push_persistent<VAR, 8> : dense == 1 ? (void *)push_persistent<VAR, 1> : (void *)push_persistent<VAR, 0>;
+}
+// the persistent kernel of a variant: scatter only (dense = 0), or with the switch to gather sweeps for one (1) / several (8) sources
+void *persistent_kernel(int variant, int dense) {
+    switch (variant) {
+        case 0: return persistent_kernel_v<0>(dense);
+        case 1: return persistent_kernel_v<1>(dense);
+        case 2: return persistent_kernel_v<2>(dense);
+        default: return persistent_kernel_v<3>(dense);
+    }
+}
 
 }  // namespace
 
@@ -132,7 +143,9 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
         // trips, which a sweep does not shorten (BASELINE configs[1]: 43 vs 18 us), and the kernel that can switch
         // carries more loop state, which costs its scatter iterations +9..+24 % when they are latency-bound (LJ/4,
         // youtube) and nothing when they are bandwidth-bound (Twitter-shaped).
-        const bool can = cfg.variant == DPPR_OPTIMIZED && mode_ == DPPR_ENGINE_LEVELSYNC && tn_.dense_div > 0.0;
+        // (every variant: the four differ in how the SCATTER form reads residuals and dedupes its frontier; a gather sweep decides each
+        // (vertex, source) once, so the episodes are the same for all of them -- round-1 verdict, item 7)
+        const bool can = mode_ == DPPR_ENGINE_LEVELSYNC && tn_.dense_div > 0.0;
         dense_ = can && tn_.dense >= 0 &&
                  (tn_.dense > 0 || (double)cfg.window_edges * (cfg.directed ? 1 : 2) * cfg.n_sources >= tn_.dense_min_edges);
         outlists_ = dense_ && D_ == 1;
@@ -163,16 +176,17 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     DPPR_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
 
     // cooperative grid per variant: every CTA must be co-resident for the software grid barrier
-    void *kern[4] = {dense_ ? (S_ == 1 ? persistent_kernel<0, 1>() : persistent_kernel<0, 8>()) : persistent_kernel<0>(), persistent_kernel<1>(),
-                     persistent_kernel<2>(), persistent_kernel<3>()};
+    const int dense_kind = dense_ ? (S_ == 1 ? 1 : 8) : 0;
+    void *kern[4] = {persistent_kernel(0, cfg_.variant == 0 ? dense_kind : 0), persistent_kernel(1, cfg_.variant == 1 ? dense_kind : 0),
+                     persistent_kernel(2, cfg_.variant == 2 ? dense_kind : 0), persistent_kernel(3, cfg_.variant == 3 ? dense_kind : 0)};
     // the switching kernels keep the relaxation factor of an accelerated sweep in (dynamic) shared memory (pull.cuh)
     dyn_smem_ = dense_ ? (size_t)env_int("DPPR_DYN_SMEM", 16) : 0;
     if (dyn_smem_ < 16 && dense_) dyn_smem_ = 16;
-    if (const char *cv = std::getenv("DPPR_CARVEOUT")) DPPR_CUDA(cudaFuncSetAttribute(kern[0], cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(cv)));
-    if (dyn_smem_) DPPR_CUDA(cudaFuncSetAttribute(kern[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem_));
+    if (const char *cv = std::getenv("DPPR_CARVEOUT")) DPPR_CUDA(cudaFuncSetAttribute(kern[cfg_.variant], cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(cv)));
+    if (dyn_smem_) DPPR_CUDA(cudaFuncSetAttribute(kern[cfg_.variant], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem_));
     for (int v = 0; v < 4; ++v) {
         int per_sm = 0;
-        DPPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern[v], kThreads, v == 0 ? dyn_smem_ : 0));
+        DPPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern[v], kThreads, v == cfg_.variant ? dyn_smem_ : 0));
         if (per_sm < 1) throw CudaFailure("push kernel does not fit on an SM");
         coop_grid_[v] = std::min(per_sm, tn_.ctas_per_sm) * sm_count_;
         if (env_int("DPPR_DEBUG", 0)) std::fprintf(stderr, "[dppr] variant %d: %d CTAs per SM fit, grid %d\n", v, per_sm, coop_grid_[v]);
@@ -595,15 +609,8 @@ void Engine::launch_push(bool init_mode) {
         return;
     }
     void *params[] = {(void *)&a};
-    void *kern = nullptr;
-    switch (cfg_.variant) {
-        case 0: kern = dense_ ? (S_ == 1 ? persistent_kernel<0, 1>() : persistent_kernel<0, 8>()) : persistent_kernel<0>(); break;
-        case 1: kern = persistent_kernel<1>(); break;
-        case 2: kern = persistent_kernel<2>(); break;
-        default: kern = persistent_kernel<3>(); break;
-    }
-    DPPR_CUDA(cudaLaunchCooperativeKernel(kern, dim3(coop_grid_[cfg_.variant]), dim3(kThreads), params,
-                                          cfg_.variant == 0 ? dyn_smem_ : 0, st_));
+    void *kern = persistent_kernel(cfg_.variant, dense_ ? (S_ == 1 ? 1 : 8) : 0);
+    DPPR_CUDA(cudaLaunchCooperativeKernel(kern, dim3(coop_grid_[cfg_.variant]), dim3(kThreads), params, dyn_smem_, st_));
     ++launch_counter();
 }
 

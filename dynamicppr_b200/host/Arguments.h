@@ -35,6 +35,13 @@ struct Settings {
     int stepwise = 0;             // --stepwise 1: one launch per push iteration
     std::string dump_file;        // --dump <file>: final estimates of every source, raw float64
     int stats = 0;                // --stats 1: per-batch counters on stdout
+    double pool_factor = 0.0;     // --pool-factor <x>: adjacency pool slots per window CSR entry (0 = library default, 8)
+    int validate = 0;             // --validate 1: the reference's -DVALIDATE checks after the initial solve and after every batch, on
+                                  //   the device (window graph vs the file's window, residual bound, push invariant); exit(-1) on a violation
+    std::string pick;             // --pick top10|top1000|top1000000: choose the source like the reference's `workload` tool does
+                                  //   (workload/Workload.cpp:47-55; 4th id of the bucket, as scripts/gpu.sh:17 does) instead of -s
+    int progress = 1;             // --progress 0: print the keys at the end only (the default follows the reference's cadence,
+                                  //   gpu/PPRGPU.cuh:116: before every batch when a batch holds more than 100 edges, else every 100)
 };
 
 class ArgScanner {
@@ -87,7 +94,8 @@ inline void print_usage() {
     std::cout << "-o: gVariant" << std::endl;
     std::cout << 0 << ": optimized, " << 1 << ": fast frontier, " << 2 << ": eager, " << 3 << ": VANILLA" << std::endl;
     std::cout << "-e: error tolerance" << std::endl;
-    std::cout << "extensions: --sources <file> --device <n> --stepwise <0|1> --dump <file> --stats <0|1>" << std::endl;
+    std::cout << "extensions: --sources <file> --device <n> --stepwise <0|1> --dump <file> --stats <0|1> --pool-factor <x>" << std::endl;
+    std::cout << "            --validate <0|1> --pick <top10|top1000|top1000000> --progress <0|1>" << std::endl;
     std::cout << "EXAMPLE: ./pagerank -d ../data/com-dblp.ungraph.bin -a 0 -i 0 -y 1 -w 0.1 -n 0 -r 0.01 -b 1000 -s 1" << std::endl;
     std::cout << "EXAMPLE: ./pagerank -d ../data/com-dblp.ungraph.bin -a 0 -i 0 -y 1 -w 0.1 -n 1 -c 100 -l 10000 -s 1" << std::endl;
 }
@@ -104,6 +112,7 @@ inline bool settings_valid(const Settings &s) {
         return false;
     }
     if (s.variant < 0 || s.variant > 3) return false;
+    if (!s.pick.empty() && s.pick != "top10" && s.pick != "top1000" && s.pick != "top1000000") return false;
     return true;
 }
 
@@ -129,6 +138,10 @@ inline Settings parse_arguments(int argc, char **argv) {
     s.stepwise = (int)a.integer("--stepwise", 0);
     s.dump_file = a.str("--dump", "");
     s.stats = (int)a.integer("--stats", 0);
+    s.pool_factor = a.real("--pool-factor", 0.0);
+    s.validate = (int)a.integer("--validate", 0);
+    s.pick = a.str("--pick", "");
+    s.progress = (int)a.integer("--progress", 1);
     if (!settings_valid(s)) {
         std::cout << "invalid arguments" << std::endl;
         print_usage();

@@ -75,6 +75,9 @@ public:
     EdgeStream &operator=(const EdgeStream &) = delete;
 
     const int32_t *initial_window() const { return pairs_; }
+    const int32_t *all_pairs() const { return pairs_; }
+    // the W edges the window holds after `done` batches: stream records [done * B, done * B + W)
+    const int32_t *window_after(size_t done) const { return pairs_ + 2 * done * per_batch; }
     // nullptr when fewer than per_batch edges remain (StreamUpdates returning true, SlidingGraphVec.h:221)
     const int32_t *next_batch() {
         if (per_batch == 0 || pos_ + per_batch > stream_length) return nullptr;

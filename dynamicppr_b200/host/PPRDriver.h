@@ -14,6 +14,7 @@
 #include "dppr.h"
 #include "Arguments.h"
 #include "EdgeStream.h"
+#include "SourcePicker.h"
 
 namespace dppr_host {
 
@@ -28,6 +29,15 @@ class PPRDriver {
 public:
     PPRDriver(const Settings &s, EdgeStream &stream) : s_(s), stream_(stream) {
         sources_.push_back(s.source);
+        if (!s.pick.empty()) {
+            // the reference's protocol: `workload` writes ten ids per bucket, scripts/gpu.sh:17 runs the 4th (SOURCES_START=3)
+            int64_t st, ed;
+            bucket_ranks(s.pick, st, ed);
+            const DegreeRanking r = rank_by_degree(s.device, stream.vertex_count, stream.directed, true, stream.all_pairs(),
+                                                   (int64_t)stream.stream_length);
+            const std::vector<int32_t> ids = choose_degree_range(r, 10, st, ed);
+            sources_[0] = ids[3];
+        }
         if (!s.sources_file.empty()) {
             sources_.clear();
             std::ifstream in(s.sources_file.c_str());
@@ -54,6 +64,7 @@ public:
         c.sources = sources_.data();
         c.engine_mode = s.stepwise ? DPPR_ENGINE_STEPWISE : DPPR_ENGINE_AUTO;
         c.record_timing = 1;
+        c.pool_factor = s.pool_factor;
         std::cout << "init sliding graph.." << std::endl;
         int rc = dppr_create(&c, &eng_);
         if (rc != DPPR_OK) {
@@ -74,6 +85,7 @@ public:
         check_health(st);
         std::cout << "elapsed time=" << st.ms_push << "ms" << std::endl;
         print_counters(st);
+        if (s_.validate) validate(0, stream_.initial_window());
         dump();
     }
 
@@ -81,11 +93,14 @@ public:
     void DynamicExecute() {
         std::cout << "start..." << std::endl;
         die_on(dppr_solve_initial(eng_), eng_, "dppr_solve_initial");
+        if (s_.validate) validate(0, stream_.initial_window());
         const size_t B = stream_.per_batch;
         size_t k = 0;            // batches enqueued
         size_t reported = 0;     // batches folded into ppr_time
         while (k < stream_.batch_count) {
-            if (k > 0 && k % 100 == 0) {  // progress at the reference's cadence for small batches (gpu/PPRGPU.cuh:116)
+            // progress at the reference's cadence (gpu/PPRGPU.cuh:116): before EVERY batch when a batch holds more than 100
+            // edges, else before every 100th (--progress 0: at the end only; the per-batch form waits for the device each time)
+            if (s_.progress && (B > 100 || (k + 1) % 100 == 0)) {
                 fold_stats(reported, k);
                 print_keys(k + 1, k);
             }
@@ -93,6 +108,7 @@ public:
             if (!batch) break;  // fewer than B edges remain: stop, as the reference does
             die_on(dppr_slide_pairs(eng_, batch, (int64_t)B), eng_, "dppr_slide_pairs");
             ++k;
+            if (s_.validate) validate(k, stream_.window_after(k));
         }
         fold_stats(reported, k);
         std::cout << "finish!" << std::endl;
@@ -146,6 +162,7 @@ private:
     void print_extras(size_t done) {
         std::cout << "batches_done " << done << std::endl;
         std::cout << "sources " << sources_.size() << std::endl;
+        std::cout << "source_batches_per_s " << (e2e_time_ > 0 ? (double)sources_.size() * (double)done / e2e_time_ * 1000.0 : 0) << std::endl;
         std::cout << "p50_batch_ms " << pct(ppr_samples_, 0.5) << std::endl;
         std::cout << "p95_batch_ms " << pct(ppr_samples_, 0.95) << std::endl;
         std::cout << "e2e_time_ms " << e2e_time_ << std::endl;
@@ -156,6 +173,25 @@ private:
         std::cout << "traversed_edges " << edges_ << std::endl;
         std::cout << "ring_relocations " << relocs_ << std::endl;
         std::cout << "pool_slots_used " << pool_used_ << std::endl;
+    }
+    // the reference's -DVALIDATE (gpu/PPRGPU.cuh:58-60,90-92,165-167), on the device: window graph bit-exact against the
+    // file's window, |r| within eps, push invariant (implies |p - pi| <= eps) -- exit(-1) on a violation, like its asserts
+    void validate(size_t batch, const int32_t *window_pairs) {
+        int64_t bad = -1;
+        die_on(dppr_check_window(eng_, window_pairs, stream_.window, &bad), eng_, "dppr_check_window");
+        double worst_r = 0, worst_inv = 0;
+        for (size_t i = 0; i < sources_.size(); ++i) {
+            double mr = 0, inv = 0;
+            die_on(dppr_validate(eng_, (int32_t)i, &mr, &inv), eng_, "dppr_validate");
+            worst_r = std::max(worst_r, mr);
+            worst_inv = std::max(worst_inv, inv);
+        }
+        std::cout << "validate batch " << batch << ": window_mismatches=" << bad << " max_abs_residual=" << worst_r
+                  << " invariant_defect=" << worst_inv << std::endl;
+        if (bad != 0 || !(worst_r <= s_.tolerance) || !(worst_inv <= 1e-12)) {
+            std::cout << "VALIDATION FAILED" << std::endl;
+            std::exit(-1);
+        }
     }
     void print_counters(const dppr_batch_stats &st) {
         std::cout << "push_iterations " << st.iterations << std::endl;

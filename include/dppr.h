@@ -214,6 +214,8 @@ int dppr_get_topk(dppr_engine *e, int32_t first_source, int32_t n_sources, int32
  * edge list + out-degrees that differ from the engine's window graph (0 = bit-exact). */
 int dppr_validate(dppr_engine *e, int32_t source_index, double *max_abs_residual, double *max_invariant_defect);
 int dppr_check_window_device(dppr_engine *e, const int32_t *device_pairs, int64_t n, int64_t *mismatches);
+/* same, the W window edges in host memory (e.g. the mmap'ed file: records [k*B, k*B + W) after k batches) */
+int dppr_check_window(dppr_engine *e, const int32_t *pairs, int64_t n, int64_t *mismatches);
 
 /* Canonical window graph, the object the reference validator compares
  * (gpu/PPRRevPushGPU.cuh:45-90): in_row_ptr[V+1], in_col_ind[E_w] with rows ascending and duplicates

@@ -47,14 +47,28 @@ def check_out_lists(eng, V, rp, ci, directed, tag):
                          ids=["all-tiers", "grid-tier-chunks-of-1", "lane-tier", "warp-tier", "grid-tier"])
 @pytest.mark.parametrize("path", GOLDEN, ids=GOLDEN_IDS)
 def test_golden_with_forced_dense_iterations(path, tiers, monkeypatch):
-    force_dense(monkeypatch, tiers=tiers)
+    _golden_forced_dense(path, tiers, 0, monkeypatch)
+
+
+@pytest.mark.parametrize("div", ["1e15", "64"], ids=["always", "mixed"])
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("path", [p for p in GOLDEN if any(t in p for t in ("pl_undirected", "hub_expiry", "dense_multi_directed", "rmat_directed"))],
+                         ids=lambda p: p.split("/")[-1][:-4])
+def test_golden_dense_iterations_for_the_other_variants(path, variant, div, monkeypatch):
+    """the sweeps are the same for every variant (they differ in how the SCATTER form reads residuals and dedupes); scatter
+    iterations of variants 1-3 (snapshot passes, status stamps, repair pass) alternate with gather episodes"""
+    _golden_forced_dense(path, (3, 12, 5), variant, monkeypatch, div=div)
+
+
+def _golden_forced_dense(path, tiers, variant, monkeypatch, div="1e15"):
+    force_dense(monkeypatch, div=div, tiers=tiers)
     g = np.load(path)
     V, directed, edges = int(g["V"]), bool(g["directed"]), g["edges"]
     wl = golden_workload(g)
     eps = float(g["eps"])
     use_ref_p = not d2_possible(g)
     sweeps = 0
-    with DynamicPPR(V, directed, wl.W, wl.B, [int(g["source"])], epsilon=eps, variant=0,
+    with DynamicPPR(V, directed, wl.W, wl.B, [int(g["source"])], epsilon=eps, variant=variant,
                     engine_mode=binding.ENGINE_LEVELSYNC) as eng:
         eng.init_window_pairs(edges[: wl.W])
         eng.solve_initial()
@@ -72,7 +86,7 @@ def test_golden_with_forced_dense_iterations(path, tiers, monkeypatch):
             np.testing.assert_array_equal(ci, g["in_col"][k], err_msg=tag)
             np.testing.assert_array_equal(od, g["outdeg"][k], err_msg=tag)
             check_out_lists(eng, V, rp, ci, directed, tag)
-            ref_p = g["v0_p"][k] if (use_ref_p and "v0_p" in g) else None
+            ref_p = g[f"v{variant}_p"][k] if (use_ref_p and f"v{variant}_p" in g) else None
             check_against(eng.estimates(), eng.residuals(), ref_p, g["pow"][k], eps, tag)
     assert sweeps > 0, f"{path}: the dense path never ran"
 
