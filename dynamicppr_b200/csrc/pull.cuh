@@ -624,6 +624,7 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
         c->ntiles_b[0] = 0; c->ntiles_b[1] = 0; c->ntiles_b[2] = 0;
         c->work_next[0] = 0; c->work_next[1] = 0;
         c->ep_slots = 0; c->ep_pairs = 0; c->ep_units = 0;
+        c->nalt[phase ^ 1] = 0;  // (this episode re-absorbs whatever an earlier one of this phase left for the next phase)
     }
     // ... and are simply UN-popped instead of being scattered edge by edge: r[u] += ru, p[u] -= a ru (one thread per hub;
     // r[u] may already hold adds of this iteration, hence the atomic).  The build pass below then finds u legal again and

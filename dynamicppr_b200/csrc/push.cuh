@@ -296,7 +296,7 @@ __device__ __forceinline__ void push_edges(const PushArgs &a, PushSmem &sm, cons
 
 // ---- seeds --------------------------------------------------------------------------------------
 __device__ void seed_pass(const PushArgs &a, PushSmem &sm, int phase, unsigned long long *qout,
-                          unsigned int *cnt_out, bool with_candidates = true) {
+                          unsigned int *cnt_out, bool with_candidates = true, bool with_alt = false) {
     const uint32_t ncand = a.init_mode ? 1u : __ldcg(a.ncand);
     const unsigned long long total = with_candidates ? (unsigned long long)ncand * (unsigned)a.S : 0ull;
     const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
@@ -319,10 +319,11 @@ __device__ void seed_pass(const PushArgs &a, PushSmem &sm, int phase, unsigned l
         if ((rd & 3) == 3) stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
     }
     stage_flush(sm, qout, cnt_out, a.qcap, a.ctrl);
-    if (a.qalt) {
-        // residuals of this phase's sign that a dense episode of the previous phase left behind (pull_compact): a sweep
-        // pushes both signs, so they may sit anywhere, not only at repaired vertices.  (A pair that is also a candidate is
-        // seeded twice: its second pop finds an exact zero and expands nothing.)
+    if (with_alt && a.qalt) {
+        // residuals of this phase's sign that the last dense episode of the previous phase left behind (pull_compact): a
+        // sweep pushes both signs, so they may sit anywhere, not only at repaired vertices.  An episode absorbs EVERY
+        // residual beyond eps, so after one this list is complete and the candidates are not scanned at all -- no
+        // (source, vertex) pair is ever seeded twice (variants 1-3 would pop a duplicate twice).
         const unsigned long long nalt = __ldcg(&a.ctrl->nalt[phase]);
         const unsigned long long rounds2 = (nalt + stride - 1) / stride;
         for (unsigned long long rd = 0; rd < rounds2; ++rd) {
@@ -680,11 +681,12 @@ __global__ void __launch_bounds__(kThreads, DENSE == 8 ? DPPR_DENSE8_MIN_BLOCKS 
     // (qalt): they seed the next phase, and further phases run while an episode keeps leaving some (normally none do).
     const int nphases = a.init_mode ? 1 : 2;
     bool alive = true;
+    bool prev_episode = false;  // an episode ran in the previous phase (every CTA takes the same decisions)
     for (int phase_i = 0; phase_i < 8 && alive; ++phase_i) {
         const int phase = phase_i & 1;
-        if (phase_i >= nphases && !(DENSE && __ldcg(&c->nalt[phase]) != 0u)) break;  // (uniform: this word was last written before
-        // the barrier that ended the previous phase; it is reset below, after the next barrier, and appended to only by
-        // episodes of the NEXT phase)
+        if (phase_i >= nphases && !(DENSE && prev_episode && __ldcg(&c->nalt[phase]) != 0u)) break;  // (uniform: this word was last
+        // written before the barrier that ended the previous phase; it is reset below, after the next barrier, and
+        // appended to only by episodes of the NEXT phase)
         if (phase_i > 0) {
             // Phase change.  Slow CTAs may still be polling cnt[it % 3] (== 0) to leave the loop below,
             // so the new seeds must not land in that slot: skip one iteration index.  The slots the
@@ -696,7 +698,9 @@ __global__ void __launch_bounds__(kThreads, DENSE == 8 ? DPPR_DENSE8_MIN_BLOCKS 
             }
             ++it;
         }
-        seed_pass(a, sm, phase, a.q[it & 1], &c->cnt[it % 3], phase_i < nphases);  // (extra phases: only what an episode left)
+        // seeds: the repaired vertices -- or, if an episode ran in the previous phase, what it left of this phase's sign
+        seed_pass(a, sm, phase, a.q[it & 1], &c->cnt[it % 3], phase_i < nphases && !prev_episode, DENSE && prev_episode);
+        prev_episode = false;  // (from here on: "an episode ran in THIS phase")
         if (!(alive = grid_barrier(c, gen, sm))) break;
         if (DENSE && blockIdx.x == 0 && threadIdx.x == 0) c->nalt[phase] = 0u;  // consumed (episodes of this phase fill nalt[phase ^ 1])
         const bool carrying = VAR == 0 && a.carry_gamma > 0.0 && a.carry_gamma < 1.0;
@@ -806,6 +810,7 @@ __global__ void __launch_bounds__(kThreads, DENSE == 8 ? DPPR_DENSE8_MIN_BLOCKS 
                 c->hpk[(it + 1) % 3] = 0;
                 hubs_acc += (uint32_t)(dense_hpk >> 32);
             }
+            prev_episode = true;
             n_prev = 0;  // (no growth estimate for the first scatter iteration after the sweeps)
             fresh_phase = false;
             t_prev = 0.0;
