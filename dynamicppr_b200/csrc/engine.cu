@@ -67,6 +67,7 @@ Tuning resolve_tuning(const dppr_tuning &t) {
     r.carry_gamma = pick_real(t.carry_gamma, "DPPR_CARRY_GAMMA", 1.0);
     r.carry_scale = pick_real(t.carry_scale, "DPPR_CARRY_SCALE", 0.01);
     r.dense_accel = pick_int(t.dense_accel, "DPPR_DENSE_ACCEL", 0);
+    r.signed_push = pick_int(t.signed_push, "DPPR_SIGNED_PUSH", 0);
     r.accel_frac = env_real("DPPR_ACCEL_FRAC", 0.9);
     r.window_path = pick_int(t.window_path, "DPPR_WINDOW_PATH", 0);
     if (t.window_path == 0 && !env_int("DPPR_COOP_WINDOW", 1)) r.window_path = 1;   // round-1 spellings
@@ -591,6 +592,7 @@ void Engine::launch_push(bool init_mode) {
     a.pull_warp_min = tn_.pull_warp_min; a.pull_big_min = pull_big_min_; a.pull_big_chunk = pull_big_chunk_;
     a.big = big_.ptr; a.bigcap = bigcap_; a.bigacc = bigacc_.ptr; a.tile_list = tile_list_.ptr; a.tile_list_cap = tile_cap_;
     a.accel_frac = (D_ == 2 && tn_.dense_accel >= 0) ? tn_.accel_frac : 0.0;
+    a.signed_push = tn_.signed_push >= 0 ? 1 : 0;
     {
         const int lanes_sources = S_ == 1 ? 1 : 8 << pull_gshift_;
         const uint64_t ntiles = (uint64_t)div_up(V_, kThreads >> pull_gshift_) * (uint64_t)((Sr_ + lanes_sources - 1) / lanes_sources);
@@ -621,9 +623,11 @@ void Engine::launch_push_stepwise(PushArgs &a) {
     const int var = cfg_.variant;
     uint32_t it = 0;
     PushCtrl h{};
-    const int nphases = a.init_mode ? 1 : 2;
-    for (int phase = 0; phase < nphases; ++phase) {
-        if (phase > 0) {  // same slot hygiene as push_persistent at a phase change
+    const bool signed_mode = var == 0 && a.signed_push && !a.init_mode;  // (push_persistent: variant 0 pushes both signs in one pass)
+    const int nphases = (a.init_mode || signed_mode) ? 1 : 2;
+    for (int phase_i = 0; phase_i < nphases; ++phase_i) {
+        const int phase = signed_mode ? kSignedPhase : phase_i;
+        if (phase_i > 0) {  // same slot hygiene as push_persistent at a phase change
             DPPR_CUDA(cudaMemsetAsync(&ctrl_.ptr->cnt[(it + 2) % 3], 0, sizeof(unsigned), st_));
             DPPR_CUDA(cudaMemsetAsync(&ctrl_.ptr->hpk[(it + 1) % 3], 0, sizeof(unsigned long long), st_));
             ++it;
@@ -638,7 +642,7 @@ void Engine::launch_push_stepwise(PushArgs &a) {
             const int level = step_level_ + (int)it + 1;
             if (theta < 0.0) {  // first iteration of the phase: the seeds' largest residual is known now
                 double t0;
-                std::memcpy(&t0, &h.theta0[phase], sizeof(double));
+                std::memcpy(&t0, &h.theta0[phase & 1], sizeof(double));
                 const bool carrying = var == 0 && a.carry_gamma > 0.0 && a.carry_gamma < 1.0;
                 theta = carrying ? t0 * a.carry_scale : a.eps;
             }

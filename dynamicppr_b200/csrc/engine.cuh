@@ -39,6 +39,7 @@ struct Tuning {
     int ctas_per_sm = 4, tile_cap = 128, max_iters = 400000;
     int dense = 0;  // 0 auto, 1 always the switching kernel, -1 scatter only
     int dense_accel = 0;      // 0 / 1: Chebyshev-accelerated sweeps on undirected windows, -1: off
+    int signed_push = 0;      // 0 / 1: variant 0 pushes both signs in one pass, -1: the reference's two passes
     double accel_frac = 0.9;  // ... while the frontier holds at least this fraction of all (vertex, source) pairs
     double dense_div = 4.0, dense_min_edges = 2.0e7;
     int pull_group = 16, pull_warp_min = 32, pull_big_min = 0, pull_big_chunk = 0;  // (0: by the number of sources)

@@ -596,8 +596,8 @@ __device__ __noinline__ void pull_compact(const PushArgs &a, PushSmem &sm, PushC
                 const double rw = a.r[row + j] + bf16_value(h);
                 a.r[row + j] = rw;
                 mine = legal_push(rw, phase, a.eps);
-                if (!mine && dense_legal(rw, a.eps)) {  // the other sign: a seed of the next phase
-                    const unsigned pos = atomicAdd(&c->nalt[phase ^ 1], 1u);
+                if (!mine && dense_legal(rw, a.eps)) {  // the other sign: a seed of the next phase (phase is 0 or 1 here)
+                    const unsigned pos = atomicAdd(&c->nalt[(phase ^ 1) & 1], 1u);
                     if (pos < a.qcap) a.qalt[pos] = ((unsigned long long)(s0 + j) << 32) | w;
                     else atomicOr(&a.ctrl->errflags, kErrQueue);
                 }
@@ -624,7 +624,7 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
         c->ntiles_b[0] = 0; c->ntiles_b[1] = 0; c->ntiles_b[2] = 0;
         c->work_next[0] = 0; c->work_next[1] = 0;
         c->ep_slots = 0; c->ep_pairs = 0; c->ep_units = 0;
-        c->nalt[phase ^ 1] = 0;  // (this episode re-absorbs whatever an earlier one of this phase left for the next phase)
+        c->nalt[(phase ^ 1) & 1] = 0;  // (this episode re-absorbs whatever an earlier one of this phase left for the next phase)
     }
     // ... and are simply UN-popped instead of being scattered edge by edge: r[u] += ru, p[u] -= a ru (one thread per hub;
     // r[u] may already hold adds of this iteration, hence the atomic).  The build pass below then finds u legal again and

@@ -149,6 +149,7 @@ struct PushArgs {
     uint32_t pull_tile_mul;      // tile visiting order: tile = (t * mul) mod ntiles, mul coprime to ntiles
     uint32_t *tile_list;         // active tiles of the running dense episode: [3][tile_list_cap], heavy tiles first
     uint32_t tile_list_cap;
+    int32_t signed_push;         // variant 0: one pass over both signs instead of the reference's two (see push_persistent)
     double accel_frac;           // Chebyshev-accelerated sweeps while the frontier holds at least this fraction of all (vertex, source)
                                  // pairs; 0 = never (directed windows: the spectrum is not real)
     HubItem *big;                // grid-tier list
@@ -189,8 +190,10 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 #define DPPR_TL(tl, slot) do { if ((tl) && threadIdx.x == 0) (tl)[slot] = global_ns(); } while (0)
 
-__device__ __forceinline__ bool legal_push(double x, int phase, double eps) {  // gpu/PPRCommon.cuh:6-11
-    return phase == 0 ? (x > eps) : (x < -eps);
+// phase 0 / 1: the reference's two passes (gpu/PPRCommon.cuh:6-11); kSignedPhase: both signs at once (variant 0, below)
+constexpr int kSignedPhase = 2;
+__device__ __forceinline__ bool legal_push(double x, int phase, double eps) {
+    return phase == 0 ? (x > eps) : phase == 1 ? (x < -eps) : (fabs(x) > eps);
 }
 
 // ---- next-frontier staging ------------------------------------------------------------------
@@ -324,7 +327,7 @@ __device__ void seed_pass(const PushArgs &a, PushSmem &sm, int phase, unsigned l
         // sweep pushes both signs, so they may sit anywhere, not only at repaired vertices.  An episode absorbs EVERY
         // residual beyond eps, so after one this list is complete and the candidates are not scanned at all -- no
         // (source, vertex) pair is ever seeded twice (variants 1-3 would pop a duplicate twice).
-        const unsigned long long nalt = __ldcg(&a.ctrl->nalt[phase]);
+        const unsigned long long nalt = __ldcg(&a.ctrl->nalt[phase & 1]);
         const unsigned long long rounds2 = (nalt + stride - 1) / stride;
         for (unsigned long long rd = 0; rd < rounds2; ++rd) {
             const unsigned long long j = rd * stride + (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
@@ -343,7 +346,7 @@ __device__ void seed_pass(const PushArgs &a, PushSmem &sm, int phase, unsigned l
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, off));
-    if (lane_id() == 0 && mx > 0.0) atomicMax(&a.ctrl->theta0[phase], (unsigned long long)__double_as_longlong(mx));
+    if (lane_id() == 0 && mx > 0.0) atomicMax(&a.ctrl->theta0[phase & 1], (unsigned long long)__double_as_longlong(mx));
 }
 
 // ---- pre pass: variants 1,3 snapshot + zero (gpu/Inspect.cuh:52-65); variant 2 status stamp ------
@@ -679,12 +682,20 @@ __global__ void __launch_bounds__(kThreads, DENSE == 8 ? DPPR_DENSE8_MIN_BLOCKS 
     // Phases alternate in sign: 0 pushes residuals above eps, 1 those below -eps (the reference runs exactly these two,
     // gpu/PPRGPU.cuh:128-163).  A dense episode pushes BOTH signs at once and may leave residuals of the other sign behind
     // (qalt): they seed the next phase, and further phases run while an episode keeps leaving some (normally none do).
-    const int nphases = a.init_mode ? 1 : 2;
+    //
+    // Variant 0 pushes both signs in ONE pass (a.signed_push): its frontier is deduped by the threshold crossing
+    // |old| <= eps < |old + add| and popped by an exchange that claims the whole residual, so mixed-sign adds are harmless --
+    // a vertex that leaves the band, is pulled back and leaves again is enqueued twice, and its second pop finds an exact
+    // zero.  The two passes of the reference each have their own ramp-up and tail of tiny iterations, and residuals of
+    // opposite sign cancel instead of being pushed separately: about half the iterations on the L2-resident configs, where an
+    // iteration costs a fixed ~6 us of dependent round trips.  Variants 1-3 keep the reference's two passes.
+    const bool signed_mode = VAR == 0 && a.signed_push && !a.init_mode;
+    const int nphases = (a.init_mode || signed_mode) ? 1 : 2;
     bool alive = true;
     bool prev_episode = false;  // an episode ran in the previous phase (every CTA takes the same decisions)
     for (int phase_i = 0; phase_i < 8 && alive; ++phase_i) {
-        const int phase = phase_i & 1;
-        if (phase_i >= nphases && !(DENSE && prev_episode && __ldcg(&c->nalt[phase]) != 0u)) break;  // (uniform: this word was last
+        const int phase = signed_mode ? kSignedPhase : (phase_i & 1);
+        if (phase_i >= nphases && !(DENSE && !signed_mode && prev_episode && __ldcg(&c->nalt[phase & 1]) != 0u)) break;  // (uniform: this word was last
         // written before the barrier that ended the previous phase; it is reset below, after the next barrier, and
         // appended to only by episodes of the NEXT phase)
         if (phase_i > 0) {
@@ -699,12 +710,12 @@ __global__ void __launch_bounds__(kThreads, DENSE == 8 ? DPPR_DENSE8_MIN_BLOCKS 
             ++it;
         }
         // seeds: the repaired vertices -- or, if an episode ran in the previous phase, what it left of this phase's sign
-        seed_pass(a, sm, phase, a.q[it & 1], &c->cnt[it % 3], phase_i < nphases && !prev_episode, DENSE && prev_episode);
+        seed_pass(a, sm, phase, a.q[it & 1], &c->cnt[it % 3], phase_i < nphases && !prev_episode, DENSE && prev_episode && !signed_mode);
         prev_episode = false;  // (from here on: "an episode ran in THIS phase")
         if (!(alive = grid_barrier(c, gen, sm))) break;
-        if (DENSE && blockIdx.x == 0 && threadIdx.x == 0) c->nalt[phase] = 0u;  // consumed (episodes of this phase fill nalt[phase ^ 1])
+        if (DENSE && blockIdx.x == 0 && threadIdx.x == 0) c->nalt[phase & 1] = 0u;  // consumed (episodes of this phase fill nalt[phase ^ 1])
         const bool carrying = VAR == 0 && a.carry_gamma > 0.0 && a.carry_gamma < 1.0;
-        double theta = carrying ? __longlong_as_double((long long)__ldcg(&c->theta0[phase])) * a.carry_scale : a.eps;
+        double theta = carrying ? __longlong_as_double((long long)__ldcg(&c->theta0[phase & 1])) * a.carry_scale : a.eps;
         uint32_t n_prev = 0;
         bool fresh_phase = true;
         double t_prev = 0.0;  // in-edges the previous scatter iteration traversed, grid-wide (DENSE)

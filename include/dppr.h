@@ -75,7 +75,8 @@ typedef struct dppr_tuning {
     double carry_gamma;         /* variant 0 threshold schedule; default off (1.0)                               [DPPR_CARRY_GAMMA] */
     double carry_scale;         /* default 0.01                                                                   [DPPR_CARRY_SCALE] */
     int32_t dense_accel;        /* Chebyshev-accelerated sweeps on undirected windows: 0/1 on (default), -1 off       [DPPR_DENSE_ACCEL] */
-    int32_t reserved[7];
+    int32_t signed_push;        /* variant 0: one pass over both residual signs: 0/1 on (default), -1 the reference's two passes [DPPR_SIGNED_PUSH] */
+    int32_t reserved[6];
 } dppr_tuning;
 
 typedef struct dppr_engine dppr_engine;

@@ -16,14 +16,14 @@ MODES = [binding.ENGINE_LEVELSYNC, binding.ENGINE_STEPWISE]
 MODE_IDS = ["levelsync", "stepwise"]
 
 
-def _run_golden(path, variant, mode, hub_degree=0):
+def _run_golden(path, variant, mode, hub_degree=0, tuning=None):
     g = np.load(path)
     V, directed, edges = int(g["V"]), bool(g["directed"]), g["edges"]
     wl = golden_workload(g)
     eps = float(g["eps"])
     use_ref_p = not d2_possible(g)  # where the reference's D2 defect can fire its p is not a valid yardstick
     with DynamicPPR(V, directed, wl.W, wl.B, [int(g["source"])], epsilon=eps, variant=variant, engine_mode=mode,
-                    hub_degree=hub_degree) as eng:
+                    hub_degree=hub_degree, tuning=tuning) as eng:
         eng.init_window_pairs(edges[: wl.W])
         eng.solve_initial()
         for k in range(int(g["n_snap"])):
@@ -46,6 +46,14 @@ def _run_golden(path, variant, mode, hub_degree=0):
 @pytest.mark.parametrize("path", GOLDEN, ids=GOLDEN_IDS)
 def test_golden_window_bit_exact_and_estimates_within_2eps(path, variant, mode):
     _run_golden(path, variant, mode)
+
+
+@pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
+@pytest.mark.parametrize("path", GOLDEN, ids=GOLDEN_IDS)
+def test_golden_variant0_with_the_reference_two_pass_structure(path, mode):
+    """variant 0 pushes both residual signs in one pass by default (push.cuh); tuning.signed_push = -1 keeps the
+    reference's positive pass followed by a negative pass -- same contract either way"""
+    _run_golden(path, 0, mode, tuning={"signed_push": -1})
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3])
