@@ -395,7 +395,7 @@ template <int VAR>
 __device__ void expand_hubs(const PushArgs &a, PushSmem &sm, const HubItem *hin, unsigned long long hpk,
                             unsigned long long *qout, unsigned int *cnt_out, int phase, int level,
                             unsigned long long &edges_acc) {
-    const uint32_t nh = (uint32_t)(hpk >> 32), nchunks = (uint32_t)hpk;
+    const uint32_t nh = min((uint32_t)(hpk >> 32), a.hcap), nchunks = (uint32_t)hpk;  // (beyond hcap: dropped, kErrHubQ raised)
     if (nh == 0) return;
     const bool cached = nh <= (uint32_t)kHubSmem;
     if (cached) {
@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, DENSE == 8 ? DPPR_DENSE8_MIN_BLOCKS 
             unsigned long long dense_hpk = 0;
             float dense_rate = 0.f;
             while (true) {
-                const uint32_t n = __ldcg(&c->cnt[it % 3]);
+                const uint32_t n = min(__ldcg(&c->cnt[it % 3]), a.qcap);  // (beyond qcap the writers dropped items and raised kErrQueue)
                 const unsigned long long hpk = __ldcg(&c->hpk[(it + 2) % 3]);
                 // (slot it & 1 was written two iterations ago: the other slot may be being rewritten right now)
                 const float rate = DENSE ? __ldcg(&c->rate_ns[it & 1]) : 0.f, sw = DENSE ? __ldcg(&c->sweep_ns) : 0.f;
@@ -871,7 +871,7 @@ __global__ void __launch_bounds__(kThreads) push_step_expand(const PushArgs a, u
     if (threadIdx.x == 0) { sm.stage_cnt = 0; sm.abort_flag = 0; }
     __syncthreads();
     PushCtrl *c = a.ctrl;
-    const uint32_t n = c->cnt[it % 3];
+    const uint32_t n = min(c->cnt[it % 3], a.qcap);
     const unsigned long long hpk = c->hpk[(it + 2) % 3];
     const uint32_t nh = (uint32_t)(hpk >> 32);
     unsigned long long edges_acc = 0, carried_acc = 0;
