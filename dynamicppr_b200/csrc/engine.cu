@@ -273,13 +273,12 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     // state
     p_.alloc((size_t)V_ * Sr_);
     r_.alloc((size_t)V_ * Sr_);
-    if (cfg_.variant >= DPPR_EAGER) status_.alloc((size_t)V_ * Sr_);
+    // level stamps: the frontier dedupe of variants 2, 3 -- and of variant 0's signed pass (push.cuh)
+    if (cfg_.variant >= DPPR_EAGER || (cfg_.variant == DPPR_OPTIMIZED && tn_.signed_push >= 0)) status_.alloc((size_t)V_ * Sr_);
     src_.alloc((size_t)S_);
     DPPR_CUDA(cudaMemcpyAsync(src_.ptr, sources_.data(), sizeof(int32_t) * S_, cudaMemcpyHostToDevice, st_));
-    // push queues: a frontier of variants 1-3 holds each (source, vertex) at most once; variant 0's signed pass may enqueue a
-    // pair again after its residual was pulled back inside the band and left it once more (the twin pops an exact zero),
-    // hence twice the pairs.  Large frontiers never reach the queues of the switching kernels (they run as sweeps, push.cuh).
-    int64_t qc = cfg_.frontier_capacity > 0 ? cfg_.frontier_capacity : std::min<int64_t>(2 * (int64_t)V_ * S_ + 1024, (int64_t)1 << 29);
+    // push queues: a frontier holds each (source, vertex) at most once
+    int64_t qc = cfg_.frontier_capacity > 0 ? cfg_.frontier_capacity : std::min<int64_t>((int64_t)V_ * S_, (int64_t)1 << 29);
     qc = std::max<int64_t>(qc, 1024);
     if (qc > 0xfffffff0ll) qc = 0xfffffff0ll;
     qcap_ = (uint32_t)qc;

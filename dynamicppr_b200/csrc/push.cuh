@@ -289,6 +289,9 @@ __device__ __forceinline__ void push_edges(const PushArgs &a, PushSmem &sm, cons
             const double cur = old[k] + add[k];
             if (VAR == 0 || VAR == 1) {  // threshold crossing, gpu/ExpandRev.cuh:75
                 want = !legal_push(old[k], phase, a.eps) && legal_push(cur, phase, a.eps);
+                // variant 0's signed pass: mixed-sign adds can carry a residual out of the band, back in and out again within
+                // one iteration -- only the first crossing of a level enqueues (one extra exchange per CROSSING, not per edge)
+                if (VAR == 0 && want && phase == kSignedPhase) want = atomicExch(&a.status[(unsigned long long)nbr[k] * a.Sr + ow.s(k)], level) < level;
             } else if (legal_push(cur, phase, a.eps)) {  // status stamp, gpu/ExpandRev.cuh:254-257
                 want = atomicExch(&a.status[(unsigned long long)nbr[k] * a.Sr + ow.s(k)], level) < level;
             }
@@ -684,9 +687,9 @@ __global__ void __launch_bounds__(kThreads, DENSE == 8 ? DPPR_DENSE8_MIN_BLOCKS 
     // (qalt): they seed the next phase, and further phases run while an episode keeps leaving some (normally none do).
     //
     // Variant 0 pushes both signs in ONE pass (a.signed_push): its frontier is deduped by the threshold crossing
-    // |old| <= eps < |old + add| and popped by an exchange that claims the whole residual, so mixed-sign adds are harmless --
-    // a vertex that leaves the band, is pulled back and leaves again is enqueued twice, and its second pop finds an exact
-    // zero.  The two passes of the reference each have their own ramp-up and tail of tiny iterations, and residuals of
+    // |old| <= eps < |old + add| and popped by an exchange that claims the whole residual, so mixed-sign adds are harmless;
+    // a residual that leaves the band, is pulled back and leaves again within one iteration is kept from being enqueued
+    // twice by a per-level stamp.  The two passes of the reference each have their own ramp-up and tail of tiny iterations, and residuals of
     // opposite sign cancel instead of being pushed separately: about half the iterations on the L2-resident configs, where an
     // iteration costs a fixed ~6 us of dependent round trips.  Variants 1-3 keep the reference's two passes.
     const bool signed_mode = VAR == 0 && a.signed_push && !a.init_mode;
