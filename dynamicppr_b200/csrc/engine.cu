@@ -277,8 +277,11 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     if (cfg_.variant >= DPPR_EAGER || (cfg_.variant == DPPR_OPTIMIZED && tn_.signed_push >= 0)) status_.alloc((size_t)V_ * Sr_);
     src_.alloc((size_t)S_);
     DPPR_CUDA(cudaMemcpyAsync(src_.ptr, sources_.data(), sizeof(int32_t) * S_, cudaMemcpyHostToDevice, st_));
-    // push queues: a frontier holds each (source, vertex) at most once
-    int64_t qc = cfg_.frontier_capacity > 0 ? cfg_.frontier_capacity : std::min<int64_t>((int64_t)V_ * S_, (int64_t)1 << 29);
+    // push queues: a frontier holds each (source, vertex) at most once -- twice in variant 0's signed pass (push_edges), plus
+    // what the CTAs hold staged while the stamping starts
+    const bool signed0 = cfg_.variant == DPPR_OPTIMIZED && tn_.signed_push >= 0;
+    int64_t qc = cfg_.frontier_capacity > 0 ? cfg_.frontier_capacity
+                                            : std::min<int64_t>((int64_t)V_ * S_ * (signed0 ? 2 : 1) + (signed0 ? (1 << 20) : 0), (int64_t)1 << 29);
     qc = std::max<int64_t>(qc, 1024);
     if (qc > 0xfffffff0ll) qc = 0xfffffff0ll;
     qcap_ = (uint32_t)qc;

@@ -181,6 +181,7 @@ struct PushSmem {
     unsigned long long pl_edges;
     uint32_t bar_units;          // grid-wide total reported at the last grid barrier
     int abort_flag;
+    int dedupe;                  // signed pass: the next frontier is past half the queue -- stamp crossings from now on
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -290,8 +291,12 @@ __device__ __forceinline__ void push_edges(const PushArgs &a, PushSmem &sm, cons
             if (VAR == 0 || VAR == 1) {  // threshold crossing, gpu/ExpandRev.cuh:75
                 want = !legal_push(old[k], phase, a.eps) && legal_push(cur, phase, a.eps);
                 // variant 0's signed pass: mixed-sign adds can carry a residual out of the band, back in and out again within
-                // one iteration -- only the first crossing of a level enqueues (one extra exchange per CROSSING, not per edge)
-                if (VAR == 0 && want && phase == kSignedPhase) want = atomicExch(&a.status[(unsigned long long)nbr[k] * a.Sr + ow.s(k)], level) < level;
+                // one iteration.  The twin is harmless (its pop finds an exact zero) but takes a queue slot, and nothing bounds
+                // the number of re-crossings: once the next frontier is past half the queue, a crossing only enqueues if it is the
+                // first one stamped at this level.  (Stamping every crossing costs one more dependent atomic per pop: +17 % on
+                // BASELINE configs[1].)  At most one unstamped + one stamped entry per pair: the queue holds twice the pairs.
+                if (VAR == 0 && want && phase == kSignedPhase && sm.dedupe)
+                    want = atomicExch(&a.status[(unsigned long long)nbr[k] * a.Sr + ow.s(k)], level) < level;
             } else if (legal_push(cur, phase, a.eps)) {  // status stamp, gpu/ExpandRev.cuh:254-257
                 want = atomicExch(&a.status[(unsigned long long)nbr[k] * a.Sr + ow.s(k)], level) < level;
             }
@@ -406,6 +411,8 @@ __device__ void expand_hubs(const PushArgs &a, PushSmem &sm, const HubItem *hin,
         __syncthreads();
     }
     for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        if (threadIdx.x == 0) sm.dedupe = __ldcg(cnt_out) > a.qcap / 2;
+        __syncthreads();
         uint32_t lo = 0, hi = nh;  // last hub with chunk0 <= c
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
@@ -460,6 +467,7 @@ __device__ void expand_tiles(const PushArgs &a, PushSmem &sm, const unsigned lon
     const uint32_t ipt = (tile_items + kThreads - 1) / kThreads;  // 1..kItemsPerThread
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t tbase = tile * tile_items;
+        if (threadIdx.x == 0) sm.dedupe = __ldcg(cnt_out) > a.qcap / 2;  // (published by the barrier that follows the pops)
         // ---- pop: stage 1 items, stage 2 ring metadata + residual claim, stage 3 estimate update ----
         unsigned long long item[kItemsPerThread];
         bool have[kItemsPerThread], carry[kItemsPerThread];
