@@ -119,8 +119,12 @@ def sample_sources(sources, n):
     return [int(sources[((2 * i + 1) * S) // (2 * n)]) for i in range(n)]
 
 
+CPU_DEADLINE_S = 900.0
+
+
 def run_reference_cpu(cfg, sources, n_batches, threads, drop, variant):
-    """Returns per-(source, batch) times of the reference CPU classes on the same stream, or None if the binary is absent."""
+    """Returns per-(source, batch) times of the reference CPU classes on the same stream, or None if the binary is absent.
+    The run is cut at CPU_DEADLINE_S; whatever batches it had timed by then are the sample (none: a lower bound is reported)."""
     from dynamicppr_b200 import workloads
     harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness_omp")
     if not os.path.exists(harness):
@@ -139,10 +143,21 @@ def run_reference_cpu(cfg, sources, n_batches, threads, drop, variant):
         # window before each batch (untimed there, as the reference's own -DVALIDATE build does) so both arms work on the same graph
         cmd.append("--scratch-graph")
     t0 = time.time()
-    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    cut = False
+    try:
+        subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=CPU_DEADLINE_S)
+    except subprocess.TimeoutExpired:
+        cut = True
     wall = time.time() - t0
-    rows = [ln.split() for ln in open(tfile)]
-    os.remove(tfile)
+    rows = [ln.split() for ln in open(tfile)] if os.path.exists(tfile) else []
+    rows = [r for r in rows if len(r) == 4]
+    if os.path.exists(tfile):
+        os.remove(tfile)
+    if not any(int(r[0]) > drop for r in rows):
+        # nothing timed before the deadline: report the bound the deadline gives
+        init = [float(r[1]) for r in rows if int(r[0]) == 0]
+        return dict(kind="reference", s_per_source_batch=float(wall), p50_ms=float(wall * 1e3), steps=0, sources=len(sources), wall_s=wall,
+                    bin_s=t_bin, init_solve_s=float(np.mean(init) / 1e6) if init else float("nan"), cut=True, bound=True)
     us = np.array([float(r[1]) for r in rows if int(r[0]) > drop])  # batch 0 = initial solve
     init_us = np.array([float(r[1]) for r in rows if int(r[0]) == 0])
     per_batch = {}
@@ -151,7 +166,8 @@ def run_reference_cpu(cfg, sources, n_batches, threads, drop, variant):
             per_batch.setdefault(int(r[0]), []).append(float(r[1]))
     step_ms = np.array([np.mean(v) for _, v in sorted(per_batch.items())]) / 1e3  # mean over the sampled sources, per batch
     return dict(kind="reference", s_per_source_batch=float(us.mean() / 1e6), p50_ms=float(np.median(step_ms)), steps=len(step_ms),
-                sources=len(sources), wall_s=wall, bin_s=t_bin, init_solve_s=float(init_us.mean() / 1e6))
+                sources=len(sources), wall_s=wall, bin_s=t_bin, init_solve_s=float(init_us.mean() / 1e6) if len(init_us) else float("nan"),
+                cut=cut, bound=False)
 
 
 def run_port_cpu(cfg, sources, n_batches, drop, variant):
@@ -185,6 +201,10 @@ def cpu_arm(cfg, job_sources, n_cpu_sources, n_batches, drop, variant, ncores):
               f"the other with all threads each; ")
     sample += ("unmodified reference cpu/ classes (oracle/_ref/ref_harness_omp), cilk_for backed by OpenMP" if res["kind"] == "reference"
                else "single-threaded C restatement of the reference (oracle/dppr_oracle.c)")
+    if res.get("bound"):
+        sample += f"; NO slide finished within the {CPU_DEADLINE_S:.0f} s deadline: the value is an UPPER bound (1 / elapsed seconds)"
+    elif res.get("cut"):
+        sample += f"; cut at the {CPU_DEADLINE_S:.0f} s deadline, the batches timed until then are the sample"
     if res["kind"] == "reference" and not cfg.directed:
         sample += "; true window rebuilt (untimed) before each batch because the reference's incremental adjacency is wrong on undirected streams (DESIGN.md D1)"
     return res, sb_per_s, sample, picked
@@ -208,7 +228,9 @@ def main():
     ap.add_argument("--cpu-batches", type=int, default=3, help="timed batches of the in-line cpu_baseline (the reference arm uses --steps)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end loop (default: --steps, or 5 when a step exceeds 0.2 s)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-deadline", type=float, default=CPU_DEADLINE_S, help="seconds after which the CPU arm is cut")
     a = ap.parse_args()
+    globals()["CPU_DEADLINE_S"] = a.cpu_deadline
     a.warmup = max(a.warmup, 3)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -338,6 +360,7 @@ def main():
         if st.error_flags:
             raise SystemExit(f"device error flags {st.error_flags}: results invalid")
     e2e_ms_per_step = float(np.mean(e2e_t)) * 1e3
+    log("e2e ms per step: " + " ".join(f"{t * 1e3:.2f}" for t in e2e_t[:12]))
     assert ids.shape == (len(my_sources), TOPK) and np.all(vals[:, 0] > 0)
 
     # ---- max over ranks; the job's only data collective (after the timed region): top-k digests of every source and

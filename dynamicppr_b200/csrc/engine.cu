@@ -1092,25 +1092,60 @@ void Engine::topk(int32_t first, int32_t n, int32_t k, int32_t *ids, double *val
     if (k < 1 || k > kTopKMax) throw InvalidArgument("k must be in [1, 128]");
     if (!solved_) throw StateError("no estimates before dppr_solve_initial");
     DPPR_CUDA(cudaSetDevice(dev_));
-    const int slices = div_up(V_, kTopSlice);
-    const size_t need = (size_t)n * slices * k, outn = (size_t)n * k;
-    if (topk_key_.count < need) { topk_key_.alloc(need); topk_id_.alloc(need); }
+    const size_t outn = (size_t)n * k;
     if (topk_out_ids_.count < outn) {
         topk_out_ids_.alloc(outn); topk_out_vals_.alloc(outn);
         topk_host_ids_.alloc(outn); topk_host_vals_.alloc(outn);
     }
-    for (int32_t lo = 0; lo < n; lo += 32768) {  // (grid.y limit)
-        const int32_t m = std::min<int32_t>(32768, n - lo);
-        topk_partial<<<dim3((unsigned)slices, (unsigned)m), kThreads, 0, st_>>>(p_.ptr, Sr_, V_, first + lo, inv_.ptr, k,
-                                                                              topk_key_.ptr + (size_t)lo * slices * k,
-                                                                              topk_id_.ptr + (size_t)lo * slices * k); ++launch_counter();
+    if (!topk_prevk_.ptr) {  // per-engine state of the fast path (topk.cuh)
+        topk_prev_.alloc((size_t)S_ * kTopKMax); topk_prevk_.alloc(S_); topk_bound_.alloc(S_); topk_count_.alloc(S_);
+        topk_over_.alloc(S_); topk_host_over_.alloc(S_);
+        topk_ckey_.alloc((size_t)S_ * kTopCand); topk_cid_.alloc((size_t)S_ * kTopCand);
+        DPPR_CUDA(cudaMemsetAsync(topk_prevk_.ptr, 0, topk_prevk_.bytes(), st_));
+        DPPR_CUDA(cudaMemsetAsync(topk_count_.ptr, 0, topk_count_.bytes(), st_));
     }
-    topk_merge<<<(unsigned)n, kThreads, 0, st_>>>(topk_key_.ptr, topk_id_.ptr, slices, k, topk_out_ids_.ptr, topk_out_vals_.ptr); ++launch_counter();
+    topk_threshold<<<(unsigned)n, kThreads, 0, st_>>>(p_.ptr, Sr_, V_, first, k, topk_prev_.ptr, topk_prevk_.ptr, topk_bound_.ptr); ++launch_counter();
+    const int64_t rows_per_warp = Sr_ < 32 ? 32 / Sr_ : 1;
+    const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(div_up((int64_t)V_, rows_per_warp), (int64_t)(kThreads / 32)), (int64_t)sm_count_ * 32));
+    bool open_sources = true;
+    for (int round = 0; round < 3 && open_sources; ++round) {
+        topk_filter<<<fgrid, kThreads, 0, st_>>>(p_.ptr, Sr_, V_, first, n, inv_.ptr, topk_bound_.ptr, topk_ckey_.ptr, topk_cid_.ptr, topk_count_.ptr,
+                                                 round ? topk_over_.ptr : nullptr); ++launch_counter();
+        topk_merge<<<(unsigned)n, kThreads, 0, st_>>>(topk_ckey_.ptr, topk_cid_.ptr, kTopCand, 0, topk_count_.ptr, k, topk_out_ids_.ptr, topk_out_vals_.ptr,
+                                                     perm_.ptr, topk_prev_.ptr + (size_t)first * kTopKMax, topk_prevk_.ptr + first, topk_over_.ptr,
+                                                     round > 0, topk_bound_.ptr); ++launch_counter();
+        DPPR_CUDA(cudaGetLastError());
+        DPPR_CUDA(cudaMemcpyAsync(topk_host_over_.ptr, topk_over_.ptr, sizeof(int) * n, cudaMemcpyDeviceToHost, st_));
+        if (round == 0) {  // (the common case ends here: one synchronisation for flags and results)
+            DPPR_CUDA(cudaMemcpyAsync(topk_host_ids_.ptr, topk_out_ids_.ptr, sizeof(int32_t) * outn, cudaMemcpyDeviceToHost, st_));
+            DPPR_CUDA(cudaMemcpyAsync(topk_host_vals_.ptr, topk_out_vals_.ptr, sizeof(double) * outn, cudaMemcpyDeviceToHost, st_));
+        }
+        DPPR_CUDA(cudaStreamSynchronize(st_));
+        open_sources = false;
+        for (int32_t i = 0; i < n; ++i) open_sources = open_sources || topk_host_over_.ptr[i] != 0;
+        if (open_sources && env_int("DPPR_DEBUG", 0)) {
+            int cnt = 0, mx = 0;
+            for (int32_t i = 0; i < n; ++i) { cnt += topk_host_over_.ptr[i] != 0; mx = std::max(mx, topk_host_over_.ptr[i]); }
+            std::fprintf(stderr, "[dppr] top-k round %d: %d of %d sources over the candidate capacity (largest list %d)\n", round, cnt, n, mx);
+        }
+        if (round == 0 && !open_sources) { check_health(); std::memcpy(ids, topk_host_ids_.ptr, sizeof(int32_t) * outn); std::memcpy(values, topk_host_vals_.ptr, sizeof(double) * outn); return; }
+    }
+    check_health();
+    // sources three rounds did not settle (a flat vector: the bound cannot rise past a tie): the exact scan
+    for (int32_t i = 0; i < n && open_sources; ++i) {
+        if (!topk_host_over_.ptr[i]) continue;
+        const int slices = div_up(V_, kTopSlice);
+        const size_t need = (size_t)slices * k;
+        if (topk_key_.count < need) { topk_key_.alloc(need); topk_id_.alloc(need); }
+        topk_partial<<<dim3((unsigned)slices, 1u), kThreads, 0, st_>>>(p_.ptr, Sr_, V_, first + i, inv_.ptr, k, topk_key_.ptr, topk_id_.ptr); ++launch_counter();
+        topk_merge<<<1, kThreads, 0, st_>>>(topk_key_.ptr, topk_id_.ptr, (int64_t)need, (int64_t)need, nullptr, k, topk_out_ids_.ptr + (size_t)i * k,
+                                           topk_out_vals_.ptr + (size_t)i * k, perm_.ptr, topk_prev_.ptr + (size_t)(first + i) * kTopKMax,
+                                           topk_prevk_.ptr + first + i, nullptr, 0, nullptr); ++launch_counter();
+    }
     DPPR_CUDA(cudaGetLastError());
     DPPR_CUDA(cudaMemcpyAsync(topk_host_ids_.ptr, topk_out_ids_.ptr, sizeof(int32_t) * outn, cudaMemcpyDeviceToHost, st_));
     DPPR_CUDA(cudaMemcpyAsync(topk_host_vals_.ptr, topk_out_vals_.ptr, sizeof(double) * outn, cudaMemcpyDeviceToHost, st_));
     DPPR_CUDA(cudaStreamSynchronize(st_));
-    check_health();
     std::memcpy(ids, topk_host_ids_.ptr, sizeof(int32_t) * outn);
     std::memcpy(values, topk_host_vals_.ptr, sizeof(double) * outn);
 }

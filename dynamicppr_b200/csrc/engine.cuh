@@ -188,6 +188,11 @@ private:
     DevBuf<double> topk_out_vals_;
     PinnedBuf<int32_t> topk_host_ids_;
     PinnedBuf<double> topk_host_vals_;
+    DevBuf<uint32_t> topk_prev_, topk_cid_;       // fast path: previous winners (internal ids), candidate ids
+    DevBuf<int> topk_prevk_, topk_over_;
+    DevBuf<unsigned long long> topk_bound_, topk_ckey_;
+    DevBuf<unsigned int> topk_count_;
+    PinnedBuf<int> topk_host_over_;
     // host staging
     static constexpr int kStageSlots = 4;
     PinnedBuf<int2> hstage_[kStageSlots];

@@ -58,6 +58,56 @@ def test_topk_with_fewer_vertices_than_k_and_ties():
         assert (p == 0).sum() > 2            # many exact ties at zero, ordered by id
 
 
+def _topk_expected(p, k):
+    return np.lexsort((np.arange(len(p)), -p))[:k]
+
+
+@pytest.mark.parametrize("n_sources", [1, 5, 40])
+def test_topk_bound_from_previous_winners_stays_exact_across_slides(n_sources):
+    # the fast path bounds the candidates by the previous call's winners (topk.cuh): slide, ask again with another k,
+    # ask for a sub-range, and compare every answer with a full sort of the exported vector
+    cfg = workloads.scaled(workloads.CONFIGS[4], 0.004)
+    srcs = workloads.top_sources(cfg, n_sources, on_host=True)
+    eng, edges, wl = _engine_on(cfg, srcs, 1)
+    with eng:
+        more = workloads.host_edges(cfg, wl.W + wl.B, 6 * wl.B)
+        for step, k in enumerate((16, 16, 64, 8, 128, 16)):
+            ids, vals = eng.topk(k)
+            for i in range(0, n_sources, max(1, n_sources // 5)):
+                p = eng.estimates(i)
+                order = _topk_expected(p, k)
+                np.testing.assert_array_equal(ids[i], order)
+                np.testing.assert_array_equal(vals[i], p[order])
+            if n_sources > 2:
+                ids, vals = eng.topk(k, first_source=1, n_sources=2)
+                np.testing.assert_array_equal(ids[1], _topk_expected(eng.estimates(2), k))
+            eng.slide_pairs(more[step * wl.B:(step + 1) * wl.B])
+        # a state the previous winners say nothing about: the bound is merely loose or, if it admits too many, the exact scan runs
+        p = np.zeros(cfg.V); r = np.zeros(cfg.V)
+        p[::3] = 1e-3; p[5] = 0.5
+        eng.set_state(0, p, r)
+        ids, vals = eng.topk(32, first_source=0, n_sources=1)
+        np.testing.assert_array_equal(ids[0], _topk_expected(p, 32))
+        np.testing.assert_array_equal(vals[0], p[ids[0]])
+
+
+def test_topk_first_call_on_a_flat_vector_falls_back_to_the_exact_scan():
+    # no edges touch most vertices: every estimate but a few is exactly 0, the first-call bound is 0 and admits all V
+    # candidates (> kTopCand): the flagged source is redone by the exact scan, ties ordered by caller id
+    V = 20000
+    edges = np.array([[i % 50, (i * 7 + 1) % 50] for i in range(400)], dtype=np.int32)
+    with DynamicPPR(V, True, 200, 10, [3, 4]) as eng:
+        eng.init_window_pairs(edges[:200])
+        eng.solve_initial()
+        for _ in range(2):
+            ids, vals = eng.topk(100)
+            for i in range(2):
+                p = eng.estimates(i)
+                np.testing.assert_array_equal(ids[i], _topk_expected(p, 100))
+                np.testing.assert_array_equal(vals[i], p[ids[i]])
+            assert (vals[0] == 0).sum() > 40
+
+
 @pytest.mark.parametrize("directed", [True, False])
 def test_device_validation_agrees_with_host_checks(directed):
     cfg = workloads.scaled(workloads.CONFIGS[3 if directed else 4], 0.003)
