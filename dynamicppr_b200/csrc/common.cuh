@@ -106,7 +106,7 @@ __device__ __forceinline__ T warp_inclusive_sum(T x) {
 }
 
 // CTA-wide exclusive scan of one value per thread (kThreads threads); every thread gets its
-// exclusive prefix, `total` the CTA sum.  `smem` needs kWarps + 1 elements.  Two barriers.
+// exclusive prefix, `total` the CTA sum.  `smem` needs kWarps + 1 elements.  Three barriers (the last one frees smem).
 template <typename T>
 __device__ __forceinline__ T block_exclusive_sum(T x, T *smem, T &total) {
     T inc = warp_inclusive_sum(x);
