@@ -9,20 +9,29 @@ namespace dppr {
 
 namespace {
 
-__global__ void gather_record(BatchRecord *rec, const PushCtrl *ctrl, const uint32_t *counters,
+// `st`: where the refresh's counters are -- the control block itself, or the sum over source panels
+__global__ void gather_record(BatchRecord *rec, const PushCtrl *ctrl, const PushCtrl *st, const uint32_t *counters,
                               const unsigned long long *pool_top) {
     BatchRecord r{};
-    r.iters = ctrl->iters; r.pops = ctrl->pops; r.edges = ctrl->edges; r.gath = ctrl->gath;
-    r.hubs = ctrl->hubs; r.carried = ctrl->carried; r.dpops = ctrl->dpops;
-    r.walk_slots = ctrl->walk_slots; r.walk_pairs = ctrl->walk_pairs; r.units = ctrl->units;
+    r.iters = st->iters; r.pops = st->pops; r.edges = st->edges; r.gath = st->gath;
+    r.hubs = st->hubs; r.carried = st->carried; r.dpops = st->dpops;
+    r.walk_slots = st->walk_slots; r.walk_pairs = st->walk_pairs; r.units = st->units;
     r.pool_top = pool_top[0]; r.pool_leaked = pool_top[1];
-    r.sweeps = ctrl->sweeps;
+    r.sweeps = st->sweeps;
     r.nseg_in = counters[0];
     r.nseg_out = counters[1];
     r.njobs = counters[2] + counters[5];
     r.errflags = ctrl->errflags;
     r.arrived = 1;
     *rec = r;
+}
+
+// a panel's refresh is done: add its counters to the running sums
+__global__ void accumulate_ctrl(PushCtrl *acc, const PushCtrl *ctrl) {
+    acc->iters += ctrl->iters; acc->pops += ctrl->pops; acc->edges += ctrl->edges; acc->gath += ctrl->gath;
+    acc->hubs += ctrl->hubs; acc->carried += ctrl->carried; acc->dpops += ctrl->dpops;
+    acc->walk_slots += ctrl->walk_slots; acc->walk_pairs += ctrl->walk_pairs; acc->units += ctrl->units;
+    acc->sweeps += ctrl->sweeps;
 }
 
 __global__ void fold_window_errors(PushCtrl *ctrl, int *win_err) {
@@ -74,6 +83,7 @@ Tuning resolve_tuning(const dppr_tuning &t) {
     else if (t.window_path == 0 && !env_int("DPPR_FUSED_WINDOW", 1)) r.window_path = 2;
     r.iterlog = pick_int(t.iterlog, "DPPR_ITERLOG", 0) > 0;
     r.probe_iter = pick_int(t.probe_iter, "DPPR_PROBE_ITER", 10);
+    r.panel_sources = std::max(1, pick_int(t.panel_sources, "DPPR_PANEL_SOURCES", 128));
     return r;
 }
 
@@ -129,7 +139,10 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     Bmax_ = cfg.max_batch_edges;
     Nb_ = std::max<int64_t>(2 * D_ * Bmax_, 1);
     S_ = cfg.n_sources;
-    Sr_ = S_ == 1 ? 1 : ((int64_t)S_ + 7) / 8 * 8;
+    n_panels_ = div_up(S_, tn_.panel_sources);
+    Pw_ = div_up(S_, n_panels_);  // (equal panels: 1000 sources -> 8 x 125, not 7 x 128 + 104)
+    Sr_ = Pw_ == 1 ? 1 : ((int64_t)Pw_ + 7) / 8 * 8;
+    panel_stride_ = (int64_t)cfg.vertex_count * Sr_;
     sources_.assign(cfg.sources, cfg.sources + S_);
     cfg_.sources = sources_.data();
     for (int32_t s : sources_)
@@ -148,17 +161,17 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
         // (vertex, source) once, so the episodes are the same for all of them -- round-1 verdict, item 7)
         const bool can = mode_ == DPPR_ENGINE_LEVELSYNC && tn_.dense_div > 0.0;
         dense_ = can && tn_.dense >= 0 &&
-                 (tn_.dense > 0 || (double)cfg.window_edges * (cfg.directed ? 1 : 2) * cfg.n_sources >= tn_.dense_min_edges);
+                 (tn_.dense > 0 || (double)cfg.window_edges * (cfg.directed ? 1 : 2) * Pw_ >= tn_.dense_min_edges);
         outlists_ = dense_ && D_ == 1;
         // several sources: a lane takes 8 sources (16 bytes of an x row), G = 2^gshift adjacent lanes share a vertex (pull.cuh)
         pull_gshift_ = 0;
-        if (S_ > 1) {
+        if (Pw_ > 1) {
             const int chunks = (int)(Sr_ / 8);
             while ((1 << pull_gshift_) < std::min(chunks, tn_.pull_group) && pull_gshift_ < 4) ++pull_gshift_;  // (<= 16 lanes: 128 accumulator columns)
         }
         // out-lists of big_min or more entries are cut into chunks any warp of the grid takes: a warp streams a list at
         // kPullUnroll rows per memory round trip, so the wider the rows (the fewer vertices a warp holds) the shorter the chunks
-        pull_big_min_ = tn_.pull_big_min > 0 ? tn_.pull_big_min : (S_ == 1 ? 4096 : 1024);
+        pull_big_min_ = tn_.pull_big_min > 0 ? tn_.pull_big_min : (Pw_ == 1 ? 4096 : 1024);
         pull_big_min_ = std::max(pull_big_min_, tn_.pull_warp_min);
         pull_big_chunk_ = tn_.pull_big_chunk > 0 ? tn_.pull_big_chunk : std::max(32, pull_big_min_ / 4);
     }
@@ -177,7 +190,7 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     DPPR_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
 
     // cooperative grid per variant: every CTA must be co-resident for the software grid barrier
-    const int dense_kind = dense_ ? (S_ == 1 ? 1 : 8) : 0;
+    const int dense_kind = dense_ ? (Pw_ == 1 ? 1 : 8) : 0;
     void *kern[4] = {persistent_kernel(0, cfg_.variant == 0 ? dense_kind : 0), persistent_kernel(1, cfg_.variant == 1 ? dense_kind : 0),
                      persistent_kernel(2, cfg_.variant == 2 ? dense_kind : 0), persistent_kernel(3, cfg_.variant == 3 ? dense_kind : 0)};
     // the switching kernels keep the relaxation factor of an accelerated sweep in (dynamic) shared memory (pull.cuh)
@@ -254,10 +267,10 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     if (outlists_) { ins_posB_.alloc((size_t)Nb_); jobsB_.alloc((size_t)Nb_); }
     if (dense_) {
         for (int i = 0; i < 2; ++i) {
-            x_[i].alloc((size_t)V_ * Sr_ + 8);
+            x_[i].alloc((size_t)n_panels_ * panel_stride_ + 8);
             DPPR_CUDA(cudaMemsetAsync(x_[i].ptr, 0, x_[i].bytes(), st_));
         }
-        const int lanes_sources = S_ == 1 ? 1 : 8 << pull_gshift_;                 // sources one pass over a vertex covers
+        const int lanes_sources = Pw_ == 1 ? 1 : 8 << pull_gshift_;                // sources one pass over a vertex covers
         const int n_cg = (int)((Sr_ + lanes_sources - 1) / lanes_sources);          // chunk groups
         tile_cap_ = (uint32_t)div_up(V_, kThreads >> pull_gshift_) * (uint32_t)n_cg;
         tile_list_.alloc((size_t)tile_cap_ * 3);
@@ -271,25 +284,26 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     DPPR_CUDA(cudaMemsetAsync(delta_.ptr, 0, delta_.bytes(), st_));
     DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, counters_.bytes(), st_));
     // state
-    p_.alloc((size_t)V_ * Sr_);
-    r_.alloc((size_t)V_ * Sr_);
+    p_.alloc((size_t)n_panels_ * panel_stride_);
+    r_.alloc((size_t)n_panels_ * panel_stride_);
+    if (n_panels_ > 1) ctrl_acc_.alloc(1);
     // level stamps: the frontier dedupe of variants 2, 3 -- and of variant 0's signed pass (push.cuh)
-    if (cfg_.variant >= DPPR_EAGER || (cfg_.variant == DPPR_OPTIMIZED && tn_.signed_push >= 0)) status_.alloc((size_t)V_ * Sr_);
+    if (cfg_.variant >= DPPR_EAGER || (cfg_.variant == DPPR_OPTIMIZED && tn_.signed_push >= 0)) status_.alloc((size_t)n_panels_ * panel_stride_);
     src_.alloc((size_t)S_);
     DPPR_CUDA(cudaMemcpyAsync(src_.ptr, sources_.data(), sizeof(int32_t) * S_, cudaMemcpyHostToDevice, st_));
     // push queues: a frontier holds each (source, vertex) at most once -- twice in variant 0's signed pass (push_edges), plus
     // what the CTAs hold staged while the stamping starts
     const bool signed0 = cfg_.variant == DPPR_OPTIMIZED && tn_.signed_push >= 0;
     int64_t qc = cfg_.frontier_capacity > 0 ? cfg_.frontier_capacity
-                                            : std::min<int64_t>((int64_t)V_ * S_ * (signed0 ? 2 : 1) + (signed0 ? (1 << 20) : 0), (int64_t)1 << 29);
+                                            : std::min<int64_t>((int64_t)V_ * Pw_ * (signed0 ? 2 : 1) + (signed0 ? (1 << 20) : 0), (int64_t)1 << 29);
     qc = std::max<int64_t>(qc, 1024);
     if (qc > 0xfffffff0ll) qc = 0xfffffff0ll;
     qcap_ = (uint32_t)qc;
     // hub list: one entry per popped (source, vertex) of in-degree >= hub_degree.  With the switching kernel the large
     // frontiers run as sweeps (hubs still pending at the switch are un-popped), so a quarter of the worst case is plenty;
     // overflow is detected (DPPR_DEVERR_HUBQ), never silent
-    int64_t hc = std::max<int64_t>(1024, (Ew_ / cfg_.hub_degree + 1) * S_);
-    if (dense_ && S_ > 8) hc = std::max<int64_t>(1 << 20, hc / 4);
+    int64_t hc = std::max<int64_t>(1024, (Ew_ / cfg_.hub_degree + 1) * Pw_);
+    if (dense_ && Pw_ > 8) hc = std::max<int64_t>(1 << 20, hc / 4);
     hcap_ = (uint32_t)std::min<int64_t>(qc, hc);
     for (int i = 0; i < 2; ++i) {
         q_[i].alloc(qcap_);
@@ -384,7 +398,7 @@ BatchRecord *Engine::record_slot(size_t k) {
 
 void Engine::finish_record() {
     fold_window_errors<<<1, 1, 0, st_>>>(ctrl_.ptr, (int *)(counters_.ptr + 3)); ++launch_counter();
-    gather_record<<<1, 1, 0, st_>>>(dev_record_.ptr, ctrl_.ptr, counters_.ptr, pool_top_.ptr); ++launch_counter();
+    gather_record<<<1, 1, 0, st_>>>(dev_record_.ptr, ctrl_.ptr, n_panels_ > 1 ? ctrl_acc_.ptr : ctrl_.ptr, counters_.ptr, pool_top_.ptr); ++launch_counter();
     DPPR_CUDA(cudaGetLastError());
     DPPR_CUDA(cudaMemcpyAsync(record_slot(meta_.size() - 1), dev_record_.ptr, sizeof(BatchRecord),
                               cudaMemcpyDeviceToHost, st_));
@@ -563,11 +577,23 @@ void Engine::build_initial_window() {
 // push launch
 // ---------------------------------------------------------------------------------------------
 void Engine::launch_push(bool init_mode) {
+    if (n_panels_ == 1) { launch_push_panel(init_mode, 0); return; }
+    DPPR_CUDA(cudaMemsetAsync(ctrl_acc_.ptr, 0, sizeof(PushCtrl), st_));
+    for (int k = 0; k < n_panels_; ++k) {
+        launch_push_panel(init_mode, k);
+        accumulate_ctrl<<<1, 1, 0, st_>>>(ctrl_acc_.ptr, ctrl_.ptr); ++launch_counter();
+    }
+}
+
+// the refresh of one source panel: its [V][Sr_] block of the state is the whole state as far as the kernels know
+void Engine::launch_push_panel(bool init_mode, int panel) {
     DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, kCtrlZeroBytes, st_));
+    const size_t pb = (size_t)panel * (size_t)panel_stride_;
+    const int Sk = panel_sources(panel);
     PushArgs a{};
     a.vmeta = vmeta_.ptr; a.pool = pool_.ptr; a.outdeg = outdeg_.ptr;
-    a.p = p_.ptr; a.r = r_.ptr; a.status = status_.ptr;
-    a.Sr = Sr_; a.S = S_; a.src = src_.ptr;
+    a.p = p_.ptr + pb; a.r = r_.ptr + pb; a.status = status_.ptr ? status_.ptr + pb : nullptr;
+    a.Sr = Sr_; a.S = Sk; a.src = src_.ptr + (size_t)panel * Pw_;
     for (int i = 0; i < 2; ++i) { a.q[i] = q_[i].ptr; a.qr[i] = qr_[i].ptr; a.hub[i] = hub_[i].ptr; }
     a.qalt = qalt_.ptr;
     a.qcap = qcap_; a.hcap = hcap_;
@@ -585,20 +611,20 @@ void Engine::launch_push(bool init_mode) {
     a.V = V_;
     a.avg_indeg = (float)((double)Ew_ / (double)V_);
     a.vmeta_out = outlists_ ? vmeta_out_.ptr : vmeta_.ptr;
-    a.x[0] = x_[0].ptr; a.x[1] = x_[1].ptr;
+    a.x[0] = x_[0].ptr ? x_[0].ptr + pb : nullptr; a.x[1] = x_[1].ptr ? x_[1].ptr + pb : nullptr;
     a.pull_gshift = pull_gshift_;
     // cost model: a sweep reads every out-list entry and every vertex row once, whatever the frontier; a scatter
     // iteration pays one random atomic per traversed in-edge.  Measured ratio ~ DPPR_DENSE_DIV (3): Twitter-shaped
     // 3.3 ms per sweep vs 17 edges/ns scattered; Orkut/4 97 us vs 40 edges/ns.
     a.dense_enter_edges = ~0ull;
-    if (dense_) a.dense_enter_edges = (unsigned long long)std::max(1.0, ((double)Ew_ + 2.0 * (double)V_) * (double)S_ / tn_.dense_div);
+    if (dense_) a.dense_enter_edges = (unsigned long long)std::max(1.0, ((double)Ew_ + 2.0 * (double)V_) * (double)Sk / tn_.dense_div);
     a.dense_exit_edges = a.dense_enter_edges / 2;
     a.pull_warp_min = tn_.pull_warp_min; a.pull_big_min = pull_big_min_; a.pull_big_chunk = pull_big_chunk_;
     a.big = big_.ptr; a.bigcap = bigcap_; a.bigacc = bigacc_.ptr; a.tile_list = tile_list_.ptr; a.tile_list_cap = tile_cap_;
     a.accel_frac = (D_ == 2 && tn_.dense_accel >= 0) ? tn_.accel_frac : 0.0;
     a.signed_push = tn_.signed_push >= 0 ? 1 : 0;
     {
-        const int lanes_sources = S_ == 1 ? 1 : 8 << pull_gshift_;
+        const int lanes_sources = Pw_ == 1 ? 1 : 8 << pull_gshift_;
         const uint64_t ntiles = (uint64_t)div_up(V_, kThreads >> pull_gshift_) * (uint64_t)((Sr_ + lanes_sources - 1) / lanes_sources);
         auto gcd = [](uint64_t x, uint64_t y) { while (y) { const uint64_t t = x % y; x = y; y = t; } return x; };
         uint64_t k = std::max<uint64_t>(1, (uint64_t)(0.6180339887 * (double)ntiles)) | 1ull;
@@ -615,7 +641,7 @@ void Engine::launch_push(bool init_mode) {
         return;
     }
     void *params[] = {(void *)&a};
-    void *kern = persistent_kernel(cfg_.variant, dense_ ? (S_ == 1 ? 1 : 8) : 0);
+    void *kern = persistent_kernel(cfg_.variant, dense_ ? (Pw_ == 1 ? 1 : 8) : 0);
     DPPR_CUDA(cudaLaunchCooperativeKernel(kern, dim3(coop_grid_[cfg_.variant]), dim3(kThreads), params, dyn_smem_, st_));
     ++launch_counter();
 }
@@ -685,7 +711,11 @@ void Engine::solve_initial() {
     batch_pending_ = false;
     begin_batch(0, 0);
     record(0);
-    state_init<<<grid_for((int64_t)V_ * Sr_), kThreads, 0, st_>>>(p_.ptr, r_.ptr, status_.ptr, V_, Sr_, S_, src_.ptr); ++launch_counter();
+    for (int k = 0; k < n_panels_; ++k) {
+        const size_t pb = (size_t)k * (size_t)panel_stride_;
+        state_init<<<grid_for(panel_stride_), kThreads, 0, st_>>>(p_.ptr + pb, r_.ptr + pb, status_.ptr ? status_.ptr + pb : nullptr, V_, Sr_,
+                                                                 panel_sources(k), src_.ptr + (size_t)k * Pw_); ++launch_counter();
+    }
     DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, sizeof(PushCtrl), st_));
     DPPR_CUDA(cudaMemsetAsync(counters_.ptr, 0, counters_.bytes(), st_));
     step_level_ = 0;
@@ -851,18 +881,25 @@ void Engine::refresh(bool repair_only) {
     if (!batch_pending_) throw StateError("dppr_refresh without a preceding dppr_apply_batch");
     DPPR_CUDA(cudaSetDevice(dev_));
     const int64_t n = cur().entries;
-    if (S_ == 1) {
-        repair_accumulate<<<std::min(grid_for(n), 8 * sm_count_), kThreads, 0, st_>>>(sb_val_, n, segB_.segof, p_.ptr, delta_.ptr); ++launch_counter();
-    } else {
-        dim3 g((unsigned)std::max(1, std::min(div_up(n, 32 * kWarps), 8 * sm_count_)), (unsigned)div_up(S_, 32 * kRepairCols));
-        repair_accumulate_rows<<<g, kThreads, 0, st_>>>(sb_val_, n, segB_.segof, p_.ptr, Sr_, S_, delta_.ptr); ++launch_counter();
+    for (int k = 0; k < n_panels_; ++k) {  // (delta_ is one panel wide: repair_finalize leaves it cleared for the next)
+        const size_t pb = (size_t)k * (size_t)panel_stride_;
+        const int Sk = panel_sources(k);
+        if (Pw_ == 1) {
+            repair_accumulate<<<std::min(grid_for(n), 8 * sm_count_), kThreads, 0, st_>>>(sb_val_, n, segB_.segof, p_.ptr + pb, delta_.ptr); ++launch_counter();
+        } else {
+            dim3 g((unsigned)std::max(1, std::min(div_up(n, 32 * kWarps), 8 * sm_count_)), (unsigned)div_up(Sk, 32 * kRepairCols));
+            repair_accumulate_rows<<<g, kThreads, 0, st_>>>(sb_val_, n, segB_.segof, p_.ptr + pb, Sr_, Sk, delta_.ptr); ++launch_counter();
+        }
+        repair_finalize<<<grid_for(n * Sk), kThreads, 0, st_>>>(segB_, seg_d0_.ptr, src_.ptr + (size_t)k * Pw_, Sk, Sr_, p_.ptr + pb, r_.ptr + pb,
+                                                              delta_.ptr, cfg_.alpha); ++launch_counter();
     }
-    repair_finalize<<<grid_for(n * S_), kThreads, 0, st_>>>(segB_, seg_d0_.ptr, src_.ptr, S_, Sr_, p_.ptr, r_.ptr, delta_.ptr,
-                                                          cfg_.alpha); ++launch_counter();
     DPPR_CUDA(cudaGetLastError());
     record(3);
     if (!repair_only) launch_push(false);
-    else DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, kCtrlZeroBytes, st_));
+    else {
+        DPPR_CUDA(cudaMemsetAsync(ctrl_.ptr, 0, kCtrlZeroBytes, st_));
+        if (n_panels_ > 1) DPPR_CUDA(cudaMemsetAsync(ctrl_acc_.ptr, 0, sizeof(PushCtrl), st_));
+    }
     record(4);
     finish_record();
     batch_pending_ = false;
@@ -925,7 +962,7 @@ void Engine::get_vector(int which, int32_t s, double *out) {
     if (s < 0 || s >= S_) throw InvalidArgument("source index out of range");
     if (!solved_) throw StateError("no estimates before dppr_solve_initial");
     sync();
-    const double *src = (which == 0 ? p_.ptr : r_.ptr) + s;  // vertex-major: element v of source s at v * Sr_ + s
+    const double *src = (which == 0 ? p_.ptr : r_.ptr) + elem_base(s);  // vertex-major inside the source's panel: element v at + v * Sr_
     if (!perm_.ptr && Sr_ == 1) {
         DPPR_CUDA(cudaMemcpy(out, src, sizeof(double) * (size_t)V_, cudaMemcpyDeviceToHost));
         return;
@@ -941,7 +978,7 @@ void Engine::copy_estimates_device(int32_t s, void *dptr) {
     if (!dptr) throw InvalidArgument("null device pointer");
     if (s < 0 || s >= S_) throw InvalidArgument("source index out of range");
     DPPR_CUDA(cudaSetDevice(dev_));
-    gather_by_perm<double><<<grid_for(V_), kThreads, 0, st_>>>(p_.ptr + s, Sr_, perm_.ptr, (double *)dptr, V_); ++launch_counter();
+    gather_by_perm<double><<<grid_for(V_), kThreads, 0, st_>>>(p_.ptr + elem_base(s), Sr_, perm_.ptr, (double *)dptr, V_); ++launch_counter();
     DPPR_CUDA(cudaStreamSynchronize(st_));
 }
 
@@ -953,7 +990,7 @@ void Engine::set_state(int32_t s, const double *p, const double *r) {
     for (int which = 0; which < 2; ++which) {
         const double *h = which == 0 ? p : r;
         if (!h) continue;
-        double *dst = (which == 0 ? p_.ptr : r_.ptr) + s;
+        double *dst = (which == 0 ? p_.ptr : r_.ptr) + elem_base(s);
         // (on the engine's stream: a pageable cudaMemcpy on the legacy stream may return before its DMA has finished, and the
         // engine's non-blocking stream does not order against it)
         DPPR_CUDA(cudaMemcpyAsync(tmp.ptr, h, sizeof(double) * (size_t)V_, cudaMemcpyHostToDevice, st_));
@@ -1063,7 +1100,7 @@ void Engine::validate(int32_t s, double *max_abs_residual, double *max_invariant
     DevBuf<unsigned long long> out;
     out.alloc(2);
     DPPR_CUDA(cudaMemsetAsync(out.ptr, 0, out.bytes(), st_));
-    const double *p = p_.ptr + s, *r = r_.ptr + s;
+    const double *p = p_.ptr + elem_base(s), *r = r_.ptr + elem_base(s);
     val_residual_max<<<grid_for(V_), kThreads, 0, st_>>>(r, Sr_, V_, out.ptr); ++launch_counter();
     DevBuf<double> acc;
     if (max_invariant_defect) {
@@ -1104,16 +1141,32 @@ void Engine::topk(int32_t first, int32_t n, int32_t k, int32_t *ids, double *val
         DPPR_CUDA(cudaMemsetAsync(topk_prevk_.ptr, 0, topk_prevk_.bytes(), st_));
         DPPR_CUDA(cudaMemsetAsync(topk_count_.ptr, 0, topk_count_.bytes(), st_));
     }
-    topk_threshold<<<(unsigned)n, kThreads, 0, st_>>>(p_.ptr, Sr_, V_, first, k, topk_prev_.ptr, topk_prevk_.ptr, topk_bound_.ptr); ++launch_counter();
+    // the request's sources, panel by panel: [lf, lf + ln) inside panel kp, at offset `off` of the request-relative arrays
+    struct Part { int kp, lf, ln, off; };
+    std::vector<Part> parts;
+    for (int kp = first / Pw_; kp <= (first + n - 1) / Pw_; ++kp) {
+        const int g0 = std::max(first, kp * Pw_), g1 = std::min(first + n, kp * Pw_ + panel_sources(kp));
+        if (g1 > g0) parts.push_back({kp, g0 - kp * Pw_, g1 - g0, g0 - first});
+    }
     const int64_t rows_per_warp = Sr_ < 32 ? 32 / Sr_ : 1;
     const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(div_up((int64_t)V_, rows_per_warp), (int64_t)(kThreads / 32)), (int64_t)sm_count_ * 32));
+    for (const Part &q : parts)
+        topk_threshold<<<(unsigned)q.ln, kThreads, 0, st_>>>(p_.ptr + (size_t)q.kp * panel_stride_, Sr_, V_, q.lf, k,
+                                                            topk_prev_.ptr + (size_t)q.kp * Pw_ * kTopKMax, topk_prevk_.ptr + (size_t)q.kp * Pw_,
+                                                            topk_bound_.ptr + q.off), ++launch_counter();
     bool open_sources = true;
     for (int round = 0; round < 3 && open_sources; ++round) {
-        topk_filter<<<fgrid, kThreads, 0, st_>>>(p_.ptr, Sr_, V_, first, n, inv_.ptr, topk_bound_.ptr, topk_ckey_.ptr, topk_cid_.ptr, topk_count_.ptr,
-                                                 round ? topk_over_.ptr : nullptr); ++launch_counter();
-        topk_merge<<<(unsigned)n, kThreads, 0, st_>>>(topk_ckey_.ptr, topk_cid_.ptr, kTopCand, 0, topk_count_.ptr, k, topk_out_ids_.ptr, topk_out_vals_.ptr,
-                                                     perm_.ptr, topk_prev_.ptr + (size_t)first * kTopKMax, topk_prevk_.ptr + first, topk_over_.ptr,
-                                                     round > 0, topk_bound_.ptr); ++launch_counter();
+        for (const Part &q : parts) {
+            const int gfirst = q.kp * Pw_ + q.lf;
+            topk_filter<<<fgrid, kThreads, 0, st_>>>(p_.ptr + (size_t)q.kp * panel_stride_, Sr_, V_, q.lf, q.ln, inv_.ptr, topk_bound_.ptr + q.off,
+                                                     topk_ckey_.ptr + (size_t)q.off * kTopCand, topk_cid_.ptr + (size_t)q.off * kTopCand,
+                                                     topk_count_.ptr + q.off, round ? topk_over_.ptr + q.off : nullptr); ++launch_counter();
+            topk_merge<<<(unsigned)q.ln, kThreads, 0, st_>>>(topk_ckey_.ptr + (size_t)q.off * kTopCand, topk_cid_.ptr + (size_t)q.off * kTopCand, kTopCand, 0,
+                                                            topk_count_.ptr + q.off, k, topk_out_ids_.ptr + (size_t)q.off * k,
+                                                            topk_out_vals_.ptr + (size_t)q.off * k, perm_.ptr,
+                                                            topk_prev_.ptr + (size_t)gfirst * kTopKMax, topk_prevk_.ptr + gfirst, topk_over_.ptr + q.off,
+                                                            round > 0, topk_bound_.ptr + q.off); ++launch_counter();
+        }
         DPPR_CUDA(cudaGetLastError());
         DPPR_CUDA(cudaMemcpyAsync(topk_host_over_.ptr, topk_over_.ptr, sizeof(int) * n, cudaMemcpyDeviceToHost, st_));
         if (round == 0) {  // (the common case ends here: one synchronisation for flags and results)
@@ -1134,13 +1187,15 @@ void Engine::topk(int32_t first, int32_t n, int32_t k, int32_t *ids, double *val
     // sources three rounds did not settle (a flat vector: the bound cannot rise past a tie): the exact scan
     for (int32_t i = 0; i < n && open_sources; ++i) {
         if (!topk_host_over_.ptr[i]) continue;
+        const int gs = first + i;  // (global source index)
         const int slices = div_up(V_, kTopSlice);
         const size_t need = (size_t)slices * k;
         if (topk_key_.count < need) { topk_key_.alloc(need); topk_id_.alloc(need); }
-        topk_partial<<<dim3((unsigned)slices, 1u), kThreads, 0, st_>>>(p_.ptr, Sr_, V_, first + i, inv_.ptr, k, topk_key_.ptr, topk_id_.ptr); ++launch_counter();
+        topk_partial<<<dim3((unsigned)slices, 1u), kThreads, 0, st_>>>(p_.ptr + (size_t)(gs / Pw_) * panel_stride_, Sr_, V_, gs % Pw_, inv_.ptr, k, topk_key_.ptr,
+                                                                       topk_id_.ptr); ++launch_counter();
         topk_merge<<<1, kThreads, 0, st_>>>(topk_key_.ptr, topk_id_.ptr, (int64_t)need, (int64_t)need, nullptr, k, topk_out_ids_.ptr + (size_t)i * k,
-                                           topk_out_vals_.ptr + (size_t)i * k, perm_.ptr, topk_prev_.ptr + (size_t)(first + i) * kTopKMax,
-                                           topk_prevk_.ptr + first + i, nullptr, 0, nullptr); ++launch_counter();
+                                           topk_out_vals_.ptr + (size_t)i * k, perm_.ptr, topk_prev_.ptr + (size_t)gs * kTopKMax,
+                                           topk_prevk_.ptr + gs, nullptr, 0, nullptr); ++launch_counter();
     }
     DPPR_CUDA(cudaGetLastError());
     DPPR_CUDA(cudaMemcpyAsync(topk_host_ids_.ptr, topk_out_ids_.ptr, sizeof(int32_t) * outn, cudaMemcpyDeviceToHost, st_));

@@ -76,7 +76,9 @@ typedef struct dppr_tuning {
     double carry_scale;         /* default 0.01                                                                   [DPPR_CARRY_SCALE] */
     int32_t dense_accel;        /* Chebyshev-accelerated sweeps on undirected windows: 0/1 on (default), -1 off       [DPPR_DENSE_ACCEL] */
     int32_t signed_push;        /* variant 0: one pass over both residual signs: 0/1 on (default), -1 the reference's two passes [DPPR_SIGNED_PUSH] */
-    int32_t reserved[6];
+    int32_t panel_sources;      /* most sources refreshed by one launch; more are split into equal panels, each with its own
+                                   contiguous [V][panel] state, refreshed one after the other; default 128            [DPPR_PANEL_SOURCES] */
+    int32_t reserved[5];
 } dppr_tuning;
 
 typedef struct dppr_engine dppr_engine;

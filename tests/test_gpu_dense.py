@@ -223,6 +223,61 @@ def test_many_sources_lane_groups(group, monkeypatch):
     assert sweeps > 0
 
 
+@pytest.mark.parametrize("variant,panel,dense", [(0, 8, True), (0, 5, False), (2, 16, True), (1, 1, False), (3, 12, True)])
+def test_source_panels_match_single_source_oracles(variant, panel, dense, monkeypatch):
+    """33 sources refreshed in panels of at most `panel` (tuning.panel_sources): 5 panels of 7, 7 of 5, 3 of 11, 33 of 1, 3 of
+    11 -- every panel its own [V][Sr] block and its own launches.  Same answers as one oracle per source; top-k, validation,
+    state export / import and the batch counters go through the panel addressing too."""
+    if dense:
+        force_dense(monkeypatch, div="1e15", tiers=(4, 120, 16))
+    V, M, directed = 2_500, 30_000, variant != 2
+    edges = graphgen.rmat_directed(V, M, seed=11) if directed else graphgen.powerlaw_undirected(V, M, seed=12)
+    wl = stream.workload(M, 0.1, 0, 0.03, 3)
+    sources = [int(x) for x in graphgen.top_out_degree(V, edges, directed, 20)] + list(range(1, 14))
+    eps = 1e-8
+    oracles = []
+    for s in sources:
+        o = orc.Oracle(V, directed, edges, wl.W, wl.B, s, eps, variant)
+        o.initial_solve()
+        oracles.append(o)
+    sweeps = 0
+    with DynamicPPR(V, directed, wl.W, wl.B, sources, epsilon=eps, variant=variant,
+                    tuning={"panel_sources": panel, "dense": 1 if dense else -1}) as eng:
+        eng.init_window_pairs(edges[: wl.W])
+        eng.solve_initial()
+        for k in range(wl.n_batches + 1):
+            if k > 0:
+                lo = wl.W + (k - 1) * wl.B
+                eng.slide_pairs(edges[lo: lo + wl.B])
+                for o in oracles:
+                    o.slide(wl.B)
+            st = eng.stats()
+            assert st.error_flags == 0 and st.frontier_pops > 0
+            sweeps += st.dense_sweeps
+            for i, o in enumerate(oracles):
+                check_against(eng.estimates(i), eng.residuals(i), o.p, None, eps, f"panel {panel} source {sources[i]} batch {k}")
+        assert (sweeps > 0) == dense
+        ids, vals = eng.topk(10)
+        sub_ids, sub_vals = eng.topk(10, first_source=6, n_sources=20)   # a range that starts and ends inside panels
+        for i in range(len(sources)):
+            p = eng.estimates(i)
+            order = np.lexsort((np.arange(V), -p))[:10]
+            np.testing.assert_array_equal(ids[i], order)
+            np.testing.assert_array_equal(vals[i], p[order])
+            if 6 <= i < 26:
+                np.testing.assert_array_equal(sub_ids[i - 6], order)
+            max_r, defect = eng.validate(i)
+            assert max_r <= eps and defect <= 1e-12
+        # state import lands in the right panel and column
+        i = len(sources) - 2
+        p, r, neighbour = eng.estimates(i), eng.residuals(i), eng.estimates(i - 1)
+        p2 = p.copy(); p2[17] += 0.25
+        eng.set_state(i, p2, r)
+        np.testing.assert_array_equal(eng.estimates(i), p2)
+        np.testing.assert_array_equal(eng.estimates(i - 1), neighbour)
+        np.testing.assert_array_equal(eng.topk(1, first_source=i, n_sources=1)[0][0], [17])
+
+
 def test_dense_off_keeps_no_out_lists(monkeypatch):
     monkeypatch.setenv("DPPR_DENSE_DIV", "0")
     V, M = 3_000, 30_000
