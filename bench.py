@@ -385,6 +385,10 @@ def main():
         Ts, Fd = f("scatter_edges"), f("dense_pops")
         L, Ls, U = f("dense_slots"), f("dense_pairs"), f("dense_units")
         push_s = float(f("ms_push").sum()) * 1e-3
+        # sources beyond 128 are refreshed in equal panels, one push launch each (engine.cuh, Pw_): the roofline is per launch
+        panel_max = int(os.environ.get("DPPR_PANEL_SOURCES", "128") or 128)
+        n_panels = -(-len(my_sources) // panel_max)
+        panel_w = -(-len(my_sources) // n_panels)
         alg_bytes = float((24.0 * Ts + 56.0 * (F - Fd) + 4.0 * L + 2.0 * Ls + 4.0 * U + 32.0 * Fd).sum())
         peak, peak_src = measured_hbm_peak()
         achieved = alg_bytes / push_s / 1e9
@@ -392,15 +396,16 @@ def main():
         traffic, traffic_note = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            ent = tj.get(f"config{cfg.index}_s{len(my_sources)}_o{a.variant}")
+            ent = tj.get(f"config{cfg.index}_s{panel_w}_o{a.variant}")
             if ent:
                 traffic, traffic_note = ent.get("dram_bytes_per_launch"), ent.get("source")
         except Exception:
             pass
-        kname = f"push_persistent<{a.variant}, {(1 if len(my_sources) == 1 else 8) if (dense or (a.variant == 0 and cfg.index in (4, 5))) else 0}>"
+        kname = f"push_persistent<{a.variant}, {(1 if panel_w == 1 else 8) if (dense or (a.variant == 0 and cfg.index in (4, 5))) else 0}>"
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg_bytes / K, "launch_ms": push_s * 1e3 / K,
+                    "algorithmic_bytes_per_launch": alg_bytes / K / n_panels, "launch_ms": push_s * 1e3 / K / n_panels,
+                    "launches_per_step": n_panels, "sources_per_launch": panel_w,
                     "scatter_form_equivalent_GBps": float((24.0 * T + 56.0 * F).sum()) / push_s / 1e9,
                     "note": ("bytes = 24 T_scatter + 56 F_scatter + 4 slots + 2 (slot, source) bf16 gathers + 4 (vertex, source) units + 32 F_dense "
                              "(DESIGN.md 3.3); 'scatter_form_equivalent' credits every gathered non-zero pair the 24 B a scatter would move "
