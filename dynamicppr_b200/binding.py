@@ -38,7 +38,7 @@ class Tuning(C.Structure):
         ("pull_warp_min", C.c_int32), ("pull_big_min", C.c_int32), ("pull_big_chunk", C.c_int32), ("window_path", C.c_int32),
         ("iterlog", C.c_int32), ("probe_iter", C.c_int32), ("dense_div", C.c_double), ("dense_min_edges", C.c_double),
         ("carry_gamma", C.c_double), ("carry_scale", C.c_double), ("dense_accel", C.c_int32), ("signed_push", C.c_int32), ("panel_sources", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("pull_warp_units", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 

@@ -84,6 +84,7 @@ Tuning resolve_tuning(const dppr_tuning &t) {
     r.iterlog = pick_int(t.iterlog, "DPPR_ITERLOG", 0) > 0;
     r.probe_iter = pick_int(t.probe_iter, "DPPR_PROBE_ITER", 10);
     r.panel_sources = std::max(1, pick_int(t.panel_sources, "DPPR_PANEL_SOURCES", 128));
+    r.pull_warp_units = std::max(0, pick_int(t.pull_warp_units, "DPPR_PULL_WARP_UNITS", 8));  // (-1 -> 0: CTA items)
     return r;
 }
 
@@ -620,6 +621,7 @@ void Engine::launch_push_panel(bool init_mode, int panel) {
     if (dense_) a.dense_enter_edges = (unsigned long long)std::max(1.0, ((double)Ew_ + 2.0 * (double)V_) * (double)Sk / tn_.dense_div);
     a.dense_exit_edges = a.dense_enter_edges / 2;
     a.pull_warp_min = tn_.pull_warp_min; a.pull_big_min = pull_big_min_; a.pull_big_chunk = pull_big_chunk_;
+    a.pull_warp_units = tn_.pull_warp_units;
     a.big = big_.ptr; a.bigcap = bigcap_; a.bigacc = bigacc_.ptr; a.tile_list = tile_list_.ptr; a.tile_list_cap = tile_cap_;
     a.accel_frac = (D_ == 2 && tn_.dense_accel >= 0) ? tn_.accel_frac : 0.0;
     a.signed_push = tn_.signed_push >= 0 ? 1 : 0;

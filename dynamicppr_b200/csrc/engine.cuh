@@ -48,6 +48,7 @@ struct Tuning {
     bool iterlog = false;
     int probe_iter = 10;
     int panel_sources = 128;  // most sources per launch (see Engine::Pw_)
+    int pull_warp_units = 8;  // multi-source sweeps: warp-slices per work item handed to a warp; 0: items go to CTAs
 };
 
 class Engine {

@@ -524,10 +524,46 @@ __device__ __forceinline__ void pull_sweep(const PushArgs &a, PushSmem &sm, Push
             }
             j = __shfl_sync(kFull, jn, 0);
         }
+    } else if (a.pull_warp_units > 0) {
+        // ---- several sources, items handed to WARPS (the default): a chunk of the grid tier, or `wu` consecutive warp-slices
+        // (32 / G vertices each; 8 = one tile).  No CTA barrier inside the sweep: with items handed to CTAs (below) the warps of
+        // a CTA spent 2.75 of 21.5 stall cycles per issued instruction waiting for the slowest warp of each item
+        // (profiles/ncu_c4_s125_r02c.txt).  BASELINE configs[3], 125 sources: 120.5 -> 108-111 ms per batch with 8 / 16 / 32
+        // slices per item (1: 117, 2: 113, 4: 111, 64: 116); configs[4], 8 sources: 163 -> 131 ms ----
+        const uint32_t wu = (uint32_t)a.pull_warp_units;
+        const uint32_t ntl = n0 + n1 + n2;
+        const uint32_t nslices = ntl * (uint32_t)kWarps;  // (a tile = kWarps warp-slices)
+        const uint32_t nwork = nchunks + (nslices + wu - 1) / wu;
+        uint32_t j = 0;
+        if (lane == 0) j = atomicAdd(next, 1u);
+        j = __shfl_sync(kFull, j, 0);
+        while (j < nwork) {
+            uint32_t jn = 0;
+            if (lane == 0) jn = atomicAdd(next, 1u);  // consumed at the bottom of the loop
+            if (j < nchunks) {
+                pull_do_chunk<SB, ACCEL>(a, q, phase, xcur, xnext, j, nh, t);
+            } else {
+                const uint32_t s_lo = (j - nchunks) * wu, s_hi = min(nslices, s_lo + wu);
+                uint32_t tt_cur = 0xffffffffu, cg = 0, w0 = 0;
+                for (uint32_t sl = s_lo; sl < s_hi; ++sl) {
+                    const uint32_t tt = sl / (uint32_t)kWarps;
+                    if (tt != tt_cur) {
+                        tt_cur = tt;
+                        const uint32_t tile = pull_tile_at<SB>(a, tt, n0, n1);
+                        cg = tile / q.tpc;
+                        w0 = (tile - cg * q.tpc) * q.vpt;
+                    }
+                    const uint32_t wf = w0 + (sl - tt * (uint32_t)kWarps) * q.vpw;
+                    if (wf < V) pull_do_vertices<SB, ACCEL>(a, q, phase, xcur, xnext, wf, cg, t);
+                }
+            }
+            j = __shfl_sync(kFull, jn, 0);
+        }
+        __syncthreads();
     } else {
-        // ---- several sources: items handed to CTAs -- kWarps chunks of the grid tier, or tiles whose vertices the CTA's
-        // warps share (32 / G each).  (Measured on BASELINE configs[3], 125 sources: 498 ms per batch against 573 ms with a
-        // flat, edge-balanced list per CTA and 683 ms with whole tiles per warp, profiles/README.md.) ----
+        // ---- several sources, items handed to CTAs (tuning.pull_warp_units = -1; kept for A/B runs) -- kWarps chunks of the grid
+        // tier, or tiles whose vertices the CTA's warps share (32 / G each).  (Early in round 2, before the pipelined walk and
+        // the 3-CTA build, this beat whole tiles per warp 498 to 683 ms; re-measured at the end of the round it loses, see above.) ----
         const uint32_t tpi = max(1u, 32u / q.vpt);  // tiles per item: at least 32 vertices
         const uint32_t ntl = n0 + n1 + n2;
         const uint32_t ngroups = (nchunks + kWarps - 1) / kWarps;

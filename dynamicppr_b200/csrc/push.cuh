@@ -146,6 +146,7 @@ struct PushArgs {
     unsigned long long dense_enter_edges;  // an iteration expected to traverse at least this many in-edges runs as a sweep
     unsigned long long dense_exit_edges;   // ... and below this the loop goes back to scatter iterations
     int32_t pull_warp_min, pull_big_min, pull_big_chunk;  // out-degree tiers of a sweep; entries per chunk of the grid tier
+    int32_t pull_warp_units;     // several sources: 0 = work items go to CTAs, n = to warps, n warp-slices of a tile at a time
     uint32_t pull_tile_mul;      // tile visiting order: tile = (t * mul) mod ntiles, mul coprime to ntiles
     uint32_t *tile_list;         // active tiles of the running dense episode: [3][tile_list_cap], heavy tiles first
     uint32_t tile_list_cap;

@@ -89,6 +89,16 @@ __device__ __forceinline__ unsigned long long top_compress(TopSmem &sm, int k) {
     return n >= (unsigned)k ? sm.key[k - 1] : 0ull;
 }
 
+// "another round of offers may not fit": the same answer in every thread.  Call right after the barrier that follows a round of
+// offers; the second barrier keeps the next round's offers (which bump sm.cnt) behind the slowest thread's read -- without
+// it a thread could see the count already raised, decide alone that the buffer is full and enter top_compress's barriers
+// without the others (found by racecheck in round 2; the scan had this since round 1).
+__device__ __forceinline__ bool top_nearly_full(TopSmem &sm) {
+    const unsigned c = sm.cnt;
+    __syncthreads();
+    return c > (unsigned)(kTopBuf - kThreads * kTopItems);
+}
+
 // candidates strictly above the threshold -- or equal to it (ties are resolved by id in the sort) -- enter the buffer
 __device__ __forceinline__ void top_offer(TopSmem &sm, bool valid, unsigned long long key, uint32_t id, unsigned long long tau) {
     if (valid && key >= tau) {
@@ -118,7 +128,7 @@ __global__ void __launch_bounds__(kThreads)
             top_offer(sm, valid, key, valid ? (inv ? inv[v] : (uint32_t)v) : 0u, tau);
         }
         __syncthreads();
-        if (sm.cnt > (unsigned)(kTopBuf - kThreads * kTopItems)) tau = top_compress(sm, k);  // (uniform)
+        if (top_nearly_full(sm)) tau = top_compress(sm, k);
     }
     top_compress(sm, k);
     const size_t out = ((size_t)s * gridDim.x + blockIdx.x) * (size_t)k;
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(kThreads)
             top_offer(sm, valid, valid ? pkey[in + i] : 0ull, valid ? pid[in + i] : 0u, tau);
         }
         __syncthreads();
-        if (sm.cnt > (unsigned)(kTopBuf - kThreads * kTopItems)) tau = top_compress(sm, keep);
+        if (top_nearly_full(sm)) tau = top_compress(sm, keep);
     }
     top_compress(sm, keep);
     const unsigned held = sm.cnt;

@@ -78,7 +78,9 @@ typedef struct dppr_tuning {
     int32_t signed_push;        /* variant 0: one pass over both residual signs: 0/1 on (default), -1 the reference's two passes [DPPR_SIGNED_PUSH] */
     int32_t panel_sources;      /* most sources refreshed by one launch; more are split into equal panels, each with its own
                                    contiguous [V][panel] state, refreshed one after the other; default 128            [DPPR_PANEL_SOURCES] */
-    int32_t reserved[5];
+    int32_t pull_warp_units;    /* multi-source sweeps: work is handed to warps, this many warp-slices (32 / lanes-per-vertex vertices each) at a
+                                   time; default 8 = one tile.  -1: to whole CTAs (a barrier per item)                [DPPR_PULL_WARP_UNITS] */
+    int32_t reserved[4];
 } dppr_tuning;
 
 typedef struct dppr_engine dppr_engine;
