@@ -251,7 +251,7 @@ def main():
     resident = cfg.index in (2, 3)  # working set fits the 126 MB L2: flush between steps
     config = {"workload": cfg.describe() + f", {'top-' + str(S_total) + ' out-degree sources' if multi else 'top out-degree source(s)'}, -o {a.variant}",
               "variant": a.variant, "sources_total": S_total, "V": cfg.V, "M": cfg.M, "W": wl.W, "B": wl.B,
-              "parallelism": (f"{S_total} sources split over {world} GPU(s), window graph replicated, no data-path collective" if multi
+              "parallelism": (f"{S_total} sources dealt round-robin (by degree rank) to {world} GPU(s), window graph replicated, no data-path collective" if multi
                               else f"source-sharded x{world} ({S_total // world} per GPU), window graph replicated"),
               "l2": ("flushed between steps (256 MiB write, outside the timed events)" if resident and not a.no_flush else
                      "not flushed: stateful stream" if resident else
@@ -290,7 +290,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     t0 = time.time()
     job_sources = workloads.top_sources(cfg, S_total, device=local_rank)
-    my_sources = sharding.shard_sources(job_sources, rank, world, None if multi else S_total // world)
+    my_sources = sharding.shard_sources(job_sources, rank, world, None if multi else S_total // world, interleave=multi)
     K, Wm = a.steps, a.warmup
     if Wm + 2 * K > avail:
         K = max(1, (avail - Wm) // 2)

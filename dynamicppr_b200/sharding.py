@@ -7,10 +7,16 @@ from __future__ import annotations
 import numpy as np
 
 
-def shard_sources(sources, rank: int, world: int, per_rank: int | None = None):
+def shard_sources(sources, rank: int, world: int, per_rank: int | None = None, interleave: bool = False):
     """Contiguous block of sources for `rank`.  With per_rank given (weak scaling) every rank gets
-    exactly that many; otherwise the list is split as evenly as possible (strong scaling)."""
+    exactly that many; otherwise the list is split as evenly as possible (strong scaling).
+    interleave (strong scaling only): rank r takes sources r, r + world, r + 2 world, ... -- the job's list is ranked by
+    degree, and a refresh costs more for the high-degree sources, so dealing the list round-robin evens the ranks out."""
     sources = np.asarray(sources, dtype=np.int32)
+    if interleave:
+        if per_rank is not None:
+            raise ValueError("interleave applies to the strong-scaling split only")
+        return np.ascontiguousarray(sources[rank::world])
     if per_rank is not None:
         if len(sources) < world * per_rank:
             raise ValueError(f"need {world * per_rank} sources for {world} ranks x {per_rank}, have {len(sources)}")

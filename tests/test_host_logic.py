@@ -204,6 +204,10 @@ def test_shard_sources():
     assert sum(parts, []) == list(range(10)) and [len(p) for p in parts] == [3, 3, 2, 2]
     with pytest.raises(ValueError):
         sharding.shard_sources(s, 0, 8, 2)
+    dealt = [sharding.shard_sources(s, r, 4, interleave=True).tolist() for r in range(4)]
+    assert dealt == [[0, 4, 8], [1, 5, 9], [2, 6], [3, 7]]
+    with pytest.raises(ValueError):
+        sharding.shard_sources(s, 0, 2, 2, interleave=True)
 
 
 _WORKER = r"""
