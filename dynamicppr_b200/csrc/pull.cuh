@@ -65,6 +65,13 @@ __device__ __forceinline__ unsigned long long l2_keep_policy() {
 #define DPPR_PULL_HINTS 3   // bit 0: streaming (evict-first) loads of slots / metadata, bit 1: evict_last gathers of x
 #endif
 template <class T> __device__ __forceinline__ T pl_ldcs(const T *p) { return (DPPR_PULL_HINTS & 1) ? __ldcs(p) : __ldcg(p); }
+// "this sector will be wanted soon": no register, no scoreboard -- the later load finds it in L2
+#ifndef DPPR_PULL_PREFETCH
+#define DPPR_PULL_PREFETCH 1
+#endif
+__device__ __forceinline__ void pl_prefetch_l2(const void *p) {
+    if (DPPR_PULL_PREFETCH) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 // a lane's piece of an x row: SB = 1 -> one bf16 (single source), SB = 8 -> 16 bytes
 template <int SB> struct XPiece;
@@ -469,7 +476,17 @@ __device__ __forceinline__ void pull_do_vertices(const PushArgs &a, const PullGe
         base = m.x; head = m.y; len = m.z; mask = m.w - 1u;
     }
     if (have) xc = x_load<SB>(xcur, (size_t)w * (size_t)a.Sr + s0);
+    if (SB > 1 && have) {
+        // the unit's own r piece (64 bytes) is read when its list has been walked, a dependent DRAM round trip later: ask
+        // for it now (pull_finish_unit's share of the stall samples was 25 %, profiles/README.md)
+        const double *rp = a.r + (size_t)w * (size_t)a.Sr + s0;
+        pl_prefetch_l2(rp); pl_prefetch_l2(rp + 4);
+    }
     const int tier = len >= (uint32_t)a.pull_big_min ? 2 : (len >= (uint32_t)a.pull_warp_min && q.vpw > 1u) ? 1 : 0;
+    if (SB > 1 && have && xc.any()) {  // ... and its p piece, which only a unit popped by the previous sweep touches
+        const double *pp = a.p + (size_t)w * (size_t)a.Sr + s0;
+        pl_prefetch_l2(pp); pl_prefetch_l2(pp + 4);
+    }
     if (tier == 0 && have && len) pull_walk<SB>(a, xcur, base, head, mask, 0u, len, 1u, s0, acc, t.nz);
     // lists of warp_min or more entries: the whole warp walks them, one after the other
     unsigned m1 = __ballot_sync(kFull, tier == 1 && g == 0 && w < V);
