@@ -57,7 +57,7 @@ out = dict(config=a.config, sources=len(srcs), rank_offset=a.rank_offset, varian
 if a.check:
     t0 = time.time()
     out["window_mismatches"] = eng.check_window_device(dev.data_ptr() + 8 * nb * wl.B, wl.W)
-    v = [eng.validate(i) for i in range(min(len(srcs), 4))]
+    v = [eng.validate(int(i)) for i in sorted(set(np.linspace(0, len(srcs) - 1, 6).astype(int).tolist()))]  # (spread over the source panels)
     out["max_abs_residual_over_eps"] = max(x[0] for x in v) / cfg.eps
     out["invariant_defect"] = max(x[1] for x in v)
     out["check_s"] = round(time.time() - t0, 2)
