@@ -781,8 +781,15 @@ struct DenseIO {
     GridBar gen;
     float rate;  // scatter cost per edge the caller decided with (0 = not measured yet)
 };
+// How the argument block reaches the out-of-line episode (measured, profiles/README.md): several sources -- by REFERENCE to
+// the kernel's __grid_constant__ parameter (no 400-byte stack copy whose fields the gather loops re-read as local loads:
+// BASELINE configs[3], 125 sources, 108.5 -> 99.5 ms per batch); one source -- by VALUE (its sweep is inlined and keeps
+// what it needs in registers; through the reference it reads the parameter window with generic loads: 37 -> 43 ms on
+// configs[4])
+template <int SB> struct DenseArgPass { using type = const PushArgs &; };
+template <> struct DenseArgPass<1> { using type = const PushArgs; };
 template <int SB>
-__device__ __noinline__ bool dense_mode(const PushArgs a, PushSmem &sm, PushCtrl *c, int phase, uint32_t it,
+__device__ __noinline__ bool dense_mode(typename DenseArgPass<SB>::type a, PushSmem &sm, PushCtrl *c, int phase, uint32_t it,
                                         unsigned long long hpk, DenseIO &io) {  // `a` BY VALUE: a reference would force
     // the caller to keep its kernel parameters in local memory instead of the constant bank, for the scatter path too
     GridBar gen = io.gen;

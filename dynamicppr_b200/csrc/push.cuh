@@ -680,7 +680,7 @@ namespace dppr {
 // per refresh on BASELINE configs[3]); 3 x 8 warps with 4 / 8 gathers per lane measured best (profiles/README.md).
 template <int VAR, int DENSE>
 __global__ void __launch_bounds__(kThreads, DENSE == 8 ? DPPR_DENSE8_MIN_BLOCKS : DENSE == 1 ? DPPR_DENSE1_MIN_BLOCKS : DPPR_MIN_BLOCKS)
-    push_persistent(const PushArgs a) {
+    push_persistent(const __grid_constant__ PushArgs a) {
     __shared__ PushSmem sm;
     PushCtrl *c = a.ctrl;
     if (threadIdx.x == 0) { sm.stage_cnt = 0; sm.abort_flag = 0; }
