@@ -128,6 +128,7 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
         if (f == DPPR_ENGINE_STEPWISE || f == DPPR_ENGINE_LEVELSYNC) mode_ = f;
     }
     tn_ = resolve_tuning(cfg.tuning);
+    debug_ = env_int("DPPR_DEBUG", 0) != 0;  // (like every DPPR_* variable: read here, once)
     if (cfg_.alpha <= 0.0) cfg_.alpha = 0.15;
     if (cfg_.alpha >= 1.0) throw InvalidArgument("alpha must be in (0, 1)");
     if (cfg_.epsilon <= 0.0) cfg_.epsilon = 1e-9;
@@ -204,7 +205,7 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
         DPPR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern[v], kThreads, v == cfg_.variant ? dyn_smem_ : 0));
         if (per_sm < 1) throw CudaFailure("push kernel does not fit on an SM");
         coop_grid_[v] = std::min(per_sm, tn_.ctas_per_sm) * sm_count_;
-        if (env_int("DPPR_DEBUG", 0)) std::fprintf(stderr, "[dppr] variant %d: %d CTAs per SM fit, grid %d\n", v, per_sm, coop_grid_[v]);
+        if (debug_) std::fprintf(stderr, "[dppr] variant %d: %d CTAs per SM fit, grid %d\n", v, per_sm, coop_grid_[v]);
     }
     {
         int per_sm = 0;
@@ -1178,7 +1179,7 @@ void Engine::topk(int32_t first, int32_t n, int32_t k, int32_t *ids, double *val
         DPPR_CUDA(cudaStreamSynchronize(st_));
         open_sources = false;
         for (int32_t i = 0; i < n; ++i) open_sources = open_sources || topk_host_over_.ptr[i] != 0;
-        if (open_sources && env_int("DPPR_DEBUG", 0)) {
+        if (open_sources && debug_) {
             int cnt = 0, mx = 0;
             for (int32_t i = 0; i < n; ++i) { cnt += topk_host_over_.ptr[i] != 0; mx = std::max(mx, topk_host_over_.ptr[i]); }
             std::fprintf(stderr, "[dppr] top-k round %d: %d of %d sources over the candidate capacity (largest list %d)\n", round, cnt, n, mx);

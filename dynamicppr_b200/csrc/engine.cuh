@@ -134,7 +134,7 @@ private:
     int64_t panel_stride_ = 0;                                       // elements between panels = V_ * Sr_
     int panel_sources(int k) const { return std::min(Pw_, S_ - k * Pw_); }
     size_t elem_base(int s) const { return (size_t)(s / Pw_) * (size_t)panel_stride_ + (size_t)(s % Pw_); }  // element (vertex 0, source s)
-    bool window_ready_ = false, solved_ = false, batch_pending_ = false;
+    bool window_ready_ = false, solved_ = false, batch_pending_ = false, debug_ = false;
     int64_t log_start_ = 0;
     int step_level_ = 0;  // stepwise mode keeps the status level on the host
     int failed_code_ = 0;         // sticky: DPPR_E_* once a batch left device error flags
