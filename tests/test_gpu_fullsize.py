@@ -163,6 +163,17 @@ def test_config4_orkut_shaped_multi_source_full_size():
     assert stats[-1].dense_pairs > 0 and stats[-1].scatter_edges > 0
 
 
+def test_config4_orkut_shaped_source_panels_full_size():
+    """the same graph, 40 sources refreshed in 3 panels (tuning.panel_sources = 16 -> 14 + 13 + 13; the default of 128 is what
+    bench.py's 1000 sources run with): every panel is its own [V][16] block and its own repair / push launches, and every
+    source of every panel satisfies the residual bound and the push invariant"""
+    cfg = workloads.CONFIGS[4]
+    job = workloads.top_sources(cfg, 1000)
+    srcs = job[np.linspace(0, 999, 40).astype(int)]
+    stats = _fullsize_run(cfg, srcs, 3, check_at=(0, 3), tuning={"panel_sources": 16})
+    assert stats[-1].dense_sweeps > 3 * 10, "three panels, each with its own sweep episode"
+
+
 def test_config5_twitter_shaped_one_source_full_size():
     """BASELINE configs[4] shape on one GPU: 41.7 M vertices, 146.8 M-edge window, 1.47 M-edge batches; the top source;
     window graph compared bit-exactly on the device (round 1 used a checksum)"""
