@@ -41,7 +41,7 @@ struct Tuning {
     int dense_accel = 0;      // 0 / 1: Chebyshev-accelerated sweeps on undirected windows, -1: off
     int signed_push = 0;      // 0 / 1: variant 0 pushes both signs in one pass, -1: the reference's two passes
     double accel_frac = 0.9;  // ... while the frontier holds at least this fraction of all (vertex, source) pairs
-    double dense_div = 4.0, dense_min_edges = 2.0e7;
+    double dense_div = 4.0, dense_min_edges = -1.0;  // (< 0: 2e7 for variant 0, 0 for variants 1-3)
     int pull_group = 16, pull_warp_min = 32, pull_big_min = 0, pull_big_chunk = 0;  // (0: by the number of sources)
     double carry_gamma = 1.0, carry_scale = 0.01;
     int window_path = 0;  // 0 auto, 1 multi-kernel only, 2 cooperative or multi-kernel (no single-CTA kernel)

@@ -71,7 +71,8 @@ typedef struct dppr_tuning {
     int32_t iterlog;            /* 1: keep a per-iteration log of the last refresh (dppr_debug_iterlog)           [DPPR_ITERLOG] */
     int32_t probe_iter;         /* iteration whose per-CTA timeline dppr_debug_ctalog returns; default 10         [DPPR_PROBE_ITER] */
     double dense_div;           /* static scatter/gather switch estimate: (E_w + 2V) S / dense_div; default 4     [DPPR_DENSE_DIV] */
-    double dense_min_edges;     /* auto: window entries x sources from which the switching kernel is used; 2e7   [DPPR_DENSE_MIN_EDGES] */
+    double dense_min_edges;     /* auto: window entries x sources from which the switching kernel is used; default 2e7 for
+                                   variant 0, always for variants 1-3                                             [DPPR_DENSE_MIN_EDGES] */
     double carry_gamma;         /* variant 0 threshold schedule; default off (1.0)                               [DPPR_CARRY_GAMMA] */
     double carry_scale;         /* default 0.01                                                                   [DPPR_CARRY_SCALE] */
     int32_t dense_accel;        /* Chebyshev-accelerated sweeps on undirected windows: 0/1 on (default), -1 off       [DPPR_DENSE_ACCEL] */
