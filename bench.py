@@ -401,7 +401,10 @@ def main():
                 traffic, traffic_note = ent.get("dram_bytes_per_launch"), ent.get("source")
         except Exception:
             pass
-        kname = f"push_persistent<{a.variant}, {(1 if panel_w == 1 else 8) if (dense or (a.variant == 0 and cfg.index in (4, 5))) else 0}>"
+        # which instantiation ran (engine.cu, Engine::Engine): variants 1-3 always get the kernel that can switch to sweeps,
+        # variant 0 from 2e7 window entries x sources per launch
+        switching = a.variant != 0 or wl.W * (1 if cfg.directed else 2) * panel_w >= 2.0e7
+        kname = f"push_persistent<{a.variant}, {(1 if panel_w == 1 else 8) if switching else 0}>"
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes / K / n_panels, "launch_ms": push_s * 1e3 / K / n_panels,
