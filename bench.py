@@ -25,8 +25,9 @@ Printed JSON (one line, rank 0):
              of every source on the rank (dppr_get_topk, D2H).
   roofline   the persistent push kernel: algorithmic bytes of what it did (scatter iterations: 24 B per traversed
              in-edge + 56 B per pop; gather sweeps: 4 B per out-list entry walked + 2 B (bf16) per (entry,
-             source) gather + 4 B per (vertex, source) unit (x read + x write) + 32 B per pop (r and p rows read and
-             written)) / CUDA-event time of that kernel, against the
+             source) gather + 4 B per (vertex, source) unit (x read + x write) + per pop 16 B of r read-modify-write and 16 B of p
+             (one source) or 8 B of the FP32 popped-amount sum that stands in for p during an episode (several sources))
+             / CUDA-event time of that kernel, against the
              measured HBM copy bandwidth (MEASURED_PEAKS.json).  `traffic` = DRAM bytes per launch from the committed
              ncu capture of the same kernel on the same config (profiles/traffic.json), else null.
   cpu_baseline  the reference's own CPU implementation (oracle/_ref/ref_harness_omp: unmodified reference classes,
@@ -389,7 +390,8 @@ def main():
         panel_max = int(os.environ.get("DPPR_PANEL_SOURCES", "128") or 128)
         n_panels = -(-len(my_sources) // panel_max)
         panel_w = -(-len(my_sources) // n_panels)
-        alg_bytes = float((24.0 * Ts + 56.0 * (F - Fd) + 4.0 * L + 2.0 * Ls + 4.0 * U + 32.0 * Fd).sum())
+        pop_bytes = 32.0 if panel_w == 1 else 24.0  # (a sweep's pop: r RMW + p RMW, or r RMW + the FP32 amount sum, pull.cuh)
+        alg_bytes = float((24.0 * Ts + 56.0 * (F - Fd) + 4.0 * L + 2.0 * Ls + 4.0 * U + pop_bytes * Fd).sum())
         peak, peak_src = measured_hbm_peak()
         achieved = alg_bytes / push_s / 1e9
         dense = bool(f("dense_sweeps").sum() > 0)
@@ -410,7 +412,7 @@ def main():
                     "algorithmic_bytes_per_launch": alg_bytes / K / n_panels, "launch_ms": push_s * 1e3 / K / n_panels,
                     "launches_per_step": n_panels, "sources_per_launch": panel_w,
                     "scatter_form_equivalent_GBps": float((24.0 * T + 56.0 * F).sum()) / push_s / 1e9,
-                    "note": ("bytes = 24 T_scatter + 56 F_scatter + 4 slots + 2 (slot, source) bf16 gathers + 4 (vertex, source) units + 32 F_dense "
+                    "note": (f"bytes = 24 T_scatter + 56 F_scatter + 4 slots + 2 (slot, source) bf16 gathers + 4 (vertex, source) units + {pop_bytes:.0f} F_dense "
                              "(DESIGN.md 3.3); 'scatter_form_equivalent' credits every gathered non-zero pair the 24 B a scatter would move "
                              "and is NOT the roofline figure" if dense else
                              "scatter iterations only: 24 B per traversed in-edge + 56 B per pop; L2-resident working set: bound by dependent "

@@ -292,6 +292,10 @@ Engine::Engine(const dppr_config &cfg) : cfg_(cfg) {
     p_.alloc((size_t)n_panels_ * panel_stride_);
     r_.alloc((size_t)n_panels_ * panel_stride_);
     if (n_panels_ > 1) ctrl_acc_.alloc(1);
+    if (dense_ && Pw_ > 1) {  // popped-amount sums of a sweep episode (pull.cuh): zero whenever no episode is running
+        pacc_.alloc((size_t)n_panels_ * panel_stride_);
+        DPPR_CUDA(cudaMemsetAsync(pacc_.ptr, 0, pacc_.bytes(), st_));
+    }
     // level stamps: the frontier dedupe of variants 2, 3 -- and of variant 0's signed pass (push.cuh)
     if (cfg_.variant >= DPPR_EAGER || (cfg_.variant == DPPR_OPTIMIZED && tn_.signed_push >= 0)) status_.alloc((size_t)n_panels_ * panel_stride_);
     src_.alloc((size_t)S_);
@@ -598,6 +602,7 @@ void Engine::launch_push_panel(bool init_mode, int panel) {
     PushArgs a{};
     a.vmeta = vmeta_.ptr; a.pool = pool_.ptr; a.outdeg = outdeg_.ptr;
     a.p = p_.ptr + pb; a.r = r_.ptr + pb; a.status = status_.ptr ? status_.ptr + pb : nullptr;
+    a.pacc = pacc_.ptr ? pacc_.ptr + pb : nullptr;
     a.Sr = Sr_; a.S = Sk; a.src = src_.ptr + (size_t)panel * Pw_;
     for (int i = 0; i < 2; ++i) { a.q[i] = q_[i].ptr; a.qr[i] = qr_[i].ptr; a.hub[i] = hub_[i].ptr; }
     a.qalt = qalt_.ptr;

@@ -188,6 +188,7 @@ private:
     DevBuf<double> qr_[2];
     DevBuf<HubItem> hub_[2];
     uint32_t qcap_ = 0, hcap_ = 0;
+    DevBuf<float> pacc_;                 // per (vertex, source): amounts popped by the running sweep episode (several sources)
     DevBuf<PushCtrl> ctrl_, ctrl_acc_;   // ctrl_acc_: counters of a refresh summed over its panels
     DevBuf<BatchRecord> dev_record_;
     DevBuf<uint4> iterlog_;

@@ -177,16 +177,32 @@ __device__ __forceinline__ uint32_t pull_finish_unit(const PushArgs &a, int phas
     if (touched) {
         const double scale = (1.0 - a.alpha) / (double)(len + 1u);
         if (xc.any()) {  // the pop decided by the previous sweep
-            if (SB == 1) {
+            if constexpr (SB == 1) {
                 a.p[row] += a.alpha * bf16_value(xc.get(0));
             } else {
+                // Several sources: the popped amounts of an episode are summed per pair in FP32 (a.pacc, zero outside an
+                // episode) and folded into p once, when the episode ends (pull_fold): 8 instead of 16 bytes of read-modify-write
+                // per pair and sweep, on the stream that is two thirds of a full sweep's DRAM traffic.  The amounts are bf16
+                // values, so an FP32 sum of them is almost always EXACT; TwoSum tells when it is not, and that amount goes
+                // to p directly.  p therefore ends up with the same exact sum of amounts as before, times alpha.
+                float pa[SB];
 #pragma unroll
-                for (int j = 0; j < SB; j += 2) {
-                    double2 pv = *reinterpret_cast<double2 *>(a.p + row + j);
-                    pv.x += a.alpha * bf16_value(xc.get(j));
-                    pv.y += a.alpha * bf16_value(xc.get(j + 1));
-                    *reinterpret_cast<double2 *>(a.p + row + j) = pv;
+                for (int j = 0; j < SB; j += 4) {
+                    const float4 v4 = *reinterpret_cast<const float4 *>(a.pacc + row + j);
+                    pa[j] = v4.x; pa[j + 1] = v4.y; pa[j + 2] = v4.z; pa[j + 3] = v4.w;
                 }
+#pragma unroll
+                for (int j = 0; j < SB; ++j) {
+                    const float av = __uint_as_float(xc.get(j) << 16);
+                    const float t = pa[j] + av;
+                    const float bb = t - pa[j];
+                    const float err = (pa[j] - (t - bb)) + (av - bb);
+                    if (err == 0.f) pa[j] = t;
+                    else a.p[row + j] += a.alpha * (double)av;  // (rare: the FP32 sum would have rounded)
+                }
+#pragma unroll
+                for (int j = 0; j < SB; j += 4)
+                    *reinterpret_cast<float4 *>(a.pacc + row + j) = make_float4(pa[j], pa[j + 1], pa[j + 2], pa[j + 3]);
             }
         }
         double rw[SB];
@@ -483,10 +499,8 @@ __device__ __forceinline__ void pull_do_vertices(const PushArgs &a, const PullGe
         pl_prefetch_l2(rp); pl_prefetch_l2(rp + 4);
     }
     const int tier = len >= (uint32_t)a.pull_big_min ? 2 : (len >= (uint32_t)a.pull_warp_min && q.vpw > 1u) ? 1 : 0;
-    if (SB > 1 && have && xc.any()) {  // ... and its p piece, which only a unit popped by the previous sweep touches
-        const double *pp = a.p + (size_t)w * (size_t)a.Sr + s0;
-        pl_prefetch_l2(pp); pl_prefetch_l2(pp + 4);
-    }
+    if (SB > 1 && have && xc.any())  // ... and its piece of the popped-amount sums, which only a unit popped by the previous sweep touches
+        pl_prefetch_l2(a.pacc + (size_t)w * (size_t)a.Sr + s0);
     if (tier == 0 && have && len) pull_walk<SB>(a, xcur, base, head, mask, 0u, len, 1u, s0, acc, t.nz);
     // lists of warp_min or more entries: the whole warp walks them, one after the other
     unsigned m1 = __ballot_sync(kFull, tier == 1 && g == 0 && w < V);
@@ -621,6 +635,35 @@ __device__ __noinline__ void pull_sweep_out(const PushArgs &a, PushSmem &sm, Pus
                                             unsigned int *cnt_out, unsigned long long *edges_out, unsigned long long &gath, uint32_t sweep_index) {
     pull_sweep<SB, ACCEL>(a, sm, c, phase, xcur, xnext, cnt_out, edges_out, gath, sweep_index);
 }
+
+// ---- end of an episode: p += alpha * (sum of the amounts the episode popped), sums back to zero (several sources) ------
+template <int SB>
+__device__ __noinline__ void pull_fold(const PushArgs &a, PushCtrl *c) {
+    const PullGeom q = pull_geom<SB>(a);
+    const uint32_t V = (uint32_t)a.V;
+    const uint32_t n0 = __ldcg(&c->ntiles_b[0]), n1 = __ldcg(&c->ntiles_b[1]), ntiles = n0 + n1 + __ldcg(&c->ntiles_b[2]);
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint32_t tile = pull_tile_at<SB>(a, t, n0, n1);
+        const uint32_t cg = tile / q.tpc;
+        const uint32_t w = (tile - cg * q.tpc) * q.vpt + (threadIdx.x >> q.gs), g = threadIdx.x & (q.G - 1u);
+        const uint32_t s0 = (cg * q.G + g) * SB;
+        if (!(w < V && s0 < (uint32_t)a.Sr)) continue;
+        const size_t row = (size_t)w * (size_t)a.Sr + s0;
+#pragma unroll
+        for (int j = 0; j < SB; j += 4) {
+            const float4 v4 = *reinterpret_cast<const float4 *>(a.pacc + row + j);
+            if (v4.x == 0.f && v4.y == 0.f && v4.z == 0.f && v4.w == 0.f) continue;
+            double2 p0 = *reinterpret_cast<double2 *>(a.p + row + j), p1 = *reinterpret_cast<double2 *>(a.p + row + j + 2);
+            p0.x += a.alpha * (double)v4.x; p0.y += a.alpha * (double)v4.y;
+            p1.x += a.alpha * (double)v4.z; p1.y += a.alpha * (double)v4.w;
+            *reinterpret_cast<double2 *>(a.p + row + j) = p0;
+            *reinterpret_cast<double2 *>(a.p + row + j + 2) = p1;
+            *reinterpret_cast<float4 *>(a.pacc + row + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+template <>
+__device__ __noinline__ void pull_fold<1>(const PushArgs &, PushCtrl *) {}  // (one source updates p in every sweep)
 
 // ---- leaving dense mode ----------------------------------------------------------------------------------------------
 // the non-zero entries of x are pops that were decided but not performed: give them back to r; those (source, vertex)
@@ -769,6 +812,7 @@ __device__ __forceinline__ bool dense_body(const PushArgs &a, PushSmem &sm, Push
         c->walk_pairs += (unsigned long long)k * __ldcg(&c->ep_pairs);
         c->units += (unsigned long long)k * __ldcg(&c->ep_units);
     }
+    if (SB > 1 && k > 0) pull_fold<SB>(a, c);  // (p, pacc: nothing the compaction below reads or writes)
     if (__ldcg(&c->dcnt[k % 3]) != 0)
         pull_compact<SB>(a, sm, c, phase, a.x[cur], a.q[(it + 1) & 1], &c->cnt[(it + 1) % 3]);
     return grid_barrier(c, gen, sm);

@@ -112,6 +112,8 @@ struct PushArgs {
     const int32_t *outdeg;
     double *p;
     double *r;
+    float *pacc;                 // (kernels that can switch, several sources) per pair: sum of the amounts the running sweep episode
+                                 // has popped so far; folded into p when the episode ends, zero otherwise (pull.cuh, pull_fold)
     int32_t *status;
     int64_t Sr;                  // row stride of p / r / status / x: these arrays are VERTEX-major, [V][Sr], Sr = 1 or S rounded up
                                  // to a multiple of 8 (padding columns stay zero): element (source s, vertex v) sits at v * Sr + s

@@ -40,7 +40,7 @@ eng.sync(); wall = time.time() - t0
 rows = [eng.stats(k + 1) for k in range(nb)]
 f = lambda n: np.array([getattr(r, n) for r in rows], dtype=np.float64)
 T, F = f("traversed_edges"), f("frontier_pops")
-alg = 24 * f("scatter_edges") + 56 * (F - f("dense_pops")) + 4 * f("dense_slots") + 2 * f("dense_pairs") + 4 * f("dense_units") + 32 * f("dense_pops")
+alg = 24 * f("scatter_edges") + 56 * (F - f("dense_pops")) + 4 * f("dense_slots") + 2 * f("dense_pairs") + 4 * f("dense_units") + (32 if len(srcs) == 1 else 24) * f("dense_pops")
 out = dict(config=a.config, sources=len(srcs), rank_offset=a.rank_offset, variant=a.variant, tuning=tuning, V=cfg.V, W=wl.W, B=wl.B, batches=nb,
            gen_s=round(tgen, 2), init_window_s=round(tinit, 2), initial_solve_ms=s0.ms_push, initial_iterations=int(s0.iterations),
            error_flags=int(max(r.error_flags for r in rows)), wall_ms_per_batch=wall * 1e3 / nb,
