@@ -417,6 +417,14 @@ def main():
                              "and is NOT the roofline figure" if dense else
                              "scatter iterations only: 24 B per traversed in-edge + 56 B per pop; L2-resident working set: bound by dependent "
                              "L2 round trips and FP64 atomics, not DRAM (DESIGN.md 3.3)")}
+        if not dense:
+            # scatter levels are one returning FP64 atomic per traversed in-edge: measured ceiling on random L2-resident
+            # addresses 117 / ns (profiles/micro_fp64_atomics_r01.txt) -- the bound that applies when the working set fits L2
+            try:
+                per_ns = float(T.sum()) / (push_s * 1e9)
+                roofline.update({"atomics_per_ns": per_ns, "atomic_ceiling_per_ns": 117.0, "frac_of_atomic_ceiling": per_ns / 117.0})
+            except Exception:
+                pass
         cpu = None
         if world == 1 and not a.no_cpu:
             res, sb_per_s, sample, _ = cpu_arm(cfg, job_sources, a.cpu_sources if multi else 1, a.cpu_batches, 1, a.variant, ncores)
